@@ -1,0 +1,155 @@
+/* flomat_cuda.h -- C ABI of libflomat_cuda, the B200 (sm_100a) backend for flomat's dense FP64 hot path.
+ *
+ * This is the drop-in boundary: the symbols below are what the reference's FFI binding layer
+ * (`define-cblas` / `define-lapack`, /root/reference/flomat/flomat.rkt:139-140) binds for this path, plus the
+ * device-resident tier that replaces the Racket-side per-element loops and GC `malloc` buffers.
+ * Plain C: pointers, 32-bit ints, doubles.  No torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - matrices are column-major, element (i,j) at a[i + j*lda]  (flomat.rkt:288-300), all dims 32-bit `int`
+ *   - LAPACK-style entry points take scalars by reference and report through `info`
+ *     (0 ok, >0 first exactly-zero pivot (1-based), <0 = -(index of the bad argument))
+ *   - ipiv is int32, 1-based: row i was swapped with row ipiv[i]-1  (flomat.rkt:1457-1463)
+ *   - fm_* functions return 0 on success or a negative FM_ERR_* code; fm_last_error() gives the message.
+ *     CUDA failures never abort the process and never fall back to a CPU path.
+ *   - device-tier calls are asynchronous on the library stream (fm_set_stream / default: legacy stream 0)
+ *     unless they return a scalar to the host.
+ */
+#ifndef FLOMAT_CUDA_H
+#define FLOMAT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_OK 0
+#define FM_ERR_CUDA (-1001)    /* a CUDA runtime/driver call failed (see fm_last_error) */
+#define FM_ERR_ARG (-1002)     /* invalid argument */
+#define FM_ERR_NOGPU (-1003)   /* no usable sm_100 device */
+#define FM_ERR_NOMEM (-1004)   /* device allocation failed */
+#define FM_ERR_NONFINITE (-1005) /* expm: norm is inf/NaN (the reference would not terminate, expm.rkt:209) */
+
+/* CBLAS enums as flomat.rkt:846-853 passes them */
+#define FM_COL_MAJOR 102
+#define FM_NO_TRANS 111
+#define FM_TRANS 112
+
+/* ------------------------------------------------------------------------------------------------
+ * Tier 1: compat symbols -- exact names and C signatures implied by the reference `_fun` types.
+ * Operands may be HOST or DEVICE pointers (decided per pointer with cudaPointerGetAttributes):
+ * host operands are staged through HBM inside the call, device operands run in place.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* flomat.rkt:855-875, call site :888 (always order=102) */
+void cblas_dgemm(int order, int transA, int transB, int M, int N, int K, double alpha, const double *A, int lda,
+                 const double *B, int ldb, double beta, double *C, int ldc);
+/* flomat.rkt:751-757, call sites :782 :797 :810 */
+void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY);
+/* flomat.rkt:483-488, call sites :500 and :544 (incX = 0 broadcast fill is relied upon) */
+void cblas_dcopy(int n, const double *X, int incX, double *Y, int incY);
+/* flomat.rkt:1014-1018, call sites :1026 :1029 */
+void cblas_dscal(int n, double alpha, double *X, int incX);
+/* flomat.rkt:1317-1324, call site :1340; norm in {'M','1','O','I','F','E'}; work may be NULL */
+double dlange_(const char *norm, const int *m, const int *n, const double *a, const int *lda, double *work);
+/* flomat.rkt:1505-1523, call site :1527; ipiv has min(m,n) entries (the reference allocates m) */
+void dgetrf_(const int *m, const int *n, double *a, const int *lda, int32_t *ipiv, int *info);
+/* flomat.rkt:2112-2124, call sites :2131 :2140 */
+void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *ipiv, double *b, const int *ldb,
+            int *info);
+/* flomat.rkt:1754-1768, call site :1778; work/lwork are accepted and ignored (workspace is device-side) */
+void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, double *work, const int *lwork, int *info);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tier 2: device-resident flomat buffers (replaces alloc-flomat :437, copy-flomat :516, make-flomat :538,
+ * unsafe-ref/unsafe-set! :986-1002 and the pointwise macros :2991-3146 of flomat.rkt)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* library / device */
+int fm_init(int device);                 /* idempotent; selects the device and creates the context */
+int fm_device_count(void);
+int fm_set_stream(void *cuda_stream);    /* cudaStream_t; NULL = legacy default stream */
+int fm_sync(void);                       /* wait for everything queued on the library stream */
+const char *fm_last_error(void);         /* thread-local, never NULL */
+const char *fm_version(void);
+uint64_t fm_kernel_launches(void);       /* number of kernels this library has launched so far */
+
+/* memory: alloc-flomat / free; upload & download are the explicit host sync points */
+double *fm_alloc(int m, int n);                          /* m*n doubles of HBM, lda = m; NULL on failure */
+void *fm_alloc_bytes(size_t bytes);
+int fm_free(void *dev);
+int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n);   /* H2D, strided */
+int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n); /* D2H, strided */
+int fm_get(const double *dev, size_t index, double *out);  /* unsafe-ref on a device buffer (syncs) */
+int fm_set(double *dev, size_t index, double value);       /* unsafe-set! */
+int fm_upload_i32(int32_t *dev, const int32_t *host, size_t n);
+int fm_download_i32(int32_t *host, const int32_t *dev, size_t n);
+
+/* fills and copies: make-flomat :538 (memset / dcopy incX=0), flomat-eye :2642, unsafe-matrix-copy! :502 */
+int fm_fill(double *a, int lda, int m, int n, double x);
+int fm_eye(double *a, int lda, int m, int n, int k);      /* zeros with ones on the k-th diagonal */
+int fm_copy2d(double *dst, int ldd, const double *src, int lds, int m, int n);
+
+/* pointwise macros .+ .- .* ./ (flomat.rkt:3021-3146): C := op(A|sa, B|sb); a NULL matrix pointer means
+ * "use the scalar".  op: 0 add, 1 sub, 2 mul, 3 div.  C may alias A or B (the `!` forms). */
+int fm_ewise(int op, int m, int n, const double *a, int lda, double sa, const double *b, int ldb, double sb, double *c,
+             int ldc);
+/* constant*flomat+flomat! (flomat.rkt:805): B := alpha*A + B for a whole matrix (replaces n daxpy calls) */
+int fm_axpy2d(int m, int n, double alpha, const double *a, int lda, double *b, int ldb);
+/* constant*matrix! (flomat.rkt:1020): A := s*A */
+int fm_scal2d(int m, int n, double s, double *a, int lda);
+/* fused expm helper: num := E + O, den := E - O in one pass (expm.rkt:197-198) */
+int fm_addsub(int m, int n, const double *e, int lde, const double *o, int ldo, double *num, int ldn, double *den,
+              int ldd);
+
+/* flomat-norm (flomat.rkt:1328): type '1' 'I' 'F' 'M'; result to host (syncs) */
+int fm_norm(char type, int m, int n, const double *a, int lda, double *out);
+
+/* C := alpha*op(A)*op(B) + beta*C, all pointers device (flomat.rkt:877-896).  beta == 0 never reads C. */
+int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double *a, int lda, const double *b,
+             int ldb, double beta, double *c, int ldc);
+/* as fm_dgemm (NN only) and then adds diag to C[i,i]: the `(plus (.* c I) (times A P))` step of mpoly, expm.rkt:176 */
+int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
+                  double *c, int ldc, double diag);
+/* batched NN gemm over `batch` equally strided items (strides in doubles) */
+int fm_dgemm_batched(int m, int n, int k, double alpha, const double *a, int lda, long long stride_a, const double *b,
+                     int ldb, long long stride_b, double beta, double *c, int ldc, long long stride_c, double diag,
+                     int batch);
+
+/* LU family, device pointers (a, b, ipiv, info all in HBM; info is one int32 per matrix) */
+int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info);
+int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb);
+int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int ldb, int32_t *info);
+int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info); /* a := inv from its LU */
+/* flomat-determinant-from-plu (flomat.rkt:1837): sign(ipiv) * left-to-right product of diag(LU); syncs */
+int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out);
+
+/* expm (expm.rkt:203): out := exp(A) by Pade [8/8] scaling-and-squaring, everything on device.
+ * *s_out receives the scaling exponent 1+ceil(log2 ||A||_1) the reference computes (may be <= 0).
+ * mode 0: reference Horner order (7+s products after dropping the two products with 0 and c*I);
+ * mode 1: minimum-product regrouping (5+s products). */
+int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
+/* batch of equally strided n x n matrices; s_out (host, `batch` doubles) may be NULL */
+int fm_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,
+                    int batch, int mode, double *s_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tier 3: multi-GPU (one process per GPU).  Column-sharded times: every rank holds all of A and the
+ * column block [j0, j0+nloc) of B, and C is reassembled on every rank.  With peer pointers the GEMM
+ * epilogue itself writes each finished C tile into every peer's copy of C over NVLink (no separate
+ * all-gather); without them the caller all-gathers with NCCL.
+ * ---------------------------------------------------------------------------------------------- */
+#define FM_IPC_HANDLE_BYTES 64
+int fm_ipc_export(void *dev, void *handle_out /* FM_IPC_HANDLE_BYTES */, size_t *offset_out);
+int fm_ipc_open(const void *handle, size_t offset, void **dev_out);
+int fm_ipc_close(void *dev);
+/* C[:, j0:j0+nloc] := A * Bloc, stored to the local C and to every peer_c[r] (r < npeers, may be 0) */
+int fm_dgemm_colshard(int m, int nloc, int k, const double *a, int lda, const double *bloc, int ldb, double *c, int ldc,
+                      int j0, double *const *peer_c, int npeers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOMAT_CUDA_H */

@@ -1,0 +1,577 @@
+// api.cu -- the C ABI of libflomat_cuda (include/flomat_cuda.h): context, memory, host<->device sync points and the
+// compat tier that carries the exact symbol names/signatures flomat.rkt binds (cblas_dgemm :855, cblas_daxpy :751,
+// cblas_dcopy :483, cblas_dscal :1014, dlange_ :1317, dgetrf_ :1505, dgesv_ :2112, dgetri_ :1754).
+// Host operands of the compat tier are staged through HBM inside the call; device operands run in place.
+// Nothing here computes on the CPU: every arithmetic result comes from a kernel in this library.
+#include "common.cuh"
+#include <cstdlib>
+#include <vector>
+#include <utility>
+#include <cmath>
+
+namespace fm {
+
+static thread_local char g_err[512] = "";
+static Context g_ctx;
+
+Context &ctx() { return g_ctx; }
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("FLOMAT_CUDA_DEBUG")) fprintf(stderr, "[libflomat_cuda] error %d: %s\n", code, g_err);
+    return code;
+}
+
+static int init_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(FM_ERR_NOGPU, "no CUDA device available (%s); libflomat_cuda has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return set_error(FM_ERR_ARG, "fm_init: device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    FM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(FM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    FM_CUDA(cudaSetDevice(device));
+    Context &c = g_ctx;
+    if (c.ready && c.device == device) return FM_OK;
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c.scratch = nullptr;
+    c.scratch_bytes = 0;
+    FM_CUDA(cudaMalloc(&c.d_scalar, 64 * sizeof(double)));
+    FM_CUDA(cudaMallocHost(&c.h_scalar, 64 * sizeof(double)));
+    c.ready = true;
+    return FM_OK;
+}
+
+int ensure_init() {
+    if (g_ctx.ready) return FM_OK;
+    const char *dev = getenv("FLOMAT_CUDA_DEVICE");
+    return init_device(dev ? atoi(dev) : 0);
+}
+
+void *scratch(size_t bytes) {
+    Context &c = g_ctx;
+    if (bytes <= c.scratch_bytes) return c.scratch;
+    if (c.scratch) cudaFree(c.scratch);  // implicit device sync: nothing in flight still uses it
+    c.scratch = nullptr;
+    c.scratch_bytes = 0;
+    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+    if (cudaMalloc(&c.scratch, want) != cudaSuccess) {
+        cudaGetLastError();
+        set_error(FM_ERR_NOMEM, "scratch allocation of %zu bytes failed", want);
+        return nullptr;
+    }
+    c.scratch_bytes = want;
+    return c.scratch;
+}
+
+// ---- pointer classification + staging for the compat tier --------------------------------------
+static bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// A host matrix staged into HBM for the duration of one compat call.
+struct Staged {
+    double *dev = nullptr;
+    int ld = 0;
+    bool owned = false;
+    double *host = nullptr;
+    int ldh = 0, m = 0, n = 0;
+    int in(const double *p, int ldp, int rows, int cols, bool copy_in) {
+        m = rows; n = cols;
+        if (is_device_ptr(p) || rows == 0 || cols == 0) { dev = const_cast<double *>(p); ld = ldp; owned = false; return FM_OK; }
+        host = const_cast<double *>(p); ldh = ldp;
+        ld = rows + (rows & 1);  // even leading dimension keeps the TMA/128-bit paths available
+        if (ld < 2) ld = 2;
+        if (cudaMalloc(&dev, (size_t)ld * cols * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(FM_ERR_NOMEM, "staging allocation of %zu bytes failed", (size_t)ld * cols * sizeof(double));
+        }
+        owned = true;
+        if (copy_in)
+            FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ld * 8, host, (size_t)ldh * 8, (size_t)rows * 8, cols, cudaMemcpyHostToDevice, g_ctx.stream));
+        return FM_OK;
+    }
+    int out() {
+        if (!owned) return FM_OK;
+        FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ld * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+        return FM_OK;
+    }
+    ~Staged() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); cudaFree(dev); } }
+};
+
+static void report(const char *who, int rc) {
+    if (rc != FM_OK) fprintf(stderr, "[libflomat_cuda] %s failed (%d): %s\n", who, rc, g_err);
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" {
+
+// =================================== library / device ===================================
+int fm_init(int device) { return init_device(device); }
+int fm_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; } return c; }
+int fm_set_stream(void *s) { FM_TRY(ensure_init()); g_ctx.stream = static_cast<cudaStream_t>(s); return FM_OK; }
+int fm_sync(void) { FM_TRY(ensure_init()); FM_CUDA(cudaStreamSynchronize(g_ctx.stream)); return FM_OK; }
+const char *fm_last_error(void) { return g_err; }
+const char *fm_version(void) { return "libflomat_cuda 0.1 (sm_100a)"; }
+uint64_t fm_kernel_launches(void) { return g_ctx.launches; }
+
+// =================================== memory ===================================
+void *fm_alloc_bytes(size_t bytes) {
+    if (ensure_init() != FM_OK) return nullptr;
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error(FM_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+double *fm_alloc(int m, int n) {
+    if (m < 0 || n < 0) { set_error(FM_ERR_ARG, "fm_alloc: negative dimension"); return nullptr; }
+    return static_cast<double *>(fm_alloc_bytes((size_t)m * (size_t)n * sizeof(double)));
+}
+int fm_free(void *dev) {
+    if (!dev) return FM_OK;
+    FM_CUDA(cudaFree(dev));
+    return FM_OK;
+}
+int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n) {
+    FM_TRY(ensure_init());
+    if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_upload: bad dimensions");
+    if (m == 0 || n == 0) return FM_OK;
+    FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ldd * 8, host, (size_t)ldh * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, g_ctx.stream));
+    return FM_OK;
+}
+int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n) {
+    FM_TRY(ensure_init());
+    if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download: bad dimensions");
+    if (m == 0 || n == 0) return FM_OK;
+    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return FM_OK;
+}
+int fm_get(const double *dev, size_t index, double *out) {
+    FM_TRY(ensure_init());
+    FM_CUDA(cudaMemcpyAsync(out, dev + index, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return FM_OK;
+}
+int fm_set(double *dev, size_t index, double value) {
+    FM_TRY(ensure_init());
+    FM_CUDA(cudaMemcpyAsync(dev + index, &value, sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return FM_OK;
+}
+int fm_upload_i32(int32_t *dev, const int32_t *host, size_t n) {
+    FM_TRY(ensure_init());
+    FM_CUDA(cudaMemcpyAsync(dev, host, n * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    return FM_OK;
+}
+int fm_download_i32(int32_t *host, const int32_t *dev, size_t n) {
+    FM_TRY(ensure_init());
+    FM_CUDA(cudaMemcpyAsync(host, dev, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return FM_OK;
+}
+
+// =================================== elementwise ===================================
+int fm_fill(double *a, int lda, int m, int n, double x) { FM_TRY(ensure_init()); return k_fill(a, lda, m, n, x); }
+int fm_eye(double *a, int lda, int m, int n, int k) { FM_TRY(ensure_init()); return k_eye(a, lda, m, n, k); }
+int fm_copy2d(double *dst, int ldd, const double *src, int lds, int m, int n) { FM_TRY(ensure_init()); return k_copy2d(dst, ldd, src, lds, m, n); }
+int fm_ewise(int op, int m, int n, const double *a, int lda, double sa, const double *b, int ldb, double sb, double *c, int ldc) {
+    FM_TRY(ensure_init());
+    return k_ewise(op, m, n, a, lda, sa, b, ldb, sb, c, ldc);
+}
+int fm_axpy2d(int m, int n, double alpha, const double *a, int lda, double *b, int ldb) { FM_TRY(ensure_init()); return k_axpy2d(m, n, alpha, a, lda, b, ldb); }
+int fm_scal2d(int m, int n, double s, double *a, int lda) { FM_TRY(ensure_init()); return k_scal2d(m, n, s, a, lda); }
+int fm_addsub(int m, int n, const double *e, int lde, const double *o, int ldo, double *num, int ldn, double *den, int ldd) {
+    FM_TRY(ensure_init());
+    return k_addsub(m, n, e, lde, o, ldo, num, ldn, den, ldd);
+}
+
+int fm_norm(char type, int m, int n, const double *a, int lda, double *out) {
+    FM_TRY(ensure_init());
+    FM_TRY(k_norm_device(type, m, n, a, lda, g_ctx.d_scalar));
+    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    *out = g_ctx.h_scalar[0];
+    return FM_OK;
+}
+
+// =================================== gemm ===================================
+int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
+             double *c, int ldc) {
+    FM_TRY(ensure_init());
+    GemmEpilogue ep;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    return k_dgemm(transA, transB, m, n, k, a, lda, 0, b, ldb, 0, c, ldc, 0, 1, ep);
+}
+int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta, double *c, int ldc,
+                  double diag) {
+    FM_TRY(ensure_init());
+    GemmEpilogue ep;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.diag = diag;
+    ep.has_diag = true;
+    return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, 0, b, ldb, 0, c, ldc, 0, 1, ep);
+}
+int fm_dgemm_batched(int m, int n, int k, double alpha, const double *a, int lda, long long stride_a, const double *b, int ldb,
+                     long long stride_b, double beta, double *c, int ldc, long long stride_c, double diag, int batch) {
+    FM_TRY(ensure_init());
+    GemmEpilogue ep;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.diag = diag;
+    ep.has_diag = (diag != 0.0);
+    return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, stride_a, b, ldb, stride_b, c, ldc, stride_c, batch, ep);
+}
+
+// =================================== LU family ===================================
+int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info) {
+    FM_TRY(ensure_init());
+    return k_getrf(m, n, a, lda, 0, ipiv, 0, info, 1);
+}
+int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb) {
+    FM_TRY(ensure_init());
+    return k_getrs(n, nrhs, lu, lda, 0, ipiv, 0, b, ldb, 0, 1);
+}
+int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int ldb, int32_t *info) {
+    FM_TRY(ensure_init());
+    FM_TRY(k_getrf(n, n, a, lda, 0, ipiv, 0, info, 1));
+    // LAPACK skips the solve when info > 0; the triangular solves below then divide by the exact zero pivot and
+    // produce inf/NaN, which is what a caller that ignores info (flomat.rkt:2140-2142) observes either way.
+    return k_getrs(n, nrhs, a, lda, 0, ipiv, 0, b, ldb, 0, 1);
+}
+int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
+    FM_TRY(ensure_init());
+    if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "fm_getri: bad dimensions");
+    if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), g_ctx.stream));
+    if (n == 0) return FM_OK;
+    // inv(A) = solution of (P L U) X = I, computed with the same blocked triangular solves as getrs.
+    const int ldx = n + (n & 1);
+    double *x = static_cast<double *>(fm_alloc_bytes((size_t)ldx * n * sizeof(double)));
+    if (!x) return FM_ERR_NOMEM;
+    int rc = k_eye(x, ldx, n, n, 0);
+    if (rc == FM_OK) rc = k_getrs(n, n, a, lda, 0, ipiv, 0, x, ldx, 0, 1);
+    if (rc == FM_OK) rc = k_copy2d(a, lda, x, ldx, n, n);
+    cudaStreamSynchronize(g_ctx.stream);
+    cudaFree(x);
+    return rc;
+}
+int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
+    FM_TRY(ensure_init());
+    FM_TRY(k_det_device(n, lu, lda, ipiv, g_ctx.d_scalar));
+    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    *out = g_ctx.h_scalar[0];
+    return FM_OK;
+}
+
+// =================================== expm ===================================
+int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host) {
+    FM_TRY(ensure_init());
+    return k_expm(n, a, lda, out, ldo, mode, s_out, info_host);
+}
+int fm_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o, int batch, int mode,
+                    double *s_out) {
+    FM_TRY(ensure_init());
+    return k_expm_batched(n, a, lda, stride_a, out, ldo, stride_o, batch, mode, s_out);
+}
+
+// =================================== multi-GPU ===================================
+int fm_ipc_export(void *dev, void *handle_out, size_t *offset_out) {
+    FM_TRY(ensure_init());
+    static_assert(sizeof(cudaIpcMemHandle_t) == FM_IPC_HANDLE_BYTES, "ipc handle size");
+    // An IPC handle names the whole allocation; the importer needs the offset of `dev` inside it.
+    typedef int (*RangeFn)(unsigned long long *, size_t *, unsigned long long);
+    static RangeFn range = nullptr;
+    if (!range) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FM_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) return set_error(FM_ERR_CUDA, "cuMemGetAddressRange entry point not available");
+        range = reinterpret_cast<RangeFn>(p);
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int r = range(&base, &size, (unsigned long long)reinterpret_cast<uintptr_t>(dev));
+    if (r != 0) return set_error(FM_ERR_CUDA, "cuMemGetAddressRange failed with CUresult %d", r);
+    cudaIpcMemHandle_t h;
+    FM_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(static_cast<uintptr_t>(base))));
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = static_cast<size_t>(reinterpret_cast<uintptr_t>(dev) - static_cast<uintptr_t>(base));
+    return FM_OK;
+}
+static std::vector<std::pair<void *, void *>> g_ipc_open;  // (pointer handed out, mapping base)
+int fm_ipc_open(const void *handle, size_t offset, void **dev_out) {
+    FM_TRY(ensure_init());
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *base = nullptr;
+    FM_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_out = static_cast<char *>(base) + offset;
+    g_ipc_open.emplace_back(*dev_out, base);
+    return FM_OK;
+}
+int fm_ipc_close(void *dev) {
+    for (size_t i = 0; i < g_ipc_open.size(); ++i)
+        if (g_ipc_open[i].first == dev) {
+            void *base = g_ipc_open[i].second;
+            g_ipc_open.erase(g_ipc_open.begin() + i);
+            FM_CUDA(cudaIpcCloseMemHandle(base));
+            return FM_OK;
+        }
+    return set_error(FM_ERR_ARG, "fm_ipc_close: pointer was not returned by fm_ipc_open");
+}
+int fm_dgemm_colshard(int m, int nloc, int k, const double *a, int lda, const double *bloc, int ldb, double *c, int ldc, int j0,
+                      double *const *peer_c, int npeers) {
+    FM_TRY(ensure_init());
+    if (npeers < 0 || npeers > 7) return set_error(FM_ERR_ARG, "fm_dgemm_colshard: npeers must be 0..7");
+    GemmEpilogue ep;
+    ep.alpha = 1.0;
+    ep.beta = 0.0;
+    double *shifted[7];
+    for (int r = 0; r < npeers; ++r) shifted[r] = peer_c[r] + (size_t)j0 * ldc;
+    ep.peers = shifted;
+    ep.npeers = npeers;
+    return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, nloc, k, a, lda, 0, bloc, ldb, 0, c + (size_t)j0 * ldc, ldc, 0, 1, ep);
+}
+
+// =================================== compat tier ===================================
+void cblas_dgemm(int order, int transA, int transB, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                 double beta, double *C, int ldc) {
+    int rc = ensure_init();
+    if (rc == FM_OK && order != FM_COL_MAJOR) rc = set_error(FM_ERR_ARG, "cblas_dgemm: only CblasColMajor (102) is supported, as flomat.rkt:888 passes");
+    if (rc == FM_OK) {
+        const bool ta = transA == FM_TRANS, tb = transB == FM_TRANS;
+        Staged a, b, c;
+        rc = a.in(A, lda, ta ? K : M, ta ? M : K, true);
+        if (rc == FM_OK) rc = b.in(B, ldb, tb ? N : K, tb ? K : N, true);
+        if (rc == FM_OK) rc = c.in(C, ldc, M, N, beta != 0.0);
+        if (rc == FM_OK) {
+            GemmEpilogue ep;
+            ep.alpha = alpha;
+            ep.beta = beta;
+            rc = k_dgemm(transA, transB, M, N, K, a.dev, a.ld, 0, b.dev, b.ld, 0, c.dev, c.ld, 0, 1, ep);
+        }
+        if (rc == FM_OK) rc = c.out();
+        if (rc == FM_OK && c.owned && cudaStreamSynchronize(g_ctx.stream) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "cblas_dgemm: sync failed");
+    }
+    report("cblas_dgemm", rc);
+}
+
+// vectors: stage n elements with their stride collapsed to 1
+struct StagedVec {
+    double *dev = nullptr;
+    long long inc = 1;
+    bool owned = false;
+    double *host = nullptr;
+    int n = 0, inch = 1;
+    std::vector<double> pack;
+    int in(const double *p, int incp, int count, bool copy_in) {
+        n = count;
+        if (is_device_ptr(p) || count <= 0) { dev = const_cast<double *>(p); inc = incp; return FM_OK; }
+        host = const_cast<double *>(p); inch = incp;
+        const int len = (incp == 0) ? 1 : count;
+        if (cudaMalloc(&dev, (size_t)(len < 2 ? 2 : len) * 8) != cudaSuccess) { cudaGetLastError(); return set_error(FM_ERR_NOMEM, "staging allocation failed"); }
+        owned = true;
+        inc = (incp == 0) ? 0 : 1;
+        if (copy_in) {
+            const long long ainc = incp < 0 ? -(long long)incp : incp;
+            const double *start = host;  // BLAS: negative inc walks backwards from (1-n)*inc
+            if (ainc <= 1) {
+                FM_CUDA(cudaMemcpyAsync(dev, start, (size_t)len * 8, cudaMemcpyHostToDevice, g_ctx.stream));
+            } else {
+                FM_CUDA(cudaMemcpy2DAsync(dev, 8, start, (size_t)ainc * 8, 8, len, cudaMemcpyHostToDevice, g_ctx.stream));
+            }
+        }
+        return FM_OK;
+    }
+    int out() {
+        if (!owned) return FM_OK;
+        const long long ainc = inch < 0 ? -(long long)inch : inch;
+        if (ainc <= 1) FM_CUDA(cudaMemcpyAsync(host, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+        else FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ainc * 8, dev, 8, 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+        FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        return FM_OK;
+    }
+    ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); cudaFree(dev); } }
+};
+
+void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY) {
+    if (n <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK && (incX < 0 || incY < 0)) rc = set_error(FM_ERR_ARG, "cblas_daxpy: negative increments are not used by flomat and not supported");
+    if (rc == FM_OK) {
+        StagedVec x, y;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = y.in(Y, incY, n, true);
+        if (rc == FM_OK) rc = k_axpy_strided(n, alpha, x.dev, x.inc, y.dev, y.inc);
+        if (rc == FM_OK) rc = y.out();
+    }
+    report("cblas_daxpy", rc);
+}
+void cblas_dcopy(int n, const double *X, int incX, double *Y, int incY) {
+    if (n <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK && (incX < 0 || incY < 0)) rc = set_error(FM_ERR_ARG, "cblas_dcopy: negative increments are not used by flomat and not supported");
+    if (rc == FM_OK) {
+        StagedVec x, y;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = y.in(Y, incY, n, incY > 1);  // strided host Y: keep the gaps' contents
+        if (rc == FM_OK) rc = k_copy_strided(n, x.dev, x.inc, y.dev, y.inc);
+        if (rc == FM_OK) rc = y.out();
+    }
+    report("cblas_dcopy", rc);
+}
+void cblas_dscal(int n, double alpha, double *X, int incX) {
+    if (n <= 0 || incX <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        StagedVec x;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = k_scal_strided(n, alpha, x.dev, x.inc);
+        if (rc == FM_OK) rc = x.out();
+    }
+    report("cblas_dscal", rc);
+}
+
+double dlange_(const char *norm, const int *m, const int *n, const double *a, const int *lda, double *work) {
+    (void)work;  // the row-sum workspace lives in HBM
+    int rc = ensure_init();
+    double out = 0.0;
+    if (rc == FM_OK) {
+        Staged A;
+        rc = A.in(a, *lda, *m, *n, true);
+        if (rc == FM_OK) rc = fm_norm(norm[0], *m, *n, A.dev, A.ld, &out);
+    }
+    report("dlange_", rc);
+    return rc == FM_OK ? out : nan("");
+}
+
+static int lapack_arg_check_getrf(int m, int n, int lda) {
+    if (m < 0) return -1;
+    if (n < 0) return -2;
+    if (lda < (m > 1 ? m : 1)) return -4;
+    return 0;
+}
+
+void dgetrf_(const int *m, const int *n, double *a, const int *lda, int32_t *ipiv, int *info) {
+    *info = lapack_arg_check_getrf(*m, *n, *lda);
+    if (*info != 0 || *m == 0 || *n == 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        const int mn = *m < *n ? *m : *n;
+        Staged A;
+        rc = A.in(a, *lda, *m, *n, true);
+        int32_t *d_ipiv = nullptr, *d_info = nullptr;
+        const bool ipiv_dev = is_device_ptr(ipiv);
+        if (rc == FM_OK) {
+            d_ipiv = ipiv_dev ? ipiv : static_cast<int32_t *>(fm_alloc_bytes((size_t)mn * 4 + 16));
+            if (!d_ipiv) rc = FM_ERR_NOMEM;
+            else d_info = ipiv_dev ? static_cast<int32_t *>(fm_alloc_bytes(16)) : d_ipiv + mn;
+            if (rc == FM_OK && !d_info) rc = FM_ERR_NOMEM;
+        }
+        if (rc == FM_OK) rc = k_getrf(*m, *n, A.dev, A.ld, 0, d_ipiv, 0, d_info, 1);
+        if (rc == FM_OK) rc = A.out();
+        int32_t hinfo = 0;
+        if (rc == FM_OK) rc = fm_download_i32(&hinfo, d_info, 1);
+        if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)mn);
+        if (rc == FM_OK) *info = hinfo;
+        if (ipiv_dev) { if (d_info) cudaFree(d_info); } else if (d_ipiv) cudaFree(d_ipiv);
+    }
+    report("dgetrf_", rc);
+    if (rc != FM_OK) *info = rc;
+}
+
+void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *ipiv, double *b, const int *ldb, int *info) {
+    *info = 0;
+    if (*n < 0) *info = -1;
+    else if (*nrhs < 0) *info = -2;
+    else if (*lda < (*n > 1 ? *n : 1)) *info = -4;
+    else if (*ldb < (*n > 1 ? *n : 1)) *info = -7;
+    if (*info != 0 || *n == 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        Staged A, B;
+        rc = A.in(a, *lda, *n, *n, true);
+        if (rc == FM_OK) rc = B.in(b, *ldb, *n, *nrhs, true);
+        const bool ipiv_dev = is_device_ptr(ipiv);
+        int32_t *d_ipiv = nullptr, *d_info = nullptr;
+        if (rc == FM_OK) {
+            d_ipiv = ipiv_dev ? ipiv : static_cast<int32_t *>(fm_alloc_bytes((size_t)*n * 4 + 16));
+            if (!d_ipiv) rc = FM_ERR_NOMEM;
+            else d_info = ipiv_dev ? static_cast<int32_t *>(fm_alloc_bytes(16)) : d_ipiv + *n;
+            if (rc == FM_OK && !d_info) rc = FM_ERR_NOMEM;
+        }
+        if (rc == FM_OK) rc = k_getrf(*n, *n, A.dev, A.ld, 0, d_ipiv, 0, d_info, 1);
+        int32_t hinfo = 0;
+        if (rc == FM_OK) rc = fm_download_i32(&hinfo, d_info, 1);
+        // LAPACK dgesv: solve only when the factorisation succeeded (info == 0); B is left untouched otherwise
+        if (rc == FM_OK && hinfo == 0 && *nrhs > 0) rc = k_getrs(*n, *nrhs, A.dev, A.ld, 0, d_ipiv, 0, B.dev, B.ld, 0, 1);
+        if (rc == FM_OK) rc = A.out();
+        if (rc == FM_OK && hinfo == 0) rc = B.out();
+        if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)*n);
+        if (rc == FM_OK) { cudaStreamSynchronize(g_ctx.stream); *info = hinfo; }
+        if (ipiv_dev) { if (d_info) cudaFree(d_info); } else if (d_ipiv) cudaFree(d_ipiv);
+    }
+    report("dgesv_", rc);
+    if (rc != FM_OK) *info = rc;
+}
+
+void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, double *work, const int *lwork, int *info) {
+    (void)work;
+    *info = 0;
+    if (*n < 0) *info = -1;
+    else if (*lda < (*n > 1 ? *n : 1)) *info = -3;
+    if (*info != 0 || *n == 0) return;
+    if (lwork && *lwork == -1) { if (work && !is_device_ptr(work)) work[0] = (double)*n; return; }  // workspace query
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        Staged A;
+        rc = A.in(a, *lda, *n, *n, true);
+        const bool ipiv_dev = is_device_ptr(ipiv);
+        int32_t *d_ipiv = const_cast<int32_t *>(ipiv);
+        if (rc == FM_OK && !ipiv_dev) {
+            d_ipiv = static_cast<int32_t *>(fm_alloc_bytes((size_t)*n * 4));
+            if (!d_ipiv) rc = FM_ERR_NOMEM;
+            else rc = fm_upload_i32(d_ipiv, ipiv, (size_t)*n);
+        }
+        // LAPACK dgetri: info = i if U(i,i) is exactly zero (singular), checked before any work
+        if (rc == FM_OK) {
+            double d = 1.0;
+            rc = fm_det(*n, A.dev, A.ld, d_ipiv, &d);  // product of the diagonal: exact zero iff some U(i,i) == 0
+            if (rc == FM_OK && d == 0.0) {
+                std::vector<double> diag((size_t)*n);
+                cudaMemcpy2D(diag.data(), 8, A.dev, ((size_t)A.ld + 1) * 8, 8, *n, cudaMemcpyDeviceToHost);
+                for (int i = 0; i < *n; ++i)
+                    if (diag[i] == 0.0) { *info = i + 1; break; }
+            }
+        }
+        if (rc == FM_OK && *info == 0) rc = fm_getri(*n, A.dev, A.ld, d_ipiv, nullptr);
+        if (rc == FM_OK && *info == 0) rc = A.out();
+        if (rc == FM_OK) cudaStreamSynchronize(g_ctx.stream);
+        if (!ipiv_dev && d_ipiv) cudaFree(d_ipiv);
+    }
+    report("dgetri_", rc);
+    if (rc != FM_OK) *info = rc;
+}
+
+}  // extern "C"

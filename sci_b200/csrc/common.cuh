@@ -1,0 +1,103 @@
+// common.cuh -- shared context, error plumbing and small device helpers for libflomat_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/flomat_cuda.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libflomat_cuda is written for sm_100a (B200) only"
+#endif
+
+namespace fm {
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;      // library stream (legacy default unless fm_set_stream)
+    unsigned long long launches = 0;    // kernels launched by this library
+    // scratch that lives for the life of the library (grown on demand, never shrunk)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double *d_scalar = nullptr;         // 64 doubles of device scratch for reductions
+    double *h_scalar = nullptr;         // pinned mirror
+    int max_smem_optin = 0;
+};
+
+Context &ctx();
+int set_error(int code, const char *fmt, ...);
+int ensure_init();
+void *scratch(size_t bytes);  // returns nullptr + sets error on failure
+
+inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
+
+#define FM_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fm::set_error(FM_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                                 cudaGetErrorString(e__));                                              \
+    } while (0)
+
+#define FM_LAUNCH_CHECK()                                                                               \
+    do {                                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                           \
+        if (e__ != cudaSuccess)                                                                         \
+            return fm::set_error(FM_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__,  \
+                                 cudaGetErrorString(e__));                                              \
+        fm::count_launch();                                                                             \
+    } while (0)
+
+#define FM_TRY(expr)                  \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != FM_OK) return rc__; \
+    } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace fm
+
+// ---- kernels' host entry points (device pointers, library stream) ------------------------------
+namespace fm {
+// ewise.cu
+int k_fill(double *a, int lda, int m, int n, double x);
+int k_eye(double *a, int lda, int m, int n, int k);
+int k_copy2d(double *dst, int ldd, const double *src, int lds, int m, int n);
+int k_ewise(int op, int m, int n, const double *a, int lda, double sa, const double *b, int ldb, double sb, double *c, int ldc);
+int k_axpy2d(int m, int n, double alpha, const double *a, int lda, double *b, int ldb);
+int k_scal2d(int m, int n, double s, double *a, int lda);
+int k_addsub(int m, int n, const double *e, int lde, const double *o, int ldo, double *num, int ldn, double *den, int ldd);
+int k_axpy_strided(int n, double alpha, const double *x, long long incx, double *y, long long incy);
+int k_copy_strided(int n, const double *x, long long incx, double *y, long long incy);
+int k_scal_strided(int n, double alpha, double *x, long long incx);
+int k_lincomb(int m, int n, double ci, double c1, const double *a1, int ld1, double c2, const double *a2, int ld2, double *out, int ldo,
+              long long s1, long long s2, long long so, int batch);
+int k_div_pow2_batched(int n, const double *a, int lda, long long sa, double *x, int ldx, long long sx, const double *scale_dev, int batch);
+// norm.cu
+int k_norm_device(char type, int m, int n, const double *a, int lda, double *d_out);  // result stays on device
+int k_norm1_batched(int n, const double *a, int lda, long long stride, int batch, double *d_out);
+// dgemm.cu
+struct GemmEpilogue {
+    double alpha = 1.0, beta = 0.0;
+    double diag = 0.0;          // added to C[i,i] after alpha/beta (fused `+ c*I`)
+    bool has_diag = false;
+    double *const *peers = nullptr;  // host array of peer C base pointers (column-shard P2P epilogue)
+    int npeers = 0;
+    const int32_t *active_until = nullptr;  // batched: item z is skipped when round >= active_until[z]
+    int round = 0;
+};
+int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,
+            double *c, int ldc, long long sc, int batch, const GemmEpilogue &ep);
+// lu.cu
+int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
+int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
+int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);
+// expm.cu
+int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
+int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out);
+}  // namespace fm

@@ -1,0 +1,455 @@
+// dgemm.cu -- C := alpha*op(A)*op(B) + beta*C (+ diag*I), FP64, column-major: the kernel behind `times`
+// (flomat.rkt:3202 -> flomat* :905 -> cblas_dgemm :888), every product inside expm (expm.rkt:167-210) and
+// the trailing updates of the blocked LU.
+//
+// B200 design (sm_100a).  tcgen05/UMMA has no f64 kind, so FP64 tensor math is the warp-level DMMA
+// (`mma.sync.aligned.m8n8k4.f64` -> SASS DMMA.8x8x4), whose measured issue peak on B200 is 37.0 TFLOP/s
+// (tools/peak_fp64.cu) -- that is the roofline denominator of this kernel.
+//
+//   * persistent kernel, one CTA per SM, static round-robin over 128x128 output tiles, tiles rasterised in
+//     bands of 16 tile-rows so that the 148 concurrently running tiles share A/B panels through the 126 MB L2;
+//   * warp-specialised: warp 8 is the TMA producer (one elected lane), warps 0-7 are DMMA consumers with
+//     64x32 warp tiles (64 accumulator doubles per thread, all in registers);
+//   * operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a ring of STAGES smem buffers
+//     guarded by full/empty mbarriers; A (MN-major in memory) arrives as 16-row boxes, B (K-major) as one box;
+//   * fragment loads are conflict-free LDS.128: the m8n8k4 row/column/k indices are permuted (see a_offsets /
+//     b_offsets) so every thread reads 16-byte pairs and the 128B swizzle spreads a quarter-warp over all banks;
+//   * epilogue applies alpha/beta/diag from registers and writes 16-byte pairs straight to C (and, for the
+//     column-sharded multi-GPU product, to every peer GPU's C over NVLink -- the all-gather is fused here).
+//
+// Operands that TMA cannot describe (odd lda, 8-byte-aligned views, transposed A/B) take dgemm_generic_kernel,
+// a plain smem-tiled DMMA kernel: same arithmetic, no fast path.  There is no CPU or library fallback.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace fm {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct EpiParams {
+    double alpha, beta, diag;
+    int has_diag;
+    int npeers;
+    double *peer[7];
+    const int32_t *active_until;  // optional per-item round limit (batched squaring in expm)
+    int round;
+};
+
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
+    constexpr int G = 16;  // band height in tiles
+    const int per = tiles_m * tiles_n;
+    z = tile / per;
+    const int r = tile - z * per;
+    const int band = r / (G * tiles_n);
+    const int rr = r - band * (G * tiles_n);
+    const int gsz = min(G, tiles_m - band * G);
+    tn = rr / gsz;
+    tm = band * G + (rr - tn * gsz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA + DMMA persistent kernel (NN)
+// ---------------------------------------------------------------------------------------------
+template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
+    static constexpr int NW = WGM * WGN;            // consumer warps
+    // Registers are allocated to a CTA in units of 4 warps, so the producer gets a whole warpgroup (3 of its warps exit
+    // at once) and hands its registers to the consumers with setmaxnreg, the canonical warp-specialised layout.
+    static constexpr int THREADS = (NW + 4) * 32;
+    static constexpr int REG_PRODUCER = 40, REG_CONSUMER = 232;  // 384 threads: 128*40 + 256*232 <= 65536
+    static constexpr int WTM = BM / WGM, WTN = BN / WGN;
+    static constexpr int MT = WTM / 8, NT = WTN / 8;  // m8n8 tiles per warp
+    static constexpr int R = WTM / 16;                // 16-byte A loads per thread per k
+    static constexpr int GPB = 8 / R;                 // fragment row-groups (g) per 16-row box
+    static constexpr int A_BOX_BYTES = BK * 128;      // one box: BK rows (k) x 16 doubles (m)
+    static constexpr int A_STAGE = (BM / 16) * A_BOX_BYTES;
+    static constexpr int B_BOX_BYTES = BN * 128;      // one box: BN rows (n) x 16 doubles (k)
+    static constexpr int B_STAGE = (BK / 16) * B_BOX_BYTES;
+    static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+    static_assert(BK % 16 == 0 && WTM % 16 == 0 && WTN % 8 == 0 && R >= 1 && R <= 4, "tile shape");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double *__restrict__ C,
+                 long long ldc, long long sc, int M, int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams ep,
+                 int vec_ok) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, NW = Cfg::NW, STAGES = Cfg::STAGES;
+    constexpr int MT = Cfg::MT, NT = Cfg::NT, R = Cfg::R, GPB = Cfg::GPB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // full[s] then empty[s]
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int KT = (K + BK - 1) / BK;
+
+    if (warp >= NW) {
+        // ===================== TMA producer warpgroup =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REG_PRODUCER));
+        if (warp == NW && lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int tm, tn, z;
+                decode_tile(tile, tiles_m, tiles_n, tm, tn, z);
+                if (ep.active_until && ep.round >= ep.active_until[z]) continue;
+                const int m0 = tm * BM, n0 = tn * BN;
+                for (int kt = 0; kt < KT; ++kt) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t fb = full_bar(stage);
+                    mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_STAGE;
+#pragma unroll
+                    for (int b = 0; b < BM / 16; ++b) tma_load_3d(sa + b * Cfg::A_BOX_BYTES, &tmA, m0 + 16 * b, kt * BK, z, fb);
+#pragma unroll
+                    for (int kb = 0; kb < BK / 16; ++kb) tma_load_3d(sb + kb * Cfg::B_BOX_BYTES, &tmB, kt * BK + 16 * kb, n0, z, fb);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== DMMA consumers =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REG_CONSUMER));
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % Cfg::WGM, wn = warp / Cfg::WGM;
+    const int wm0 = wm * Cfg::WTM, wn0 = wn * Cfg::WTN;
+    // A fragment rows: thread-group g owns, inside 16-row box (g / GPB), the 16-byte chunks c*GPB + g%GPB (c < R):
+    // local rows 16*(g/GPB) + 2*(c*GPB + g%GPB) + {0,1}  -> m-tiles 2c, 2c+1.  k index for MMA j: 2t + (j&1) + 8*(j>>1).
+    const int a_box = (wm0 >> 4) + g / GPB;
+    const int a_chunk0 = g % GPB;
+    uint32_t a_off[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int kr = 2 * t + e;  // row inside the box for j = e (j = e + 2 adds 8 rows = 1024 B)
+        a_off[e] = a_box * Cfg::A_BOX_BYTES + kr * 128 + ((a_chunk0 ^ kr) << 4);
+    }
+    // B fragment columns: n-tile ni column  wn0 + 8*ni + perm(g), perm(g) = 4*(g&1) + (g>>1); k pairs: chunk t and t+4.
+    const int permg = ((g & 1) << 2) | (g >> 1);
+    const uint32_t b_off = (wn0 + permg) * 128 + ((t ^ permg) << 4);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tm, tn, z;
+        decode_tile(tile, tiles_m, tiles_n, tm, tn, z);
+        if (ep.active_until && ep.round >= ep.active_until[z]) continue;
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_wait(full_bar(stage), phase);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sb = sa + Cfg::A_STAGE;
+#pragma unroll
+            for (int kb = 0; kb < BK / 16; ++kb) {
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    double bf[NT][2];
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni)
+                        lds128((sb + kb * Cfg::B_BOX_BYTES + b_off + ni * 1024) ^ (jp << 6), bf[ni][0], bf[ni][1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double af[MT];
+#pragma unroll
+                        for (int c = 0; c < R; ++c)
+                            lds128((sa + a_off[e] + kb * 2048 + jp * 1024) ^ ((c * GPB) << 4), af[2 * c], af[2 * c + 1]);
+#pragma unroll
+                        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < NT; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni][e]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+
+        // ---------------- epilogue: registers -> global ----------------
+        const int m_base = tm * BM + wm0 + 16 * (g / GPB) + 2 * a_chunk0;
+        const int n_base = tn * BN + wn0;
+        double *Cz = C + z * sc;
+        const long long zoff = z * sc;
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int n = n_base + 8 * ni + (x ? 4 + t : t);
+                if (n >= N) continue;
+#pragma unroll
+                for (int c = 0; c < R; ++c) {
+                    const int m = m_base + 2 * c * GPB;
+                    if (m >= M) continue;
+                    double v0 = ep.alpha * acc[2 * c][ni][x];
+                    double v1 = ep.alpha * acc[2 * c + 1][ni][x];
+                    double *p = Cz + (long long)n * ldc + m;
+                    const bool pair = vec_ok && (m + 1 < M);
+                    if (ep.beta != 0.0) {
+                        if (pair) {
+                            const double2 o = *reinterpret_cast<const double2 *>(p);
+                            v0 += ep.beta * o.x;
+                            v1 += ep.beta * o.y;
+                        } else {
+                            v0 += ep.beta * p[0];
+                            if (m + 1 < M) v1 += ep.beta * p[1];
+                        }
+                    }
+                    if (ep.has_diag) {
+                        if (m == n) v0 += ep.diag;
+                        if (m + 1 == n) v1 += ep.diag;
+                    }
+                    if (pair) {
+                        *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+#pragma unroll
+                        for (int r = 0; r < 7; ++r)
+                            if (r < ep.npeers)
+                                *reinterpret_cast<double2 *>(ep.peer[r] + zoff + (long long)n * ldc + m) = make_double2(v0, v1);
+                    } else {
+                        p[0] = v0;
+                        if (m + 1 < M) p[1] = v1;
+#pragma unroll
+                        for (int r = 0; r < 7; ++r)
+                            if (r < ep.npeers) {
+                                double *q = ep.peer[r] + zoff + (long long)n * ldc + m;
+                                q[0] = v0;
+                                if (m + 1 < M) q[1] = v1;
+                            }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic DMMA kernel: any transposition, alignment and leading dimension; 64x64x16 tiles, 4 warps of 32x32.
+// ---------------------------------------------------------------------------------------------
+constexpr int GB = 64, GK = 16, GPAD = 4;
+
+__global__ void __launch_bounds__(128)
+dgemm_generic_kernel(int ta, int tb, int M, int N, int K, const double *__restrict__ A, long long lda, long long sa_,
+                     const double *__restrict__ B, long long ldb, long long sb_, double *C, long long ldc, long long sc, EpiParams ep) {
+    __shared__ double As[GK][GB + GPAD];  // As[k][m]
+    __shared__ double Bs[GK][GB + GPAD];  // Bs[k][n]
+    const int z = blockIdx.z;
+    if (ep.active_until && ep.round >= ep.active_until[z]) return;
+    A += z * sa_;
+    B += z * sb_;
+    C += z * sc;
+    const int m0 = blockIdx.x * GB, n0 = blockIdx.y * GB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        // cooperative loads with bounds checks; index order follows the contiguous direction of each operand
+        for (int idx = tid; idx < GB * GK; idx += 128) {
+            int mm, kk;
+            if (!ta) { mm = idx % GB; kk = idx / GB; } else { kk = idx % GK; mm = idx / GK; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            double v = 0.0;
+            if (gm < M && gk < K) v = ta ? A[(long long)gm * lda + gk] : A[(long long)gk * lda + gm];
+            As[kk][mm] = v;
+        }
+        for (int idx = tid; idx < GB * GK; idx += 128) {
+            int nn, kk;
+            if (!tb) { kk = idx % GK; nn = idx / GK; } else { nn = idx % GB; kk = idx / GB; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            double v = 0.0;
+            if (gn < N && gk < K) v = tb ? B[(long long)gk * ldb + gn] : B[(long long)gn * ldb + gk];
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < GK / 4; ++j) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) af[mi] = As[4 * j + t][wm0 + 8 * mi + g];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = Bs[4 * j + t][wn0 + 8 * ni + g];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int m = m0 + wm0 + 8 * mi + g, n = n0 + wn0 + 8 * ni + 2 * t + x;
+                if (m < M && n < N) {
+                    double *p = C + (long long)n * ldc + m;
+                    double v = ep.alpha * acc[mi][ni][x];
+                    if (ep.beta != 0.0) v += ep.beta * *p;
+                    if (ep.has_diag && m == n) v += ep.diag;
+                    *p = v;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r)
+                        if (r < ep.npeers) ep.peer[r][z * sc + (long long)n * ldc + m] = v;
+                }
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D map over a column-major (rows x cols) x batch operand: dim0 = rows (contiguous), dim1 = cols, dim2 = batch
+int make_map(CUtensorMap *map, const double *base, long long rows, long long cols, long long ld, long long stride, int batch,
+             int box_rows, int box_cols) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(FM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)cols, (cuuint64_t)batch};
+    long long s2 = batch > 1 ? stride : ld * (cols > 0 ? cols : 1);
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8ull, (cuuint64_t)s2 * 8ull};
+    cuuint32_t box[3] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FM_OK;
+}
+
+using CfgBig = GemmCfg<128, 128, 16, 2, 4, 6>;
+
+template <class Cfg>
+int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
+               long long sc, int batch, const EpiParams &ep) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FM_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    FM_TRY(make_map(&tmA, a, m, k, lda, sa, batch, 16, Cfg::BK));
+    FM_TRY(make_map(&tmB, b, k, n, ldb, sb, batch, 16, Cfg::BN));
+    const int tiles_m = ceil_div(m, Cfg::BM), tiles_n = ceil_div(n, Cfg::BN);
+    const long long total = (long long)tiles_m * tiles_n * batch;
+    if (total > 0x7fffffffLL) return set_error(FM_ERR_ARG, "dgemm: too many tiles");
+    const int grid = (int)(total < ctx().sm_count ? total : ctx().sm_count);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15u) == 0 && (ldc % 2) == 0 && (sc % 2) == 0) ? 1 : 0;
+    int vec_all = vec_ok;
+    for (int r = 0; r < ep.npeers; ++r)
+        if (reinterpret_cast<uintptr_t>(ep.peer[r]) & 15u) vec_all = 0;
+    dgemm_tma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx().stream>>>(tmA, tmB, c, ldc, sc, m, n, k, tiles_m, tiles_n,
+                                                                                  (int)total, ep, vec_all);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+}  // namespace
+
+int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,
+            double *c, int ldc, long long sc, int batch, const GemmEpilogue &epi) {
+    const bool ta = (transA == FM_TRANS), tb = (transB == FM_TRANS);
+    if ((transA != FM_TRANS && transA != FM_NO_TRANS) || (transB != FM_TRANS && transB != FM_NO_TRANS))
+        return set_error(FM_ERR_ARG, "dgemm: trans flags must be 111 or 112");
+    if (m < 0 || n < 0 || k < 0 || batch < 0) return set_error(FM_ERR_ARG, "dgemm: negative dimension");
+    const int rows_a = ta ? k : m, rows_b = tb ? n : k;
+    if (lda < (rows_a > 1 ? rows_a : 1) || ldb < (rows_b > 1 ? rows_b : 1) || ldc < (m > 1 ? m : 1))
+        return set_error(FM_ERR_ARG, "dgemm: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
+    if (epi.npeers > 7) return set_error(FM_ERR_ARG, "dgemm: at most 7 peers");
+    if (m == 0 || n == 0 || batch == 0) return FM_OK;
+    EpiParams ep;
+    ep.alpha = epi.alpha;
+    ep.beta = epi.beta;
+    ep.diag = epi.diag;
+    ep.has_diag = epi.has_diag ? 1 : 0;
+    ep.npeers = epi.npeers;
+    for (int r = 0; r < 7; ++r) ep.peer[r] = r < epi.npeers ? epi.peers[r] : nullptr;
+    ep.active_until = epi.active_until;
+    ep.round = epi.round;
+
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                        (batch == 1 || (sa % 2 == 0 && sb % 2 == 0)) && encode_fn() != nullptr;
+    if (tma_ok) return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+
+    dim3 grid(ceil_div(m, GB), ceil_div(n, GB), batch);
+    if (grid.y > 65535 || grid.z > 65535) return set_error(FM_ERR_ARG, "dgemm(generic): grid too large");
+    dgemm_generic_kernel<<<grid, 128, 0, ctx().stream>>>(ta ? 1 : 0, tb ? 1 : 0, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, ep);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+}  // namespace fm

@@ -1,0 +1,204 @@
+// expm.cu -- matrix exponential by diagonal Pade [8/8] with scaling and squaring, the algorithm of
+// /root/reference/flomat/expm.rkt:134-215 (NOT Pade-13: the reference uses the n8/d8 coefficient lists, :146-147),
+// kept entirely on the device: norm -> scaling exponent -> X = A/2^s -> even/odd polynomials in X^2 -> solve
+// (even-odd) R = (even+odd) by LU -> s squarings.  One 8-byte D2H (the 1-norm) is the only host round trip.
+//
+// mode bit 0:  0 = the reference's Horner order (expm.rkt:167-177) with the two trivial products dropped
+//                  (AA*0 and AA*(c*I) are formed exactly by an elementwise pass): 7+s DGEMMs
+//              1 = minimum-product regrouping: X^2, X^4, (c6 X^2 + c8 X^4) X^4, (c5 I + c7 X^2) X^4, X*(...): 5+s DGEMMs
+// mode bit 1:  0 = reference behaviour for s <= 0 (expm.rkt:205-210 scales A *up* by 2^-s and never squares:
+//                  bug-compatible);  1 = clamp s at 0 (mathematically correct result).
+// Non-finite norm: the reference's `repeated-squaring` never terminates (F5-iii); we return FM_ERR_NONFINITE.
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+
+namespace fm {
+namespace {
+
+// c_i = (16-i)! 8! / (16! i! (8-i)!)  (expm.rkt:136-146), rounded once from the exact rational
+const double kC[9] = {1.0,
+                      0.5,
+                      0x1.ddddddddddddep-4,
+                      0x1.1111111111111p-6,
+                      0x1.a41a41a41a41ap-10,
+                      0x1.c01c01c01c01cp-14,
+                      0x1.45e5d2ba42ea0p-18,
+                      0x1.29f6b20961c00p-23,
+                      0x1.08db48ebe51c7p-29};
+
+struct Pool {
+    void *buf[8] = {};
+    size_t bytes[8] = {};
+    void *get(int slot, size_t want) {
+        if (bytes[slot] >= want) return buf[slot];
+        if (buf[slot]) cudaFree(buf[slot]);
+        buf[slot] = nullptr;
+        bytes[slot] = 0;
+        if (cudaMalloc(&buf[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            set_error(FM_ERR_NOMEM, "expm workspace allocation of %zu bytes failed", want);
+            return nullptr;
+        }
+        bytes[slot] = want;
+        return buf[slot];
+    }
+};
+Pool g_pool;
+
+// out_z := (s_z is odd ? b1_z : b0_z)   -- collects each item's result from the ping-pong buffer it ended in
+__global__ void __launch_bounds__(256) select_copy_kernel(int n, const double *b0, const double *b1, long long ldw, long long sw,
+                                                           const int32_t *rounds, double *out, long long ldo, long long so) {
+    const int z = blockIdx.z;
+    const double *src = ((rounds[z] > 0 ? rounds[z] : 0) & 1) ? b1 : b0;
+    src += z * sw;
+    out += z * so;
+    for (int j = blockIdx.y; j < n; j += gridDim.y)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[j * ldo + i] = src[j * ldw + i];
+}
+
+double scaling_exponent(double norm1) {
+    // (+ 1 (ceiling (log N 2)))  with (log N 2) = log N / log 2   (expm.rkt:214)
+    return 1.0 + std::ceil(std::log(norm1) / std::log(2.0));
+}
+
+// The whole pipeline for `batch` equally strided matrices.  Workspaces have leading dimension ldw and item stride sw.
+int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host) {
+    const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
+    cudaStream_t st = ctx().stream;
+    const int ldw = n + (n & 1);
+    const long long sw = (long long)ldw * n;
+    const size_t mat_bytes = (size_t)sw * batch * sizeof(double);
+    double *B[6];
+    for (int i = 0; i < 6; ++i) {
+        B[i] = static_cast<double *>(g_pool.get(i, mat_bytes));
+        if (!B[i]) return FM_ERR_NOMEM;
+    }
+    // small arrays: norms | scales (doubles), rounds | ipiv | info (int32)
+    const size_t small_bytes = (size_t)batch * (2 * sizeof(double) + 2 * sizeof(int32_t)) + (size_t)batch * n * sizeof(int32_t) + 64;
+    char *small = static_cast<char *>(g_pool.get(6, small_bytes));
+    if (!small) return FM_ERR_NOMEM;
+    double *d_norm = reinterpret_cast<double *>(small);
+    double *d_scale = d_norm + batch;
+    int32_t *d_rounds = reinterpret_cast<int32_t *>(d_scale + batch);
+    int32_t *d_info = d_rounds + batch;
+    int32_t *d_ipiv = d_info + batch;
+
+    // ---- scaling exponents (expm.rkt:212-215) ----
+    FM_TRY(k_norm1_batched(n, a, lda, sa, batch, d_norm));
+    std::vector<double> h_norm(batch), h_scale(batch);
+    std::vector<int32_t> h_rounds(batch);
+    FM_CUDA(cudaMemcpyAsync(h_norm.data(), d_norm, batch * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaStreamSynchronize(st));
+    int max_rounds = 0;
+    for (int z = 0; z < batch; ++z) {
+        const double nz = h_norm[z];
+        if (std::isnan(nz) || std::isinf(nz))
+            return set_error(FM_ERR_NONFINITE, "expm: ||A||_1 of item %d is %f; the reference does not terminate on this input (expm.rkt:209)", z, nz);
+        double s = scaling_exponent(nz);  // -inf for the zero matrix
+        if (clamp && !(s > 0.0)) s = 0.0;
+        if (s_host) s_host[z] = s;
+        h_scale[z] = std::pow(2.0, s);  // (expt 2 s); 0.0 when s = -inf, reproducing the reference's A/0 = NaN
+        h_rounds[z] = s > 0.0 ? (int32_t)s : 0;
+        if (h_rounds[z] > max_rounds) max_rounds = h_rounds[z];
+    }
+    FM_CUDA(cudaMemcpyAsync(d_scale, h_scale.data(), batch * sizeof(double), cudaMemcpyHostToDevice, st));
+    FM_CUDA(cudaMemcpyAsync(d_rounds, h_rounds.data(), batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FM_CUDA(cudaStreamSynchronize(st));  // h_* go out of scope at return; the copies must have read them
+
+    auto gemm = [&](const double *x, const double *y, double *z, double beta, bool has_diag, double diag) {
+        GemmEpilogue ep;
+        ep.alpha = 1.0;
+        ep.beta = beta;
+        ep.has_diag = has_diag;
+        ep.diag = diag;
+        return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, x, ldw, sw, y, ldw, sw, z, ldw, sw, batch, ep);
+    };
+    auto lin = [&](double ci, double c1, const double *a1, double c2, const double *a2, double *o) {
+        return k_lincomb(n, n, ci, c1, a1, ldw, c2, a2, ldw, o, ldw, sw, sw, sw, batch);
+    };
+
+    double *X = B[0], *A2 = B[1];
+    FM_TRY(k_div_pow2_batched(n, a, lda, sa, X, ldw, sw, d_scale, batch));   // A/2^s   (expm.rkt:206)
+    FM_TRY(gemm(X, X, A2, 0.0, false, 0.0));                                // AA       (expm.rkt:194)
+    double *E, *O, *num, *den, *spare;
+    if (!minprod) {
+        // even = c0 I + AA(c2 I + AA(c4 I + AA(c6 I + AA(c8 I + AA*0))))   (expm.rkt:195 via mpoly :167-177)
+        FM_TRY(lin(kC[6], kC[8], A2, 0.0, nullptr, B[2]));         // c6 I + AA*(c8 I), exact elementwise
+        FM_TRY(gemm(A2, B[2], B[3], 0.0, true, kC[4]));
+        FM_TRY(gemm(A2, B[3], B[2], 0.0, true, kC[2]));
+        FM_TRY(gemm(A2, B[2], B[3], 0.0, true, kC[0]));
+        E = B[3];
+        // odd = X * (c1 I + AA(c3 I + AA(c5 I + AA(c7 I + AA*0))))          (expm.rkt:196)
+        FM_TRY(lin(kC[5], kC[7], A2, 0.0, nullptr, B[2]));
+        FM_TRY(gemm(A2, B[2], B[4], 0.0, true, kC[3]));
+        FM_TRY(gemm(A2, B[4], B[2], 0.0, true, kC[1]));
+        FM_TRY(gemm(X, B[2], B[4], 0.0, false, 0.0));
+        O = B[4];
+        num = B[2];
+        den = B[1];
+        spare = B[5];
+    } else {
+        double *A4 = B[2];
+        FM_TRY(gemm(A2, A2, A4, 0.0, false, 0.0));
+        FM_TRY(lin(0.0, kC[6], A2, kC[8], A4, B[3]));               // c6 X^2 + c8 X^4
+        FM_TRY(lin(kC[0], kC[2], A2, kC[4], A4, B[4]));             // c0 I + c2 X^2 + c4 X^4
+        FM_TRY(gemm(B[3], A4, B[4], 1.0, false, 0.0));              // even
+        E = B[4];
+        FM_TRY(lin(kC[5], kC[7], A2, 0.0, nullptr, B[3]));          // c5 I + c7 X^2
+        FM_TRY(lin(kC[1], kC[3], A2, 0.0, nullptr, B[5]));          // c1 I + c3 X^2
+        FM_TRY(gemm(B[3], A4, B[5], 1.0, false, 0.0));
+        FM_TRY(gemm(X, B[5], B[3], 0.0, false, 0.0));               // odd
+        O = B[3];
+        num = B[5];
+        den = B[1];
+        spare = B[2];
+    }
+    // num = even + odd, den = even - odd, R = den \ num   (expm.rkt:197-199 -> flomat.rkt:2145-2152)
+    // the workspaces of a batch are contiguous (item stride = ldw*n), i.e. one ldw x (n*batch) matrix: one launch
+    FM_TRY(k_addsub(n, n * batch, E, ldw, O, ldw, num, ldw, den, ldw));
+    FM_TRY(k_getrf(n, n, den, ldw, sw, d_ipiv, n, d_info, batch));
+    FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
+    // ---- repeated squaring (expm.rkt:209-210), per-item round counts ----
+    double *cur = num, *nxt = spare;
+    if (batch == 1) {
+        if (max_rounds == 0) return k_copy2d(out, ldo, cur, ldw, n, n);
+        for (int r = 0; r < max_rounds; ++r) {
+            GemmEpilogue ep;
+            const bool last = (r == max_rounds - 1);
+            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, cur, ldw, 0, cur, ldw, 0, last ? out : nxt, last ? ldo : ldw, 0, 1, ep));
+            double *t = cur; cur = nxt; nxt = t;
+        }
+        return FM_OK;
+    }
+    for (int r = 0; r < max_rounds; ++r) {
+        GemmEpilogue ep;
+        ep.active_until = d_rounds;
+        ep.round = r;
+        FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, cur, ldw, sw, cur, ldw, sw, nxt, ldw, sw, batch, ep));
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    // item z ended in `num` if its round count is even, in `spare` if odd
+    dim3 grid(ceil_div(n, 256), n > 256 ? 256 : n, batch);
+    select_copy_kernel<<<grid, 256, 0, st>>>(n, num, spare, ldw, sw, d_rounds, out, ldo, so);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+}  // namespace
+
+int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host) {
+    if (n < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm: bad dimensions");
+    if (info_host) *info_host = 0;
+    if (n == 0) return FM_OK;
+    return expm_pipeline(n, a, lda, 0, out, ldo, 0, 1, mode, s_out);
+}
+
+int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out) {
+    if (n < 0 || batch < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm_batched: bad dimensions");
+    if (n == 0 || batch == 0) return FM_OK;
+    if (batch > 65535) return set_error(FM_ERR_ARG, "expm_batched: at most 65535 items per call");
+    return expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out);
+}
+
+}  // namespace fm

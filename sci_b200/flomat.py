@@ -1,0 +1,455 @@
+"""Host-side mirror of flomat's high-level API for the dense FP64 hot path, over the libflomat_cuda C ABI.
+
+Racket is not available in this image, so this module plays the role of the (replaced) binding layer plus the thin
+Racket wrappers above it: same function names, argument meaning and error behaviour as the reference, with the
+matrix buffer living in HBM.  File:line citations are into /root/reference/flomat/.
+
+    struct flomat (m n a lda)        flomat.rkt:219      -> class Flomat (a = device address)
+    alloc/copy/make/zeros/ones/eye   :437 :516 :538 :2913 :2642
+    shared-submatrix!  / sub!        :295                 -> Flomat.sub (a view: same buffer, lda kept)
+    times / plus / minus             :3202 :3158 :3180
+    .+ .- .* ./                      :3021-3146           -> dot_plus dot_minus dot_times dot_div
+    norm det inv mldivide power      :3273 :3276 :3297 :3289 :3220
+    expm                             expm.rkt:203
+
+Explicit host sync points: `matrix()` / `Flomat.from_numpy` upload, `Flomat.to_numpy()` / `ref` download.
+Nothing here computes on the CPU and there is no fallback: without the CUDA library every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int32
+
+import numpy as np
+
+from . import _lib
+from ._lib import FlomatCudaError, check
+
+NO_TRANS, TRANS = 111, 112
+OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
+
+
+def _L():
+    lib = _lib.load()
+    return lib
+
+
+class _Buffer:
+    """Owns one device allocation (the reference leaves this to the GC: flomat.rkt:437-441)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = _L().fm_alloc_bytes(max(int(nbytes), 16))
+        if not self.ptr:
+            raise FlomatCudaError(f"fm_alloc_bytes({nbytes}) failed: {_lib.last_error()}")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                _L().fm_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Flomat:
+    """`(struct flomat (m n a lda))`: m rows, n columns, device address `a`, leading dimension lda (column-major)."""
+
+    __slots__ = ("m", "n", "a", "lda", "_buf")
+
+    def __init__(self, m: int, n: int, a: int, lda: int, buf):
+        self.m, self.n, self.a, self.lda, self._buf = int(m), int(n), int(a), int(lda), buf
+
+    # ---- construction -----------------------------------------------------------------------------
+    @staticmethod
+    def alloc(m: int, n: int) -> "Flomat":
+        """alloc-flomat (flomat.rkt:437): uninitialised m x n, lda = m."""
+        if m < 0 or n < 0:
+            raise ValueError("alloc-flomat: expected non-negative dimensions")
+        buf = _Buffer(m * n * 8)
+        return Flomat(m, n, buf.ptr, max(m, 1), buf)
+
+    @staticmethod
+    def from_numpy(x) -> "Flomat":
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x.reshape(-1, 1)
+        if x.ndim != 2:
+            raise ValueError("matrix: expected a 2-d array")
+        h = np.asfortranarray(x)
+        out = Flomat.alloc(*h.shape)
+        if h.size:
+            check(_L().fm_upload(out.a, out.lda, h.ctypes.data, max(h.shape[0], 1), h.shape[0], h.shape[1]), "fm_upload")
+            check(_L().fm_sync(), "fm_sync")  # h may be a temporary
+        return out
+
+    def to_numpy(self) -> np.ndarray:
+        h = np.empty((self.m, self.n), dtype=np.float64, order="F")
+        if h.size:
+            check(_L().fm_download(h.ctypes.data, max(self.m, 1), self.a, self.lda, self.m, self.n), "fm_download")
+        return h
+
+    # ---- views (shared-submatrix!, flomat.rkt:295-300): pointer arithmetic only -----------------------
+    def sub(self, i: int, j: int, m: int, n: int) -> "Flomat":
+        if not (0 <= i and 0 <= j and m >= 0 and n >= 0 and i + m <= self.m and j + n <= self.n):
+            raise IndexError("shared-submatrix!: index out of range")
+        return Flomat(m, n, self.a + 8 * (i + j * self.lda), self.lda, self._buf)
+
+    # ---- element access (unsafe-ref / unsafe-set!, flomat.rkt:986-1002): one host sync each ------------
+    def ref(self, i: int, j: int) -> float:
+        if not (0 <= i < self.m and 0 <= j < self.n):
+            raise IndexError("flomat-ref: index out of range")
+        out = c_double()
+        check(_L().fm_get(self.a, i + j * self.lda, byref(out)), "fm_get")
+        return out.value
+
+    def set(self, i: int, j: int, x: float) -> None:
+        if not (0 <= i < self.m and 0 <= j < self.n):
+            raise IndexError("flomat-set!: index out of range")
+        check(_L().fm_set(self.a, i + j * self.lda, float(x)), "fm_set")
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def __repr__(self):
+        return f"Flomat({self.m}x{self.n}, lda={self.lda}, a=0x{self.a:x})"
+
+
+# --------------------------------------------------------------------------------------------------
+# checks (flomat.rkt:322-402) -- error text follows the reference's
+# --------------------------------------------------------------------------------------------------
+def _check_same(a: Flomat, b: Flomat, who: str):
+    if a.m != b.m or a.n != b.n:
+        raise ValueError(f"{who}: expected two matrices of the same size, got {a.m}x{a.n} and {b.m}x{b.n}")
+
+
+def _check_square(a: Flomat, who: str):
+    if a.m != a.n:
+        raise ValueError(f"{who}: expected square matrix, got {a.m}x{a.n}")
+
+
+def _is_num(x) -> bool:
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+
+
+# --------------------------------------------------------------------------------------------------
+# constructors
+# --------------------------------------------------------------------------------------------------
+def matrix(x) -> Flomat:
+    """`(matrix obj)` (flomat.rkt:2880): upload a nested list / numpy array (row-major literal, stored column-major)."""
+    return x if isinstance(x, Flomat) else Flomat.from_numpy(x)
+
+
+def make_flomat(m: int, n: int, x: float = 0.0) -> Flomat:
+    """make-flomat (flomat.rkt:538)."""
+    out = Flomat.alloc(m, n)
+    check(_L().fm_fill(out.a, out.lda, m, n, float(x)), "fm_fill")
+    return out
+
+
+def zeros(m: int, n: int | None = None) -> Flomat:
+    return make_flomat(m, m if n is None else n, 0.0)
+
+
+def ones(m: int, n: int | None = None) -> Flomat:
+    return make_flomat(m, m if n is None else n, 1.0)
+
+
+def eye(m: int, n: int | None = None, k: int = 0) -> Flomat:
+    """eye / flomat-eye (flomat.rkt:3303, :2642)."""
+    n = m if n is None else n
+    out = Flomat.alloc(m, n)
+    check(_L().fm_eye(out.a, out.lda, m, n, int(k)), "fm_eye")
+    return out
+
+
+def copy_flomat(a: Flomat) -> Flomat:
+    """copy-flomat (flomat.rkt:516): dense copy (lda = m) of a matrix or view."""
+    out = Flomat.alloc(a.m, a.n)
+    check(_L().fm_copy2d(out.a, out.lda, a.a, a.lda, a.m, a.n), "fm_copy2d")
+    return out
+
+
+def nrows(a: Flomat) -> int:
+    return a.m
+
+
+def ncols(a: Flomat) -> int:
+    return a.n
+
+
+# --------------------------------------------------------------------------------------------------
+# pointwise (.+ .- .* ./ and their ! forms, flomat.rkt:3021-3146)
+# --------------------------------------------------------------------------------------------------
+def _ewise(op: int, a, b, c: Flomat | None, who: str) -> Flomat:
+    if isinstance(a, Flomat) and isinstance(b, Flomat):
+        _check_same(a, b, who)
+        ref = a
+    elif isinstance(a, Flomat) and _is_num(b):
+        ref = a
+    elif _is_num(a) and isinstance(b, Flomat):
+        ref = b
+    else:
+        raise TypeError(f"{who}: wrong input types")
+    if c is None:
+        c = Flomat.alloc(ref.m, ref.n)
+    else:
+        _check_same(ref, c, who)
+    pa, lda, sa = (a.a, a.lda, 0.0) if isinstance(a, Flomat) else (None, 1, float(a))
+    pb, ldb, sb = (b.a, b.lda, 0.0) if isinstance(b, Flomat) else (None, 1, float(b))
+    check(_L().fm_ewise(op, ref.m, ref.n, pa, lda, sa, pb, ldb, sb, c.a, c.lda), who)
+    return c
+
+
+def dot_plus(a, b, c: Flomat | None = None) -> Flomat:
+    """`.+` / `.+!` (pass c=a for the ! form)."""
+    return _ewise(OP_ADD, a, b, c, ".+")
+
+
+def dot_times(a, b, c: Flomat | None = None) -> Flomat:
+    """`.*`."""
+    return _ewise(OP_MUL, a, b, c, ".*")
+
+
+def dot_minus(a, b=None, c: Flomat | None = None) -> Flomat:
+    """`.-` binary, or unary negation (flomat.rkt:3123-3133)."""
+    if b is None:
+        return _ewise(OP_MUL, a, -1.0, c, ".-")  # (- aij): exact negation, signed zeros included
+    return _ewise(OP_SUB, a, b, c, ".-")
+
+
+def dot_div(a, b=None, c: Flomat | None = None) -> Flomat:
+    """`./` binary, or unary reciprocal."""
+    if b is None:
+        return _ewise(OP_DIV, 1.0, a, c, "./")
+    return _ewise(OP_DIV, a, b, c, "./")
+
+
+# --------------------------------------------------------------------------------------------------
+# plus / minus (flomat.rkt:3148-3190 -> flomat+ :826, flomat- :836 -> constant*flomat+flomat :805-819)
+# --------------------------------------------------------------------------------------------------
+def _axpy_into_copy(alpha: float, a: Flomat, b: Flomat, who: str) -> Flomat:
+    """constant*flomat+flomat (flomat.rkt:815): copy B, then B' := alpha*A + B' -- fused here into ONE pass that
+    reads A and B once and writes the result once (24 B/element instead of the reference's 40)."""
+    _check_same(a, b, who)
+    op = OP_ADD if alpha == 1.0 else OP_SUB
+    # alpha = +1: B + A ; alpha = -1: B - A   (one IEEE add/sub per element, identical to daxpy with alpha = +-1)
+    return _ewise(op, b, a, None, who)
+
+
+def flomat_plus(a: Flomat, b: Flomat) -> Flomat:
+    """flomat+ (flomat.rkt:826): A + B = copy B then += 1.0*A."""
+    return _axpy_into_copy(1.0, a, b, "flomat+")
+
+
+def flomat_minus(a: Flomat, b: Flomat | None = None) -> Flomat:
+    """flomat- (flomat.rkt:836): A - B = copy A then += -1.0*B; unary: scale by -1 (dscal)."""
+    if b is None:
+        return flomat_scale(-1.0, a)
+    return _axpy_into_copy(-1.0, b, a, "flomat-")
+
+
+def flomat_plus_bang(a: Flomat, b: Flomat) -> Flomat:
+    """flomat+! (flomat.rkt:821): B := A + B in place (n daxpys in the reference, one kernel here)."""
+    _check_same(a, b, "flomat+!")
+    check(_L().fm_axpy2d(a.m, a.n, 1.0, a.a, a.lda, b.a, b.lda), "fm_axpy2d")
+    return b
+
+
+def flomat_scale(s: float, a: Flomat) -> Flomat:
+    """flomat-scale (flomat.rkt:1036) = copy + dscal; fused into one s*a_ij pass."""
+    return _ewise(OP_MUL, float(s), a, None, "flomat-scale")
+
+
+def plus(a, *bs):
+    """`plus` (flomat.rkt:3158): left fold over matrices and numbers."""
+    _check_all_same([x for x in (a, *bs) if isinstance(x, Flomat)], "plus")
+    for b in bs:
+        if isinstance(a, Flomat) and isinstance(b, Flomat):
+            a = flomat_plus(a, b)
+        else:
+            a = dot_plus(a, b) if (isinstance(a, Flomat) or isinstance(b, Flomat)) else a + b
+    return a
+
+
+def minus(a, *bs):
+    """`minus` (flomat.rkt:3180): unary negation or left-folded difference."""
+    _check_all_same([x for x in (a, *bs) if isinstance(x, Flomat)], "minus")
+    if not bs:
+        return dot_minus(a)
+    for b in bs:
+        if isinstance(a, Flomat) and isinstance(b, Flomat):
+            a = flomat_minus(a, b)
+        else:
+            a = dot_minus(a, b) if (isinstance(a, Flomat) or isinstance(b, Flomat)) else a - b
+    return a
+
+
+def _check_all_same(ms, who):
+    """check-all-matrices-same-size (flomat.rkt:330)."""
+    for x in ms[1:]:
+        _check_same(ms[0], x, who)
+
+
+# --------------------------------------------------------------------------------------------------
+# times (flomat.rkt:3202 -> flomat* :905 -> constant*matrix*matrix+constant*matrix! :877 -> cblas_dgemm :888)
+# --------------------------------------------------------------------------------------------------
+def flomat_times(a: Flomat, b: Flomat, c: Flomat | None = None, alpha: float = 1.0, beta: float = 1.0,
+                 transpose_a: bool = False, transpose_b: bool = False) -> Flomat:
+    """flomat* (flomat.rkt:905): C := alpha*op(A)*op(B) + beta*C.  Without C the reference allocates a ZERO matrix and
+    calls dgemm with beta = 1 (:909, :538); that equals beta = 0 on an uninitialised buffer, which is what runs here
+    (saves the memset and the read of C)."""
+    ma, na = (a.n, a.m) if transpose_a else (a.m, a.n)
+    mb, nb = (b.n, b.m) if transpose_b else (b.m, b.n)
+    if na != mb:
+        raise ValueError(f"flomat*: expected two matrices with compatible dimensions, got {ma}x{na} and {mb}x{nb}")
+    if c is None:
+        c = Flomat.alloc(ma, nb)
+        beta = 0.0
+    elif c.m != ma or c.n != nb:
+        raise ValueError("flomat*!: result matrix has the wrong dimensions")
+    check(_L().fm_dgemm(TRANS if transpose_a else NO_TRANS, TRANS if transpose_b else NO_TRANS, ma, nb, na, float(alpha),
+                        a.a, a.lda, b.a, b.lda, float(beta), c.a, c.lda), "fm_dgemm")
+    return c
+
+
+def times(a, *bs):
+    """`times` (flomat.rkt:3202): left fold; matrix*matrix -> flomat*, anything with a number -> `.*`."""
+    for b in bs:
+        if isinstance(a, Flomat) and isinstance(b, Flomat):
+            a = flomat_times(a, b)
+        elif isinstance(a, Flomat) or isinstance(b, Flomat):
+            a = dot_times(a, b)
+        else:
+            a = a * b
+    return a
+
+
+def power(a: Flomat, n: int) -> Flomat:
+    """`power` / flomat-expt (flomat.rkt:918-927): same recursion, hence the same product order."""
+    _check_square(a, "matrix-expt")
+    if n < 0:
+        raise ValueError("flomat-expt: expected a natural number")
+    if n == 0:
+        return eye(a.m)
+    if n == 1:
+        return copy_flomat(a)
+    if n == 2:
+        return flomat_times(a, a)
+    if n % 2 == 0:
+        h = power(a, n // 2)
+        return flomat_times(h, h)
+    return flomat_times(a, power(a, n - 1))
+
+
+# --------------------------------------------------------------------------------------------------
+# norm / LU family
+# --------------------------------------------------------------------------------------------------
+def norm(a: Flomat, kind="frob") -> float:
+    """`norm` (flomat.rkt:3273 -> flomat-norm :1328 -> dlange_): kind in 1, 'inf', 'frob', 'max'."""
+    code = {1: b"1", "1": b"1", "inf": b"I", "frob": b"F", "max": b"M"}.get(kind)
+    if code is None:
+        raise ValueError("flomat-norm: unknown norm type")
+    out = c_double()
+    check(_L().fm_norm(code, a.m, a.n, a.a, a.lda, byref(out)), "fm_norm")
+    return out.value
+
+
+class Pivots:
+    """`(struct pivots (ps))` (flomat.rkt:1457): int32, 1-based, device resident; plus the LAPACK `info` word."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        off = 4 * max(self.n, 1)
+        off += (16 - off % 16) % 16
+        self._buf = _Buffer(off + 16)
+        self.ptr = self._buf.ptr
+        self.info_ptr = self.ptr + off
+
+    def to_numpy(self) -> np.ndarray:
+        h = np.zeros(self.n, dtype=np.int32)
+        if self.n:
+            check(_L().fm_download_i32(h.ctypes.data, self.ptr, self.n), "fm_download_i32")
+        return h
+
+    def info(self) -> int:
+        h = np.zeros(1, dtype=np.int32)
+        check(_L().fm_download_i32(h.ctypes.data, self.info_ptr, 1), "fm_download_i32")
+        return int(h[0])
+
+    def sign(self) -> int:
+        """pivots-sign (flomat.rkt:1487)."""
+        p = self.to_numpy()
+        return -1 if int(np.count_nonzero(p - 1 != np.arange(self.n))) % 2 else 1
+
+
+def _pivots(n: int) -> Pivots:
+    return Pivots(n)
+
+
+def flomat_lu_bang(a: Flomat):
+    """flomat-lu! (flomat.rkt:1525): in-place dgetrf; returns (pivots, info)."""
+    piv = _pivots(min(a.m, a.n))
+    check(_L().fm_getrf(a.m, a.n, a.a, a.lda, piv.ptr, piv.info_ptr), "fm_getrf")
+    return piv, piv.info()
+
+
+def mldivide(a: Flomat, b: Flomat) -> Flomat:
+    """`mldivide` (flomat.rkt:3289) -> flomat-solve-many :2145: copies A and B, dgesv, info ignored; returns X."""
+    _check_square(a, "mldivide")
+    if b.m != a.m:
+        raise ValueError("mldivide: A and B must have the same number of rows")
+    lu, x = copy_flomat(a), copy_flomat(b)
+    piv = _pivots(a.m)
+    check(_L().fm_gesv(a.m, x.n, lu.a, lu.lda, piv.ptr, x.a, x.lda, piv.info_ptr), "fm_gesv")
+    return x
+
+
+def inv(a: Flomat) -> Flomat:
+    """`inv` (flomat.rkt:3297) -> flomat-inverse! :1770: copy, dgetrf, dgetri."""
+    _check_square(a, "flomat-inverse!")
+    lu = copy_flomat(a)
+    piv = _pivots(a.m)
+    check(_L().fm_getrf(a.m, a.n, lu.a, lu.lda, piv.ptr, piv.info_ptr), "fm_getrf")
+    check(_L().fm_getri(a.m, lu.a, lu.lda, piv.ptr, None), "fm_getri")
+    return lu
+
+
+def det(a: Flomat) -> float:
+    """`det` (flomat.rkt:3276) -> :1844 -> :1837: copy, dgetrf, sign(ipiv) * left-to-right diagonal product."""
+    _check_square(a, "matrix-determinant")
+    lu = copy_flomat(a)
+    piv = _pivots(a.m)
+    check(_L().fm_getrf(a.m, a.n, lu.a, lu.lda, piv.ptr, piv.info_ptr), "fm_getrf")
+    out = c_double()
+    check(_L().fm_det(a.m, lu.a, lu.lda, piv.ptr, byref(out)), "fm_det")
+    return out.value
+
+
+# --------------------------------------------------------------------------------------------------
+# expm (expm.rkt:203)
+# --------------------------------------------------------------------------------------------------
+EXPM_REFERENCE_ORDER = 0   # the reference's Horner order (7+s products)
+EXPM_MIN_PRODUCTS = 1      # 5+s products
+EXPM_CLAMP_S = 2           # do not reproduce the reference's s<=0 quirk
+
+
+def expm(a: Flomat, mode: int = EXPM_REFERENCE_ORDER, return_s: bool = False):
+    """`expm` (expm.rkt:203-207): Pade [8/8] scaling and squaring, fully on device."""
+    _check_square(a, "expm")
+    out = Flomat.alloc(a.m, a.n)
+    s = c_double()
+    info = c_int32()
+    check(_L().fm_expm(a.m, a.a, a.lda, out.a, out.lda, int(mode), byref(s), byref(info)), "fm_expm")
+    return (out, s.value) if return_s else out
+
+
+def expm_batched(a_ptr: int, n: int, batch: int, out_ptr: int, mode: int = EXPM_REFERENCE_ORDER, s_out: np.ndarray | None = None):
+    """Batch of `batch` dense n x n matrices stored back to back (stride n*n) at device address a_ptr."""
+    sp = s_out.ctypes.data if s_out is not None else None
+    check(_L().fm_expm_batched(n, a_ptr, n, n * n, out_ptr, n, n * n, batch, int(mode), sp), "fm_expm_batched")
+
+
+def sync() -> None:
+    check(_L().fm_sync(), "fm_sync")

@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library builds/loads without a GPU and exports every symbol include/flomat_cuda.h declares;
+host-side argument checks of the Python mirror raise before any device work; no product module imports the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), os.pardir))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "flomat_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|double|uint64_t|char)\s*\*?\s*\*?\s*(\w+)\s*\(", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    from sci_b200 import _lib
+
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 45, names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/flomat_cuda.h but not exported"
+    # and the Python binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_compat_symbols_have_reference_names():
+    lib = ctypes.CDLL(os.path.join(ROOT, "sci_b200", "lib", "libflomat_cuda.so"))
+    for n in ("cblas_dgemm", "cblas_daxpy", "cblas_dcopy", "cblas_dscal", "dlange_", "dgetrf_", "dgesv_", "dgetri_"):
+        getattr(lib, n)  # the names flomat.rkt binds (flomat.rkt:855, 751, 483, 1014, 1317, 1505, 2112, 1754)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import sci_b200
+    from sci_b200 import _lib
+
+    lib = _lib.load()
+    if lib.fm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(sci_b200.FlomatCudaError):
+        sci_b200.zeros(4)
+    assert b"no CPU fallback" in lib.fm_last_error()
+
+
+def test_host_side_checks_raise_before_device_work():
+    from sci_b200.flomat import Flomat, flomat_plus, flomat_times, inv, power
+
+    a = Flomat(2, 3, 0, 2, None)
+    b = Flomat(2, 3, 0, 2, None)
+    with pytest.raises(ValueError):  # check-product-dimensions (flomat.rkt:340)
+        flomat_times(a, b)
+    with pytest.raises(ValueError):  # check-same-dimensions (flomat.rkt:326)
+        flomat_plus(a, Flomat(3, 2, 0, 3, None))
+    with pytest.raises(ValueError):  # check-square (flomat.rkt:388)
+        inv(a)
+    with pytest.raises(ValueError):
+        power(a, 2)
+    with pytest.raises(IndexError):
+        a.sub(1, 1, 2, 3)
+    v = Flomat(4, 4, 1024, 4, None).sub(1, 2, 2, 2)  # shared-submatrix!: pointer arithmetic only (flomat.rkt:295)
+    assert (v.m, v.n, v.lda, v.a) == (2, 2, 4, 1024 + 8 * (1 + 2 * 4))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sci_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"

@@ -1,0 +1,361 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs, the reference's
+golden vectors, committed fixtures, and size-independent properties at larger sizes.
+
+Tolerances: elementwise ops are bit-exact; dgemm / LU / expm use the north_star gate
+||X_gpu - X_ref||_1 / ||X_ref||_1 <= 64 * n * eps  (eps = 2^-52), written as tol(n) below."""
+import ctypes
+import math
+from ctypes import byref, c_double, c_int
+
+import numpy as np
+import pytest
+
+from oracle.flomat_oracle import fortran, normwise_rel_err, tol
+
+pytestmark = pytest.mark.gpu
+
+EPS13 = 1e-13  # flomat's epsilon (flomat.rkt:160)
+
+
+def up(fm, x):
+    return fm.matrix(np.asfortranarray(x, dtype=np.float64))
+
+
+def rnd(seed, m, n, scale=1.0):
+    return np.asfortranarray(np.random.default_rng(seed).standard_normal((m, n)) * scale)
+
+
+# ---------------------------------------------------------------- reference golden vectors through the ABI
+def test_golden_gemm_device_and_compat(fm, golden):
+    lib = fm.load()
+    for case in golden["gemm"]:
+        A, B, AB = fortran(case["A"]), fortran(case["B"]), np.array(case["AB"], dtype=float)
+        assert np.array_equal(fm.times(up(fm, A), up(fm, B)).to_numpy(), AB), case["cite"]
+        # compat tier with HOST pointers, exactly the call flomat.rkt:888 makes (alpha = beta = 1 into zeros)
+        C = np.zeros(AB.shape, order="F")
+        lib.cblas_dgemm(102, 111, 111, A.shape[0], B.shape[1], A.shape[1], 1.0, A.ctypes.data, A.shape[0], B.ctypes.data,
+                        B.shape[0], 1.0, C.ctypes.data, C.shape[0])
+        assert np.array_equal(C, AB), case["cite"]
+
+
+def test_golden_expt_plus_minus_scale(fm, golden):
+    A = up(fm, fortran(golden["expt"]["A"]))
+    for k, want in golden["expt"]["powers"].items():
+        assert np.array_equal(fm.power(A, int(k)).to_numpy(), np.array(want, dtype=float)), k
+    g = golden["plus_minus"]
+    A, B = up(fm, fortran(g["A"])), up(fm, fortran(g["B"]))
+    assert np.array_equal(fm.plus(A, B).to_numpy(), np.array(g["A+B"], dtype=float))
+    assert np.array_equal(fm.minus(A, B).to_numpy(), np.array(g["A-B"], dtype=float))
+    assert np.array_equal(fm.minus(A).to_numpy(), np.array(g["-A"], dtype=float))
+    assert np.array_equal(fm.flomat_minus(A).to_numpy(), np.array(g["-A"], dtype=float))
+    s = golden["scale"]
+    assert np.array_equal(fm.flomat_scale(s["s"], up(fm, fortran(s["A"]))).to_numpy(), np.array(s["sA"], dtype=float))
+
+
+def test_golden_solve_inverse_det_plu(fm, golden):
+    M, b = fortran(golden["solve"]["M"]), fortran(golden["solve"]["b"])
+    x = fm.mldivide(up(fm, M), up(fm, b))
+    assert np.max(np.abs(fm.times(up(fm, M), x).to_numpy() - b)) <= EPS13
+    M = fortran(golden["inverse"]["M"])
+    Mi = fm.inv(up(fm, M))
+    assert np.max(np.abs(fm.times(up(fm, M), Mi).to_numpy() - np.eye(2))) <= EPS13
+    assert np.max(np.abs(fm.times(Mi, up(fm, M)).to_numpy() - np.eye(2))) <= EPS13
+    for case in golden["det"]:
+        d = fm.det(up(fm, fortran(case["M"])))
+        if case["tol"] == 0.0:
+            assert d == case["det"], (case["cite"], d)
+        else:
+            assert abs(d - case["det"]) < case["tol"], (case["cite"], d)
+    M = fortran(golden["plu"]["M"])
+    lu = up(fm, M)
+    piv, info = fm.flomat_lu_bang(lu)
+    assert info == 0
+    LU, ip = lu.to_numpy(), piv.to_numpy()
+    n = 4
+    P = np.eye(n)
+    for i in range(n - 1, -1, -1):
+        if ip[i] - 1 != i:
+            P[[i, ip[i] - 1], :] = P[[ip[i] - 1, i], :]
+    assert np.max(np.abs(P @ (np.tril(LU, -1) + np.eye(n)) @ np.triu(LU) - M)) <= EPS13
+
+
+def test_identity_and_const(fm):
+    for n in (1, 2, 3, 17):
+        assert np.array_equal(fm.eye(n).to_numpy(), np.eye(n))
+    assert np.array_equal(fm.eye(3, 5, 1).to_numpy(), np.eye(3, 5, 1))
+    assert np.array_equal(fm.make_flomat(2, 3, 0.0).to_numpy(), np.zeros((2, 3)))
+    assert np.array_equal(fm.ones(5, 2).to_numpy(), np.ones((5, 2)))
+
+
+# ---------------------------------------------------------------- elementwise: bit exact
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 3), (7, 5), (64, 64), (129, 33), (1000, 17), (2048, 512)])
+def test_ewise_bit_exact(fm, ref, m, n):
+    a, b = rnd(1, m, n), rnd(2, m, n)
+    A, B = up(fm, a), up(fm, b)
+    assert np.array_equal(fm.dot_plus(A, B).to_numpy(), ref.dot_plus(a, b))
+    assert np.array_equal(fm.dot_minus(A, B).to_numpy(), ref.dot_minus(a, b))
+    assert np.array_equal(fm.dot_times(A, B).to_numpy(), ref.dot_times(a, b))
+    assert np.array_equal(fm.dot_div(A, B).to_numpy(), ref.dot_divide(a, b))
+    assert np.array_equal(fm.dot_times(A, 3.25).to_numpy(), ref.dot_times(a, 3.25))
+    assert np.array_equal(fm.dot_minus(1.5, B).to_numpy(), ref.dot_minus(1.5, b))
+    assert np.array_equal(fm.dot_div(A).to_numpy(), ref.dot_divide(a))
+    assert np.array_equal(fm.dot_minus(A).to_numpy(), -a)
+    assert np.array_equal(fm.plus(A, B).to_numpy(), ref.plus(a, b))
+    assert np.array_equal(fm.minus(A, B).to_numpy(), ref.minus(a, b))
+    assert np.array_equal(fm.plus(A, B, 2.0, A).to_numpy(), ref.plus(a, b, 2.0, a))
+    assert np.array_equal(fm.flomat_scale(-0.5, A).to_numpy(), ref.scale(-0.5, a))
+    assert np.array_equal(fm.copy_flomat(A).to_numpy(), a)
+
+
+def test_ewise_views_and_inplace(fm, ref):
+    a, b = rnd(3, 40, 30), rnd(4, 40, 30)
+    A, B = up(fm, a), up(fm, b)
+    va, vb = A.sub(3, 5, 21, 11), B.sub(3, 5, 21, 11)  # odd offsets: 8-byte aligned only, lda > m
+    assert np.array_equal(fm.dot_times(va, vb).to_numpy(), a[3:24, 5:16] * b[3:24, 5:16])
+    fm.dot_plus(va, vb, va)  # the `!` form writes through the view
+    want = a.copy()
+    want[3:24, 5:16] += b[3:24, 5:16]
+    assert np.array_equal(A.to_numpy(), want)
+    fm.flomat_plus_bang(vb, va)
+    want[3:24, 5:16] = b[3:24, 5:16] + want[3:24, 5:16]
+    assert np.array_equal(A.to_numpy(), want)
+
+
+def test_empty_matrices(fm):
+    z = fm.zeros(0, 5)
+    assert fm.dot_plus(z, z).to_numpy().shape == (0, 5)
+    assert fm.times(fm.zeros(3, 0), fm.zeros(0, 4)).to_numpy().tolist() == np.zeros((3, 4)).tolist()
+    assert fm.norm(z, 1) == 0.0
+
+
+@pytest.mark.parametrize("m,n", [(5, 7), (64, 64), (300, 129), (1024, 77)])
+def test_norms(fm, ref, m, n):
+    a = rnd(5, m, n)
+    A = up(fm, a)
+    for kind in (1, "inf", "frob", "max"):
+        got, want = fm.norm(A, kind), ref.norm(a, kind)
+        assert abs(got - want) <= 4 * max(m, n) * 2.0 ** -52 * abs(want), kind
+    assert fm.norm(A, "max") == np.abs(a).max()
+    v = A.sub(1, 1, m - 2, n - 2)
+    assert abs(fm.norm(v, 1) - np.abs(a[1:-1, 1:-1]).sum(axis=0).max()) <= 1e-12 * m
+
+
+# ---------------------------------------------------------------- dgemm
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (8, 8, 4), (16, 16, 16), (127, 65, 33), (128, 128, 128), (130, 258, 70), (256, 256, 256),
+                                   (512, 384, 1000), (1024, 1024, 1024), (100, 2000, 48), (2000, 100, 48)])
+def test_dgemm_nn_parity(fm, ref, m, n, k):
+    a, b = rnd(10, m, k), rnd(11, k, n)
+    got = fm.times(up(fm, a), up(fm, b)).to_numpy()
+    want = ref.gemm(a, b)
+    assert normwise_rel_err(got, want) <= tol(max(m, n, k))
+
+
+def test_dgemm_alpha_beta_trans_and_views(fm, ref):
+    rng = np.random.default_rng(12)
+    for (ta, tb) in [(False, False), (True, False), (False, True), (True, True)]:
+        m, n, k = 150, 90, 70
+        a = rnd(13, k, m) if ta else rnd(13, m, k)
+        b = rnd(14, n, k) if tb else rnd(14, k, n)
+        c = rnd(15, m, n)
+        C = up(fm, c)
+        fm.flomat_times(up(fm, a), up(fm, b), C, alpha=-0.75, beta=0.5, transpose_a=ta, transpose_b=tb)
+        want = ref.gemm(a, b, c.copy(order="F"), alpha=-0.75, beta=0.5, ta=ta, tb=tb)
+        assert normwise_rel_err(C.to_numpy(), want) <= tol(k), (ta, tb)
+    # views: odd row offsets (not 16-byte aligned) and even ones (TMA path with lda > m)
+    big_a, big_b = rnd(16, 300, 300), rnd(17, 300, 300)
+    A, B = up(fm, big_a), up(fm, big_b)
+    for (i, j) in [(1, 3), (2, 4), (16, 32)]:
+        va, vb = A.sub(i, j, 200, 180), B.sub(j, i, 180, 150)
+        got = fm.times(va, vb).to_numpy()
+        want = ref.gemm(np.asfortranarray(big_a[i:i + 200, j:j + 180]), np.asfortranarray(big_b[j:j + 180, i:i + 150]))
+        assert normwise_rel_err(got, want) <= tol(200), (i, j)
+
+
+def test_dgemm_exact_integers_large(fm):
+    """Integer-valued inputs make every partial sum exact, so any summation order must give identical results."""
+    rng = np.random.default_rng(18)
+    a = np.asfortranarray(rng.integers(-8, 9, (640, 520)).astype(float))
+    b = np.asfortranarray(rng.integers(-8, 9, (520, 700)).astype(float))
+    assert np.array_equal(fm.times(up(fm, a), up(fm, b)).to_numpy(), a @ b)
+
+
+def test_dgemm_linearity_at_full_size(fm):
+    """BASELINE config size n=4096..8192: (A1+A2)B == A1 B + A2 B within tolerance; no CPU product needed."""
+    n = 4096
+    a1, a2, b = rnd(20, n, n), rnd(21, n, n), rnd(22, n, n)
+    A1, A2, B = up(fm, a1), up(fm, a2), up(fm, b)
+    lhs = fm.times(fm.plus(A1, A2), B)
+    rhs = fm.plus(fm.times(A1, B), fm.times(A2, B))
+    diff = fm.norm(fm.minus(lhs, rhs), 1)
+    assert diff / fm.norm(rhs, 1) <= tol(n)
+    # spot-check 64 random entries against float64 dot products
+    got = lhs.to_numpy()
+    rng = np.random.default_rng(23)
+    for _ in range(64):
+        i, j = rng.integers(0, n, 2)
+        want = float((a1[i, :] + a2[i, :]) @ b[:, j])
+        assert abs(got[i, j] - want) <= 64 * n * 2.0 ** -52 * (np.abs(a1[i, :] + a2[i, :]) @ np.abs(b[:, j]))
+
+
+# ---------------------------------------------------------------- LU family
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (2, 1), (5, 3), (16, 16), (17, 2), (64, 7), (130, 5), (256, 256), (500, 33), (1024, 64),
+                                    (1500, 10)])
+def test_solve_parity(fm, ref, n, nrhs):
+    a, b = rnd(30, n, n), rnd(31, n, nrhs)
+    x = fm.mldivide(up(fm, a), up(fm, b)).to_numpy()
+    want = ref.mldivide(a, b)
+    cond_slack = 50  # forward error also carries cond(A); randn matrices: cond ~ n
+    assert normwise_rel_err(x, want) <= tol(n) * cond_slack
+    resid = np.abs(a @ x - b).sum(axis=0).max() / (np.abs(a).sum(axis=0).max() * np.abs(x).sum(axis=0).max())
+    assert resid <= tol(n)
+
+
+@pytest.mark.parametrize("n", [8, 33, 64, 130])
+def test_lu_fixtures_ipiv_and_factors(fm, fixtures, n):
+    m = np.asfortranarray(fixtures[f"lu_in_{n}"])
+    lu = up(fm, m)
+    piv, info = fm.flomat_lu_bang(lu)
+    assert info == 0
+    assert np.array_equal(piv.to_numpy(), fixtures[f"oracle_ipiv_{n}"])  # same pivot sequence as the reference's LAPACK
+    LU = lu.to_numpy()
+    P = np.arange(n)
+    for i, p in enumerate(piv.to_numpy()):
+        P[[i, p - 1]] = P[[p - 1, i]]
+    rec = (np.tril(LU, -1) + np.eye(n)) @ np.triu(LU)
+    assert normwise_rel_err(rec, m[P, :]) <= tol(n)
+    assert normwise_rel_err(fm.inv(up(fm, m)).to_numpy(), fixtures[f"oracle_inv_out_{n}"]) <= tol(n) * 50
+    d, want = fm.det(up(fm, m)), float(fixtures[f"oracle_det_out_{n}"])
+    assert abs(d - want) <= 1e-10 * abs(want)
+    x = fm.mldivide(up(fm, m), up(fm, fixtures[f"rhs_in_{n}"])).to_numpy()
+    assert normwise_rel_err(x, fixtures[f"oracle_solve_out_{n}"]) <= tol(n) * 50
+
+
+def test_lu_rectangular_and_singular(fm, ref):
+    for (m, n) in [(40, 20), (20, 40), (300, 130)]:
+        a = rnd(32, m, n)
+        lu = up(fm, a)
+        piv, info = fm.flomat_lu_bang(lu)
+        want_lu, want_piv, want_info = ref.lu(a)
+        assert info == want_info == 0
+        assert np.array_equal(piv.to_numpy(), want_piv[: min(m, n)])
+        assert normwise_rel_err(lu.to_numpy(), want_lu) <= tol(max(m, n)) * 20
+    # exactly singular: a zero column -> info = its 1-based index (dgetrf semantics; the reference ignores it)
+    a = rnd(33, 6, 6)
+    a[:, 2] = 0.0
+    piv, info = fm.flomat_lu_bang(up(fm, a))
+    assert info == 3 == ref.lu(a)[2]
+
+
+def test_compat_lapack_symbols_host_pointers(fm, ref):
+    """dgesv_/dgetrf_/dgetri_/dlange_ called exactly as the Racket FFI calls them: scalars by reference, host buffers."""
+    lib = fm.load()
+    n, nrhs = 50, 3
+    a, b = rnd(34, n, n), rnd(35, n, nrhs)
+    A, B = a.copy(order="F"), b.copy(order="F")
+    ipiv = np.zeros(n, dtype=np.int32)
+    info = c_int(-99)
+    lib.dgesv_(byref(c_int(n)), byref(c_int(nrhs)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, B.ctypes.data, byref(c_int(n)),
+               byref(info))
+    assert info.value == 0
+    assert normwise_rel_err(B, ref.mldivide(a, b)) <= tol(n) * 50
+    want_lu, want_piv, _ = ref.lu(a)
+    assert np.array_equal(ipiv, want_piv)
+    # inverse: dgetrf_ + dgetri_ (flomat.rkt:1770-1779)
+    A = a.copy(order="F")
+    lib.dgetrf_(byref(c_int(n)), byref(c_int(n)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, byref(info))
+    assert info.value == 0
+    work = np.zeros(n * n)
+    lib.dgetri_(byref(c_int(n)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, work.ctypes.data, byref(c_int(n * n)), byref(info))
+    assert info.value == 0
+    assert normwise_rel_err(A, ref.inv(a)) <= tol(n) * 50
+    got = lib.dlange_(b"1", byref(c_int(n)), byref(c_int(n)), a.ctypes.data, byref(c_int(n)), None)
+    assert abs(got - ref.norm(a, 1)) <= 1e-12 * got
+    # daxpy / dscal / dcopy incl. the incX = 0 broadcast make-flomat relies on (flomat.rkt:544)
+    x, y = rnd(36, 100, 1).ravel().copy(), rnd(37, 100, 1).ravel().copy()
+    want = y + 2.0 * x
+    lib.cblas_daxpy(100, 2.0, x.ctypes.data, 1, y.ctypes.data, 1)
+    assert np.array_equal(y, want)
+    lib.cblas_dscal(100, -3.0, y.ctypes.data, 1)
+    assert np.array_equal(y, -3.0 * want)
+    one = np.array([7.5])
+    lib.cblas_dcopy(100, one.ctypes.data, 0, y.ctypes.data, 1)
+    assert np.array_equal(y, np.full(100, 7.5))
+
+
+def test_solve_roundtrip_at_config_size(fm):
+    """BASELINE config 3 shape (n=8192 would need a 3.7e11-flop CPU check): n=4096, 64 rhs, residual property."""
+    n, nrhs = 4096, 64
+    a, b = rnd(38, n, n), rnd(39, n, nrhs)
+    A, B = up(fm, a), up(fm, b)
+    X = fm.mldivide(A, B)
+    R = fm.minus(fm.times(A, X), B)
+    assert fm.norm(R, 1) / (fm.norm(A, 1) * fm.norm(X, 1)) <= tol(n)
+
+
+# ---------------------------------------------------------------- expm
+@pytest.mark.parametrize("mode", [0, 1])
+def test_expm_closed_forms_and_quirks(fm, mode):
+    E = fm.expm(up(fm, [[1, 0], [0, 2]]), mode).to_numpy()
+    assert normwise_rel_err(E, np.diag([math.e, math.e ** 2])) <= tol(2)
+    t = 0.7
+    E = fm.expm(up(fm, [[0, -t], [t, 0]]), mode).to_numpy()
+    assert normwise_rel_err(E, [[math.cos(t), -math.sin(t)], [math.sin(t), math.cos(t)]]) <= tol(2)
+    N = np.array([[0, 1, 2], [0, 0, 3], [0, 0, 0]], dtype=float)
+    assert normwise_rel_err(fm.expm(up(fm, N), mode).to_numpy(), np.eye(3) + N + N @ N / 2) <= tol(3)
+    # s <= 0 is reproduced by default, fixed with EXPM_CLAMP_S
+    q = np.diag([0.1, 0.05])
+    E, s = fm.expm(up(fm, q), mode, return_s=True)
+    assert s == -2.0
+    assert normwise_rel_err(E.to_numpy(), np.diag([math.exp(0.4), math.exp(0.2)])) <= 1e-14
+    E = fm.expm(up(fm, q), mode | fm.EXPM_CLAMP_S).to_numpy()
+    assert normwise_rel_err(E, np.diag([math.exp(0.1), math.exp(0.05)])) <= 1e-14
+    with pytest.raises(fm.FlomatCudaError):  # F5-iii: the reference would spin forever
+        fm.expm(up(fm, [[np.inf, 0], [0, 1]]), mode)
+
+
+@pytest.mark.parametrize("n", [8, 33, 64, 130])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_expm_fixtures(fm, fixtures, n, mode):
+    a = np.asfortranarray(fixtures[f"expm_in_{n}"])
+    E, s = fm.expm(up(fm, a), mode, return_s=True)
+    assert s == float(fixtures[f"oracle_expm_s_{n}"])
+    assert normwise_rel_err(E.to_numpy(), fixtures[f"oracle_expm_out_{n}"]) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [256, 512])
+def test_expm_parity_config_sizes(fm, ref, n):
+    """BASELINE configs 2 (n=512) and 5 (n=256 items): randn/sqrt(n) inputs of SURVEY 8d."""
+    a = rnd(2001, n, n, 1.0 / math.sqrt(n))
+    want = ref.expm(a)
+    for mode in (0, 1):
+        E, s = fm.expm(up(fm, a), mode, return_s=True)
+        assert s == ref.scaling_exponent(a)
+        assert normwise_rel_err(E.to_numpy(), want) <= tol(n), mode
+
+
+def test_expm_batched(fm, ref):
+    n, batch = 64, 9
+    rng = np.random.default_rng(5001)
+    items = [np.asfortranarray(rng.standard_normal((n, n)) / 8.0 * (0.3 if z == 4 else 1.0 + 0.5 * (z % 3))) for z in range(batch)]
+    stacked = np.concatenate([x.ravel(order="F") for x in items])
+    lib = fm.load()
+    src = fm.Flomat.from_numpy(stacked.reshape(-1, 1))
+    dst = fm.Flomat.alloc(n * n * batch, 1)
+    s_out = np.zeros(batch)
+    fm.expm_batched(src.a, n, batch, dst.a, 0, s_out)
+    got = dst.to_numpy().ravel()
+    assert len(set(s_out.tolist())) > 1  # items with different squaring counts in one batch
+    for z in range(batch):
+        assert s_out[z] == ref.scaling_exponent(items[z])
+        Ez = got[z * n * n:(z + 1) * n * n].reshape(n, n, order="F")
+        assert normwise_rel_err(Ez, ref.expm(items[z])) <= tol(n), z
+
+
+def test_expm_semigroup_property_large(fm):
+    """exp(A)^2 == exp(2A) at n=1024 (size-independent property; no CPU expm needed)."""
+    n = 1024
+    a = rnd(6003, n, n, 1.0 / math.sqrt(n))
+    E1 = fm.expm(up(fm, a))
+    E2 = fm.expm(up(fm, 2.0 * a))
+    sq = fm.times(E1, E1)
+    assert fm.norm(fm.minus(sq, E2), 1) / fm.norm(E2, 1) <= tol(n)
