@@ -58,10 +58,87 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
+// Replays the interchanges piv[0..cnt) (absolute row numbers; pivot i swaps rows k1+i and piv[i]) on one column `c` whose
+// top rows k1..k1+15 and distinct far rows are staged in the caller's shared-memory slots S[slot*stride + lane]:
+// every load is issued before the first dependent use, so a group of 16 interchanges costs one memory round trip.
+// `first` = first pivot index to apply (own-leaf columns skip the pivots that were applied in registers).
+__device__ __forceinline__ void swap_group(double *c, int k1, int cnt, const int *other, const int *farrow, double *S, int stride, int lane,
+                                           int first) {
+    // stage through registers so that the (generic-pointer) shared stores cannot serialise the global loads
+    double top[LEAF], far[LEAF];
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j) top[j] = j < cnt ? c[k1 + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j) far[j] = (j >= first && j < cnt && farrow[j] >= 0) ? c[farrow[j]] : 0.0;
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j) {
+        S[j * stride + lane] = top[j];
+        S[(LEAF + j) * stride + lane] = far[j];
+    }
+    for (int j = first; j < cnt; ++j) {
+        const int o = other[j];
+        if (o != j) {
+            const double t = S[j * stride + lane];
+            S[j * stride + lane] = S[o * stride + lane];
+            S[o * stride + lane] = t;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j) {
+        top[j] = S[j * stride + lane];
+        far[j] = S[(LEAF + j) * stride + lane];
+    }
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j)
+        if (j < cnt) c[k1 + j] = top[j];
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j)
+        if (j >= first && j < cnt && farrow[j] >= 0) c[farrow[j]] = far[j];
+}
+
+// For pivots piv[0..cnt) of rows k1..k1+cnt: other[j] = slot exchanged with top slot j (a top slot, or LEAF + first
+// occurrence of that far row), farrow[j] = far row to load into slot LEAF+j (or -1).  Called by threads j < LEAF.
+__device__ __forceinline__ void swap_plan(int j, int k1, int cnt, const int *piv, int *other, int *farrow) {
+    int o = j, f = -1;
+    if (j < cnt) {
+        const int p = piv[j];
+        if (p < k1 + cnt) o = p - k1;
+        else {
+            int first = j;
+            for (int i = 0; i < j; ++i)
+                if (piv[i] == p) { first = i; break; }
+            o = LEAF + first;
+            if (first == j) f = p;
+        }
+    }
+    other[j] = o;
+    farrow[j] = f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel kernel: factors an m x pw panel (pw <= 128) in ONE launch on ONE cluster.  Leaves of 16 columns are factored
+// in registers (column steps as described above); between leaves, inside the same kernel, the leaf's interchanges are
+// applied to the other panel columns, the 16 x rest block row of U is obtained by a register-level triangular solve,
+// and every thread applies the rank-16 update to its own rows of the remaining panel columns (right-looking).
+// ---------------------------------------------------------------------------------------------
+constexpr int PAY = LEAF + 3;
+
+#ifdef FM_LU_PROF
+__device__ long long g_prof[32];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0, t1) do { if (tid == 0 && crank == 0 && blockIdx.y == 0) g_prof[slot] += (t1) - (t0); } while (0)
+#else
+#define PROF_T(var) do {} while (0)
+#define PROF_ADD(slot, t0, t1) do {} while (0)
+#endif
+  // payload of a candidate: |pivot|, row, 1/pivot, the 16 row values
+
 template <int NT, int RPT>
 __global__ void __launch_bounds__(NT, 1)
-lu_leaf_kernel(double *a, long long lda, long long sa, int m, int w, int row0, int col0, int32_t *ipiv, long long sp, int32_t *info) {
+lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0, int col0, int32_t *ipiv, long long sp, int32_t *info) {
     constexpr int W = LEAF, NWARP = NT / 32, ROWS = NT * RPT;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NOROW = 0x7fffffff;
     uint32_t crank, csize;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
@@ -70,196 +147,278 @@ lu_leaf_kernel(double *a, long long lda, long long sa, int m, int w, int row0, i
     ipiv += item * sp;
     info += item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rbase = crank * ROWS + tid;  // rows rbase + k*NT, k < RPT
+    const int rbase = crank * ROWS + tid;  // panel-local rows rbase + k*NT, k < RPT
 
+    extern __shared__ double dyn[];  // 32 x 128 doubles: swap staging, later the U block s_U[t*NB + c]
     __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ double s_wval[NWARP];
+    __shared__ unsigned s_whi[NWARP], s_wlo[NWARP];
     __shared__ int s_wrow[NWARP];
-    __shared__ double s_wdata[NWARP][W];
-    __shared__ double s_cand[2][MAXC][W + 2];  // per parity, per source CTA: |pivot|, row, the candidate row
-    __shared__ double s_rowj[2][W];            // row j before the interchange (pushed by CTA 0)
+    __shared__ double s_wdata[NWARP][W + 1];  // candidate row of each warp (+ reciprocal of its pivot)
+    __shared__ double s_cand[2][MAXC][PAY];
+    __shared__ double s_rowj[2][W];
     __shared__ double s_myrowj[W];
+    __shared__ double s_L[W][W + 1];
+    __shared__ int s_piv[W], s_other[W], s_far[W];
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    double v[RPT][W];
-#pragma unroll
-    for (int k = 0; k < RPT; ++k)
-#pragma unroll
-        for (int c = 0; c < W; ++c) {
-            const int r = rbase + k * NT;
-            v[k][c] = (r < m && c < w) ? a[c * lda + r] : 0.0;
-        }
-    // every CTA's barriers are initialised before anybody pushes
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    const uint32_t tx_bytes = csize * (W + 2) * 8 + W * 8;
+    const uint32_t tx_bytes = csize * PAY * 8 + W * 8;
 
-    // The column loop is NOT unrolled (an unrolled body is ~350 KB of straight-line SASS that runs once: the kernel was
-    // instruction-fetch bound).  To keep every register index static the row is ROTATED by one slot per step: slot 0 is
-    // always the current column, updated trailing entries move down one slot, and the finished value of the step (the
-    // multiplier l, or the U entry for rows that are already done) is appended at slot 15.  After w steps slot 16-w+c holds
-    // column c, for every row.  Whole-row interchanges automatically carry the multipliers of earlier columns along.
+    for (int lc0 = 0; lc0 < pw; lc0 += W) {
+        const int w = min(W, pw - lc0);
+        PROF_T(tL0);
+        // ---- 1. this thread's rows of the leaf columns ----
+        double v[RPT][W];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = rbase + k * NT;
+#pragma unroll
+            for (int c = 0; c < W; ++c) v[k][c] = (r >= lc0 && r < m && c < w) ? a[(lc0 + c) * lda + r] : 0.0;
+        }
+        // ---- 2. column steps.  The row is ROTATED one slot per step so that all register indices stay static and the loop
+        //         is not unrolled: slot 0 = current column, finished values are appended at slot 15. ----
+        PROF_T(tL1);
+        PROF_ADD(0, tL0, tL1);
 #pragma unroll 1
-    for (int j = 0; j < w; ++j) {
-        const int par = j & 1;
-        const uint32_t bar = lsmem(&s_bar[par]);
-        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
-        // ---- candidate among this thread's rows still in play (row >= j); lowest row wins ties (IDAMAX) ----
-        double val = -1.0;
-        int row = 0x7fffffff, kb = 0;
+        for (int j = 0; j < w; ++j) {
+            PROF_T(tc0);
+            const int jj = lc0 + j;  // panel-local index of the pivot position
+            const int par = jj & 1;
+            const uint32_t bar = lsmem(&s_bar[par]);
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+            // candidate among this thread's rows still in play; lowest row wins ties (IDAMAX)
+            double val = -1.0, piv0 = 1.0;
+            int row = NOROW, kb = 0;
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const int r = rbase + k * NT;
-            const double x = fabs(v[k][0]);
-            if (r >= j && r < m && x > val) { val = x; row = r; kb = k; }
-        }
-        const int myrow = row;
-        double bval = val;
-        int brow = row;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bval, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-            if (ov > bval || (ov == bval && orow < brow)) { bval = ov; brow = orow; }
-        }
-        if (bval >= 0.0 && myrow == brow) {  // exactly one lane: publish the warp's candidate row
-#pragma unroll
-            for (int c = 0; c < W; ++c) {
-                double x = v[0][c];
-#pragma unroll
-                for (int k = 1; k < RPT; ++k) x = (kb == k) ? v[k][c] : x;
-                s_wdata[warp][c] = x;
+            for (int k = 0; k < RPT; ++k) {
+                const int r = rbase + k * NT;
+                const double x = fabs(v[k][0]);
+                if (r >= jj && r < m && x > val) { val = x; row = r; kb = k; piv0 = v[k][0]; }
             }
-        }
-        if (lane == 0) { s_wval[warp] = bval; s_wrow[warp] = brow; }
-        if (crank == 0 && tid == j) {  // row j lives in CTA 0, thread j, k = 0 (j < 16 <= NT)
+            const double myrcp = 1.0 / piv0;  // issued early: its latency hides behind the REDUX chain
+            // warp argmax on the bit pattern of |x| (monotonic for non-negative doubles): three REDUX instead of a shuffle tree
+            const unsigned long long key = row != NOROW ? (unsigned long long)__double_as_longlong(val) : 0ull;
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned mh = __reduce_max_sync(FULL, hi);
+            const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+            const int wrow = __reduce_min_sync(FULL, (hi == mh && lo == ml) ? row : NOROW);
+            if (row == wrow && row != NOROW) {  // exactly one lane: publish the warp's candidate row
 #pragma unroll
-            for (int c = 0; c < W; ++c) s_myrowj[c] = v[0][c];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double x = lane < NWARP ? s_wval[lane] : -2.0;
-            int r = lane < NWARP ? s_wrow[lane] : 0x7fffffff;
-            int src = lane;
+                for (int k = 0; k < RPT; ++k)
+                    if (kb == k) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, x, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, r, o);
-                const int osrc = __shfl_xor_sync(0xffffffffu, src, o);
-                if (ov > x || (ov == x && orow < r)) { x = ov; r = orow; src = osrc; }
+                        for (int c = 0; c < W; ++c) s_wdata[warp][c] = v[k][c];
+                    }
+                s_wdata[warp][W] = myrcp;
             }
-            if (lane < W + 2) {
-                const double payload = lane == 0 ? x : (lane == 1 ? (double)r : (x >= 0.0 ? s_wdata[src][lane - 2] : 0.0));
-                const uint32_t dst = lsmem(&s_cand[par][crank][lane]);
-                for (uint32_t d = 0; d < csize; ++d) st_async(mapa(dst, d), payload, mapa(bar, d));
+            if (lane == 0) { s_whi[warp] = mh; s_wlo[warp] = ml; s_wrow[warp] = wrow; }
+            if (crank == 0 && tid == jj) {  // row jj lives in CTA 0, thread jj, k = 0 (jj < 128 <= NT)
+#pragma unroll
+                for (int c = 0; c < W; ++c) s_myrowj[c] = v[0][c];
             }
-            if (crank == 0 && lane < W) {
-                const double payload = s_myrowj[lane];
-                const uint32_t dst = lsmem(&s_rowj[par][lane]);
-                for (uint32_t d = 0; d < csize; ++d) st_async(mapa(dst, d), payload, mapa(bar, d));
-            }
-        }
-        bar_wait(bar, (j >> 1) & 1);
-        // ---- global winner: same decision in every thread ----
-        double best = -2.0;
-        int p = 0x7fffffff, wr = 0;
-        for (int d = 0; d < (int)csize; ++d) {
-            const double cv = s_cand[par][d][0];
-            const int cr = (int)s_cand[par][d][1];
-            if (cv > best || (cv == best && cr < p)) { best = cv; p = cr; wr = d; }
-        }
-        const double *pr = &s_cand[par][wr][2];
-        const double pval = pr[0];
-        if (crank == 0 && tid == 0) {
-            ipiv[col0 + j] = row0 + p + 1;
-            if (pval == 0.0 && *info == 0) *info = col0 + j + 1;
-        }
-        const double rcp = 1.0 / pval;
-        const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
-        const int last = W - 1 - j;                   // slots 1..last are trailing columns; beyond them: earlier multipliers
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const int r = rbase + k * NT;
-            if (p != j) {
-                if (r == p) {  // the pivot row's old slot receives row j
-#pragma unroll
-                    for (int c = 0; c < W; ++c) v[k][c] = s_rowj[par][c];
-                } else if (r == j) {
-#pragma unroll
-                    for (int c = 0; c < W; ++c) v[k][c] = pr[c];
+            __syncthreads();
+            PROF_T(tc1);
+            PROF_ADD(1, tc0, tc1);
+            {
+                // every warp finds the CTA's candidate (redundantly) and pushes it to the destination CTAs warp, warp+NWARP, ...
+                const unsigned h2 = lane < NWARP ? s_whi[lane] : 0u, l2 = lane < NWARP ? s_wlo[lane] : 0u;
+                const int r2 = lane < NWARP ? s_wrow[lane] : NOROW;
+                const unsigned MH = __reduce_max_sync(FULL, r2 != NOROW ? h2 : 0u);
+                const unsigned ML = __reduce_max_sync(FULL, (r2 != NOROW && h2 == MH) ? l2 : 0u);
+                const int MR = __reduce_min_sync(FULL, (r2 != NOROW && h2 == MH && l2 == ML) ? r2 : NOROW);
+                const unsigned who = __ballot_sync(FULL, r2 == MR && r2 != NOROW);
+                const int src = who ? __ffs(who) - 1 : 0;
+                double payload = 0.0;
+                if (lane == 0) payload = (double)MR;
+                else if (lane < PAY) payload = (MR == NOROW) ? 0.0 : (lane == 1 ? s_wdata[src][W] : s_wdata[src][lane - 2]);
+                const double rowj_payload = (crank == 0 && lane < W) ? s_myrowj[lane] : 0.0;
+                const uint32_t dst = lsmem(&s_cand[par][crank][lane < PAY ? lane : 0]);
+                const uint32_t dstj = lsmem(&s_rowj[par][lane < W ? lane : 0]);
+                for (uint32_t d = warp; d < csize; d += NWARP) {
+                    const uint32_t rbar = mapa(bar, d);
+                    if (lane < PAY) st_async(mapa(dst, d), payload, rbar);
+                    if (crank == 0 && lane < W) st_async(mapa(dstj, d), rowj_payload, rbar);
                 }
             }
-            const bool active = (r > j && r < m && pval != 0.0);
-            const double l = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
-            const double app = active ? l : v[k][0];
+            PROF_T(tc2);
+            PROF_ADD(2, tc1, tc2);
+            bar_wait(bar, (jj >> 1) & 1);
+            PROF_T(tc3);
+            PROF_ADD(3, tc2, tc3);
+            // global winner: same decision in every warp (lane d looks at CTA d's candidate)
+            int p, wr;
+            {
+                const int cr = lane < (int)csize ? (int)s_cand[par][lane][0] : NOROW;
+                const double cv = (lane < (int)csize && cr != NOROW) ? fabs(s_cand[par][lane][2]) : 0.0;
+                const bool ok = cr != NOROW;
+                const unsigned long long ck = ok ? (unsigned long long)__double_as_longlong(cv) : 0ull;
+                const unsigned ch = (unsigned)(ck >> 32), cl = (unsigned)ck;
+                const unsigned GH = __reduce_max_sync(FULL, ch);
+                const unsigned GL = __reduce_max_sync(FULL, (ok && ch == GH) ? cl : 0u);
+                p = __reduce_min_sync(FULL, (ok && ch == GH && cl == GL) ? cr : NOROW);
+                const unsigned who = __ballot_sync(FULL, ok && cr == p);
+                wr = who ? __ffs(who) - 1 : 0;
+            }
+            const double *pr = &s_cand[par][wr][2];
+            const double pval = pr[0];
+            const double rcp = s_cand[par][wr][1];
+            if (tid == 0) {
+                s_piv[j] = p;
+                if (crank == 0) {
+                    ipiv[col0 + jj] = row0 + p + 1;
+                    if (pval == 0.0 && *info == 0) *info = col0 + jj + 1;
+                }
+            }
+            PROF_T(tc4);
+            PROF_ADD(4, tc3, tc4);
+            const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
+            const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
+            double pm[W];
 #pragma unroll
-            for (int c = 1; c < W; ++c) v[k][c - 1] = (c <= last) ? v[k][c] - l * pr[c] : v[k][c];
-            v[k][W - 1] = app;
+            for (int c = 1; c < W; ++c) pm[c] = (c <= last) ? pr[c] : 0.0;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = rbase + k * NT;
+                if (p != jj) {
+                    if (r == p) {  // the pivot row's old slot receives row jj
+#pragma unroll
+                        for (int c = 0; c < W; ++c) v[k][c] = s_rowj[par][c];
+                    } else if (r == jj) {
+#pragma unroll
+                        for (int c = 0; c < W; ++c) v[k][c] = pr[c];
+                    }
+                }
+                const bool active = (r > jj && r < m && pval != 0.0);
+                const double l = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
+                const double app = active ? l : v[k][0];
+#pragma unroll
+                for (int c = 1; c < W; ++c) v[k][c - 1] = v[k][c] - l * pm[c];
+                v[k][W - 1] = app;
+            }
+            PROF_T(tc5);
+            PROF_ADD(5, tc4, tc5);
         }
-    }
+        PROF_T(tL2);
+        // ---- 3. write the leaf back (slot W-w+c holds column c); the multipliers stay in registers for step 9 ----
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-        const int r = rbase + k * NT;
-        if (r < m) {
+        for (int k = 0; k < RPT; ++k) {
+            const int r = rbase + k * NT;
+            if (r >= lc0 && r < m) {
 #pragma unroll
-            for (int c = 0; c < W; ++c)
-                if (c >= W - w) a[(c - (W - w)) * lda + r] = v[k][c];
+                for (int c = 0; c < W; ++c)
+                    if (c >= W - w) a[(lc0 + c - (W - w)) * lda + r] = v[k][c];
+            }
         }
+        PROF_T(tL3);
+        PROF_ADD(6, tL2, tL3);
+        if (pw <= W) break;  // single-leaf panel: nothing else to do (uniform)
+        // ---- 4. CTA 0 applies the leaf's interchanges to the other columns of the panel ----
+        if (crank == 0) {
+            if (tid >= lc0 && tid < lc0 + W) {  // rows lc0..lc0+15 are final: keep L_ii for the triangular solve
+#pragma unroll
+                for (int c = 0; c < W; ++c) s_L[tid - lc0][c] = v[0][c];
+            }
+            __syncthreads();  // s_piv complete (written by tid 0 during the column steps)
+            if (tid < W) swap_plan(tid, lc0, w, s_piv, s_other, s_far);
+            __syncthreads();
+            if (tid < pw && (tid < lc0 || tid >= lc0 + w)) swap_group(a + tid * lda, lc0, w, s_other, s_far, dyn, NB, tid, 0);
+            __threadfence();
+        }
+        PROF_T(tL4);
+        PROF_ADD(7, tL3, tL4);
+        asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        PROF_T(tL5);
+        PROF_ADD(8, tL4, tL5);
+        const int rest0 = lc0 + W, ncols = pw - rest0;
+        if (ncols <= 0) break;  // last leaf (uniform)
+        // ---- 6. CTA 0: U(lc0:lc0+16, rest) = L_ii^{-1} * A(lc0:lc0+16, rest), one column per thread, in registers ----
+        if (crank == 0) {
+            if (tid >= rest0 && tid < pw) {
+                double x[W];
+                double *col = a + tid * lda + lc0;
+#pragma unroll
+                for (int t = 0; t < W; ++t) x[t] = col[t];
+#pragma unroll
+                for (int t = 0; t < W; ++t)
+#pragma unroll
+                    for (int q = t + 1; q < W; ++q) x[q] -= s_L[q][t] * x[t];
+#pragma unroll
+                for (int t = 0; t < W; ++t) col[t] = x[t];
+            }
+            __threadfence();
+        }
+        PROF_T(tL6);
+        PROF_ADD(9, tL5, tL6);
+        asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        PROF_T(tL7);
+        PROF_ADD(10, tL6, tL7);
+        // ---- 8. everybody stages the U block row, 9. and applies the rank-16 update to its own rows of the rest columns ----
+        for (int idx = tid; idx < W * ncols; idx += NT) {
+            const int t = idx % W, c = idx / W;
+            dyn[t * NB + c] = a[(rest0 + c) * lda + lc0 + t];
+        }
+        __syncthreads();
+        PROF_T(tL8);
+        PROF_ADD(11, tL7, tL8);
+        {
+            constexpr int CU = 16 / RPT;  // columns per batch: RPT*CU = 16 independent loads in flight per thread
+            bool rowok[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) rowok[k] = (rbase + k * NT >= rest0) && (rbase + k * NT < m);
+            for (int c0 = 0; c0 < ncols; c0 += CU) {
+                double x[RPT][CU];
+#pragma unroll
+                for (int k = 0; k < RPT; ++k)
+#pragma unroll
+                    for (int u = 0; u < CU; ++u)
+                        x[k][u] = (rowok[k] && c0 + u < ncols) ? a[(rest0 + c0 + u) * lda + rbase + k * NT] : 0.0;
+#pragma unroll
+                for (int t = 0; t < W; ++t)
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) {
+                        const double ut = dyn[t * NB + c0 + u];
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) x[k][u] -= v[k][t] * ut;
+                    }
+#pragma unroll
+                for (int k = 0; k < RPT; ++k)
+#pragma unroll
+                    for (int u = 0; u < CU; ++u)
+                        if (rowok[k] && c0 + u < ncols) a[(rest0 + c0 + u) * lda + rbase + k * NT] = x[k][u];
+            }
+        }
+        __syncthreads();  // dyn is reused by the next leaf's interchanges
+        PROF_T(tL9);
+        PROF_ADD(12, tL8, tL9);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// DLASWP for the <= 16 pivots of one leaf, applied to every column outside [skip0, skip1): one thread per column.
-// All loads are issued up front (16 contiguous top rows + the distinct far rows), the interchange sequence is then
-// replayed on the thread's private copy in shared memory, and everything is written back: one memory round trip
-// instead of 16 dependent ones.
+// DLASWP for the cnt (<= 128) pivots of one panel, applied to every column outside [skip0, skip1): one thread per column,
+// the pivots are replayed in groups of 16 (one memory round trip per group, see swap_group).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) laswp_leaf_kernel(double *a, long long lda, long long sa, int ncols, int skip0, int skip1, int k1,
-                                                          int cnt, const int32_t *ipiv, long long sp) {
+__global__ void __launch_bounds__(256) laswp_panel_kernel(double *a, long long lda, long long sa, int ncols, int skip0, int skip1, int k1,
+                                                           int cnt, const int32_t *ipiv, long long sp) {
     extern __shared__ double S[];  // S[slot * 256 + tid], slots 0..15 top rows, 16..31 far rows
-    __shared__ int other[LEAF];    // slot swapped with top slot j
-    __shared__ int farrow[LEAF];   // far row loaded into slot 16+j (or -1)
+    __shared__ int piv[LEAF], other[LEAF], farrow[LEAF];
     a += blockIdx.y * sa;
     ipiv += blockIdx.y * sp;
     const int tid = threadIdx.x;
-    if (tid < LEAF) {
-        int o = tid, f = -1;
-        if (tid < cnt) {
-            const int p = ipiv[k1 + tid] - 1;
-            if (p < k1 + cnt) o = p - k1;
-            else {
-                int first = tid;
-                for (int i = 0; i < tid; ++i)
-                    if (ipiv[k1 + i] - 1 == p) { first = i; break; }
-                o = LEAF + first;
-                if (first == tid) f = p;
-            }
-        }
-        other[tid] = o;
-        farrow[tid] = f;
-    }
-    __syncthreads();
     int col = blockIdx.x * 256 + tid;
     if (col >= skip0) col += skip1 - skip0;
-    if (col >= ncols) return;
-    double *c = a + col * lda;
-    for (int j = 0; j < cnt; ++j) S[j * 256 + tid] = c[k1 + j];
-    for (int j = 0; j < cnt; ++j)
-        if (farrow[j] >= 0) S[(LEAF + j) * 256 + tid] = c[farrow[j]];
-    for (int j = 0; j < cnt; ++j) {
-        const int o = other[j];
-        if (o != j) {
-            const double t = S[j * 256 + tid];
-            S[j * 256 + tid] = S[o * 256 + tid];
-            S[o * 256 + tid] = t;
-        }
+    for (int g0 = 0; g0 < cnt; g0 += LEAF) {
+        const int gc = min(LEAF, cnt - g0);
+        __syncthreads();
+        if (tid < LEAF) piv[tid] = tid < gc ? ipiv[k1 + g0 + tid] - 1 : 0;
+        __syncthreads();
+        if (tid < LEAF) swap_plan(tid, k1 + g0, gc, piv, other, farrow);
+        __syncthreads();
+        if (col < ncols) swap_group(a + col * lda, k1 + g0, gc, other, farrow, S, 256, tid, 0);
     }
-    for (int j = 0; j < cnt; ++j) c[k1 + j] = S[j * 256 + tid];
-    for (int j = 0; j < cnt; ++j)
-        if (farrow[j] >= 0) c[farrow[j]] = S[(LEAF + j) * 256 + tid];
 }
 
 // General DLASWP (used by getrs on the right-hand sides): for i in [k1,k2): swap rows i and ipiv[i]-1, thread per column.
@@ -383,17 +542,20 @@ struct Mat {
     double *at(int i, int j) const { return a + (size_t)j * lda + i; }
 };
 
+constexpr int PANEL_DYN_SMEM = 2 * LEAF * NB * (int)sizeof(double);
+
 template <int NT, int RPT>
-int launch_leaf(const Mat &A, int i0, int j0, int m, int w, int32_t *ipiv, long long sp, int32_t *info, int csize) {
+int launch_panel(const Mat &A, int i0, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, int csize) {
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(lu_leaf_kernel<NT, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_DYN_SMEM));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize, A.batch, 1);
     cfg.blockDim = dim3(NT, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = PANEL_DYN_SMEM;
     cfg.stream = ctx().stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -402,32 +564,33 @@ int launch_leaf(const Mat &A, int i0, int j0, int m, int w, int32_t *ipiv, long 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_leaf_kernel<NT, RPT>, A.at(i0, j0), (long long)A.lda, A.stride, m, w, i0, j0, ipiv, sp, info));
+    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT>, A.at(i0, j0), (long long)A.lda, A.stride, m, pw, i0, j0, ipiv, sp, info));
     count_launch();
     return FM_OK;
 }
 
-int leaf(const Mat &A, int i0, int j0, int m, int w, int32_t *ipiv, long long sp, int32_t *info) {
-    if (m <= 256) return launch_leaf<256, 1>(A, i0, j0, m, w, ipiv, sp, info, 1);
-    if (m <= 512) return launch_leaf<256, 2>(A, i0, j0, m, w, ipiv, sp, info, 1);
+// factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch
+int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info) {
+    if (m <= 256) return launch_panel<256, 1>(A, j0, j0, m, pw, ipiv, sp, info, 1);
+    if (m <= 512) return launch_panel<256, 2>(A, j0, j0, m, pw, ipiv, sp, info, 1);
     int csize = 1;
     while (csize * 1024 < m) csize *= 2;
     if (csize > MAXC)
         return set_error(FM_ERR_ARG, "getrf: panels taller than %d rows are not supported yet (m=%d)", MAXC * 1024, m);
-    return launch_leaf<256, 4>(A, i0, j0, m, w, ipiv, sp, info, csize);
+    return launch_panel<256, 4>(A, j0, j0, m, pw, ipiv, sp, info, csize);
 }
 
-// apply the pivots [k1, k1+cnt) of one leaf to all columns except [skip0, skip1)
-int laswp_leaf(const Mat &A, int ncols_total, int skip0, int skip1, int k1, int cnt, const int32_t *ipiv, long long sp) {
+// apply the pivots [k1, k1+cnt) of one panel to all columns except [skip0, skip1)
+int laswp_panel(const Mat &A, int ncols_total, int skip0, int skip1, int k1, int cnt, const int32_t *ipiv, long long sp) {
     const int ncols = ncols_total - (skip1 - skip0);
     if (ncols <= 0 || cnt <= 0) return FM_OK;
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(laswp_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LEAF * 256 * (int)sizeof(double)));
+        FM_CUDA(cudaFuncSetAttribute(laswp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LEAF * 256 * (int)sizeof(double)));
         attr = true;
     }
     dim3 grid(ceil_div(ncols, 256), A.batch);
-    laswp_leaf_kernel<<<grid, 256, 2 * LEAF * 256 * sizeof(double), ctx().stream>>>(A.a, A.lda, A.stride, ncols_total, skip0, skip1, k1, cnt, ipiv, sp);
+    laswp_panel_kernel<<<grid, 256, 2 * LEAF * 256 * sizeof(double), ctx().stream>>>(A.a, A.lda, A.stride, ncols_total, skip0, skip1, k1, cnt, ipiv, sp);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -466,21 +629,6 @@ int gemm_update(const Mat &A, int ci, int cj, int m, int n, int k, int ai, int a
                    A.stride, A.batch, ep);
 }
 
-// factor columns [j0, j0+w) of A (rows j0..m), w <= NB, recursively (DGETRF2-style splitting).  Each 16-column leaf
-// applies its row interchanges to ALL other columns of the matrix right away, so no interchanges are pending anywhere.
-int panel(const Mat &A, int m, int n, int j0, int w, int32_t *ipiv, long long sp, int32_t *info) {
-    if (w <= LEAF) {
-        FM_TRY(leaf(A, j0, j0, m - j0, w, ipiv, sp, info));
-        return laswp_leaf(A, n, j0, j0 + w, j0, w, ipiv, sp);
-    }
-    int w1 = ((w / 2 + LEAF - 1) / LEAF) * LEAF;
-    const int w2 = w - w1;
-    FM_TRY(panel(A, m, n, j0, w1, ipiv, sp, info));
-    FM_TRY(trsm<false>(w1, w2, A.at(j0, j0), A.lda, A.stride, A.at(j0, j0 + w1), A.lda, A.stride, A.batch));
-    FM_TRY(gemm_update(A, j0 + w1, j0 + w1, m - j0 - w1, w2, w1, j0 + w1, j0, j0, j0 + w1));
-    return panel(A, m, n, j0 + w1, w2, ipiv, sp, info);
-}
-
 }  // namespace
 
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch) {
@@ -493,7 +641,8 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     const int mn = m < n ? m : n;
     for (int j0 = 0; j0 < mn; j0 += NB) {
         const int jb = (mn - j0) < NB ? (mn - j0) : NB;
-        FM_TRY(panel(A, m, n, j0, jb, ipiv, sp, info));
+        FM_TRY(panel_factor(A, j0, m - j0, jb, ipiv, sp, info));
+        FM_TRY(laswp_panel(A, n, j0, j0 + jb, j0, jb, ipiv, sp));
         const int nr = n - j0 - jb;
         if (nr > 0) {
             FM_TRY(trsm<false>(jb, nr, A.at(j0, j0), lda, sa, A.at(j0, j0 + jb), lda, sa, batch));
@@ -533,6 +682,18 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     }
     return FM_OK;
 }
+
+#ifdef FM_LU_PROF
+}  // namespace fm
+extern "C" int fm_lu_prof(long long *out32) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, fm::g_prof, sizeof(long long) * 32);
+    long long z[32] = {};
+    cudaMemcpyToSymbol(fm::g_prof, z, sizeof(z));
+    return 0;
+}
+namespace fm {
+#endif
 
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out) {
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "det: bad dimensions");

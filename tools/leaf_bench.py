@@ -12,7 +12,7 @@ def t_ms(fn, reps=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 for m in (256, 1024, 2048, 4096, 8192):
-    for w in (1, 4, 16):
+    for w in (1, 16, 32, 128):
         g = torch.Generator(device="cuda"); g.manual_seed(3)
         t = torch.randn(m * w, dtype=torch.float64, device="cuda", generator=g)
         piv = fm.Pivots(16)
