@@ -101,6 +101,8 @@ def cpu_reference_sample(n_times: int, n_expm: int, steps: int, warmup: int):
     from oracle.flomat_oracle import Flomat, default_provider
 
     prov = default_provider()
+    if hasattr(prov, "_set"):  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses all the host threads it can
+        prov._set(os.cpu_count() or 1)
     F = Flomat(prov)
     rng = np.random.default_rng(6001)
     a = np.asfortranarray(rng.standard_normal((n_times, n_times)))
@@ -271,7 +273,7 @@ def run_gpu(args):
         cs.close()
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # CPU baseline: rank 0 at N=1 only
         cpu = cpu_reference_sample(args.ref_n_times, args.ref_n_expm, 1, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

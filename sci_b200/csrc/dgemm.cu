@@ -69,6 +69,7 @@ struct EpiParams {
     double *peer[7];
     const int32_t *active_until;  // optional per-item round limit (batched squaring in expm)
     int round;
+    unsigned zero;  // always 0; opaque to the compiler (see the stage-release token in the consumer loop)
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -193,6 +194,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(full_bar(stage), phase);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + Cfg::A_STAGE;
+            unsigned tok = 0;  // folds in one word of every LDS result of this stage (see the release below)
 #pragma unroll
             for (int kb = 0; kb < BK / 16; ++kb) {
 #pragma unroll
@@ -200,13 +202,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     double bf[NT][2];
 #pragma unroll
                     for (int ni = 0; ni < NT; ++ni)
+                    {
                         lds128((sb + kb * Cfg::B_BOX_BYTES + b_off + ni * 1024) ^ (jp << 6), bf[ni][0], bf[ni][1]);
+                        tok ^= (unsigned)__double2loint(bf[ni][1]);
+                    }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         double af[MT];
 #pragma unroll
                         for (int c = 0; c < R; ++c)
+                        {
                             lds128((sa + a_off[e] + kb * 2048 + jp * 1024) ^ ((c * GPB) << 4), af[2 * c], af[2 * c + 1]);
+                            tok ^= (unsigned)__double2loint(af[2 * c + 1]);
+                        }
 #pragma unroll
                         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -214,8 +222,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            // Release the stage only after every LDS of the stage has RETURNED: the arrive's address depends (through a runtime
+            // zero mask) on one word of each LDS result, so the scoreboard holds it back.  Without this ptxas hoists the arrive
+            // above the last DMMAs, and when the LSU is congested (NVLink stores of other warps in the fused multi-GPU epilogue)
+            // the TMA refill overtakes in-flight LDS: rare wrong A fragments.  Found with 2 GPUs, see DESIGN.md section 6.
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar(stage));
+            if (lane == 0) mbar_arrive(empty_bar(stage) + (tok & ep.zero));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
 
@@ -439,6 +451,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     for (int r = 0; r < 7; ++r) ep.peer[r] = r < epi.npeers ? epi.peers[r] : nullptr;
     ep.active_until = epi.active_until;
     ep.round = epi.round;
+    ep.zero = 0u;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&

@@ -359,3 +359,46 @@ def test_expm_semigroup_property_large(fm):
     E2 = fm.expm(up(fm, 2.0 * a))
     sq = fm.times(E1, E1)
     assert fm.norm(fm.minus(sq, E2), 1) / fm.norm(E2, 1) <= tol(n)
+
+
+# ---------------------------------------------------------------- multi-GPU (needs >= 2 B200; skipped on a 1-GPU box)
+def test_colshard_fused_two_gpus(fm, tmp_path):
+    """Column-sharded times with the all-gather fused into the GEMM epilogue (peer stores over NVLink), 2 ranks:
+    every rank's assembled C must equal the producer's copy bit for bit and match an independent product."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import textwrap
+
+    if fm.load().fm_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), os.pardir))
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {root!r})
+        import torch, torch.distributed as dist
+        import sci_b200 as fm
+        from sci_b200.multigpu import ColShardTimes
+        rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local); fm.init(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        for n in (1024, 8192):
+            cs = ColShardTimes(n, 2, rank)
+            for _ in range(3):
+                cs.c_tensor().fill_(-7.0); torch.cuda.synchronize(); dist.barrier()
+                cs.step_fused(); torch.cuda.synchronize(); dist.barrier()
+                assert cs.verify(), ("fused", n)
+            cs.c_tensor().fill_(-7.0); cs.step_nccl(); torch.cuda.synchronize(); dist.barrier()
+            assert cs.verify(), ("nccl", n)
+            cs.close()
+        dist.destroy_process_group(); print("ok", rank)
+    """))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o
