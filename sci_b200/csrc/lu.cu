@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -150,19 +151,19 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
     const int rbase = crank * ROWS + tid;  // panel-local rows rbase + k*NT, k < RPT
 
     extern __shared__ double dyn[];  // 32 x 128 doubles: swap staging, later the U block s_U[t*NB + c]
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ unsigned s_whi[NWARP], s_wlo[NWARP];
-    __shared__ int s_wrow[NWARP];
-    __shared__ double s_wdata[NWARP][W + 1];  // candidate row of each warp (+ reciprocal of its pivot)
-    __shared__ double s_cand[2][MAXC][PAY];
-    __shared__ double s_rowj[2][W];
-    __shared__ double s_myrowj[W];
+    __shared__ __align__(8) unsigned long long s_bar[3];
+    __shared__ unsigned s_whi[2][NWARP], s_wlo[2][NWARP];
+    __shared__ int s_wrow[2][NWARP];
+    __shared__ double s_wdata[2][NWARP][W + 1];  // candidate row of each warp (+ reciprocal of its pivot)
+    __shared__ double s_cand[3][MAXC][PAY];      // triple buffered: column q uses buffer q % 3 (see the pipelining note below)
+    __shared__ double s_rowj[3][W];
+    __shared__ double s_myrowj[2][W];
     __shared__ double s_L[W][W + 1];
     __shared__ int s_piv[W], s_other[W], s_far[W];
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[1])) : "memory");
+#pragma unroll
+        for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -179,81 +180,101 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
 #pragma unroll
             for (int c = 0; c < W; ++c) v[k][c] = (r >= lc0 && r < m && c < w) ? a[(lc0 + c) * lda + r] : 0.0;
         }
-        // ---- 2. column steps.  The row is ROTATED one slot per step so that all register indices stay static and the loop
-        //         is not unrolled: slot 0 = current column, finished values are appended at slot 15. ----
         PROF_T(tL1);
         PROF_ADD(0, tL0, tL1);
-#pragma unroll 1
-        for (int j = 0; j < w; ++j) {
-            PROF_T(tc0);
-            const int jj = lc0 + j;  // panel-local index of the pivot position
-            const int par = jj & 1;
-            const uint32_t bar = lsmem(&s_bar[par]);
+        // ---- 2. column steps.
+        //  * The row is ROTATED one slot per step so that all register indices stay static and the loop is not unrolled:
+        //    slot 0 = current column, updated trailing entries move down one slot, the finished value is appended at slot 15.
+        //  * The loop is SOFTWARE PIPELINED: as soon as pivot q is known every thread updates only the next column (one FMA
+        //    per row), the candidates for pivot q+1 are reduced and pushed, and the remaining 14 FMAs per row of update q run
+        //    while that push is in flight.  A CTA may therefore still read the candidates of pivot q while its peers already
+        //    push pivot q+2: candidate buffers and mbarriers are triple buffered (q % 3).
+        double l[RPT], app[RPT], pm[W];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) { l[k] = 0.0; app[k] = 0.0; }
+#pragma unroll
+        for (int c = 0; c < W; ++c) pm[c] = 0.0;
+
+        // stage the candidates of panel column q: x0[k] = value of column q in row k of this thread; when `upd` the row to
+        // publish is the row AFTER update q-1 (computed on the fly for the one publishing lane only)
+        auto candidate_and_push = [&](const int q, const double (&x0)[RPT], const bool upd) {
+            const int buf = q % 3, wb = q & 1;
+            const uint32_t bar = lsmem(&s_bar[buf]);
             if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
-            // candidate among this thread's rows still in play; lowest row wins ties (IDAMAX)
             double val = -1.0, piv0 = 1.0;
             int row = NOROW, kb = 0;
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
                 const int r = rbase + k * NT;
-                const double x = fabs(v[k][0]);
-                if (r >= jj && r < m && x > val) { val = x; row = r; kb = k; piv0 = v[k][0]; }
+                const double x = fabs(x0[k]);
+                if (r >= q && r < m && x > val) { val = x; row = r; kb = k; piv0 = x0[k]; }
             }
             const double myrcp = 1.0 / piv0;  // issued early: its latency hides behind the REDUX chain
-            // warp argmax on the bit pattern of |x| (monotonic for non-negative doubles): three REDUX instead of a shuffle tree
+            // warp argmax on the bit pattern of |x| (monotonic for non-negative doubles); lowest row wins ties (IDAMAX)
             const unsigned long long key = row != NOROW ? (unsigned long long)__double_as_longlong(val) : 0ull;
             const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
             const unsigned mh = __reduce_max_sync(FULL, hi);
             const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
             const int wrow = __reduce_min_sync(FULL, (hi == mh && lo == ml) ? row : NOROW);
+            auto row_value = [&](int k, int c) -> double {  // slot c of row k after the pending update (if any)
+                if (!upd) return v[k][c];
+                return c < W - 1 ? v[k][c + 1] - l[k] * pm[c + 1] : app[k];
+            };
             if (row == wrow && row != NOROW) {  // exactly one lane: publish the warp's candidate row
 #pragma unroll
                 for (int k = 0; k < RPT; ++k)
                     if (kb == k) {
 #pragma unroll
-                        for (int c = 0; c < W; ++c) s_wdata[warp][c] = v[k][c];
+                        for (int c = 0; c < W; ++c) s_wdata[wb][warp][c] = row_value(k, c);
                     }
-                s_wdata[warp][W] = myrcp;
+                s_wdata[wb][warp][W] = myrcp;
             }
-            if (lane == 0) { s_whi[warp] = mh; s_wlo[warp] = ml; s_wrow[warp] = wrow; }
-            if (crank == 0 && tid == jj) {  // row jj lives in CTA 0, thread jj, k = 0 (jj < 128 <= NT)
+            if (lane == 0) { s_whi[wb][warp] = mh; s_wlo[wb][warp] = ml; s_wrow[wb][warp] = wrow; }
+            if (crank == 0 && tid == q) {  // row q lives in CTA 0, thread q, k = 0 (q < 128 <= NT)
 #pragma unroll
-                for (int c = 0; c < W; ++c) s_myrowj[c] = v[0][c];
+                for (int c = 0; c < W; ++c) s_myrowj[wb][c] = row_value(0, c);
             }
             __syncthreads();
-            PROF_T(tc1);
-            PROF_ADD(1, tc0, tc1);
-            {
-                // every warp finds the CTA's candidate (redundantly) and pushes it to the destination CTAs warp, warp+NWARP, ...
-                const unsigned h2 = lane < NWARP ? s_whi[lane] : 0u, l2 = lane < NWARP ? s_wlo[lane] : 0u;
-                const int r2 = lane < NWARP ? s_wrow[lane] : NOROW;
-                const unsigned MH = __reduce_max_sync(FULL, r2 != NOROW ? h2 : 0u);
-                const unsigned ML = __reduce_max_sync(FULL, (r2 != NOROW && h2 == MH) ? l2 : 0u);
-                const int MR = __reduce_min_sync(FULL, (r2 != NOROW && h2 == MH && l2 == ML) ? r2 : NOROW);
-                const unsigned who = __ballot_sync(FULL, r2 == MR && r2 != NOROW);
-                const int src = who ? __ffs(who) - 1 : 0;
-                double payload = 0.0;
-                if (lane == 0) payload = (double)MR;
-                else if (lane < PAY) payload = (MR == NOROW) ? 0.0 : (lane == 1 ? s_wdata[src][W] : s_wdata[src][lane - 2]);
-                const double rowj_payload = (crank == 0 && lane < W) ? s_myrowj[lane] : 0.0;
-                const uint32_t dst = lsmem(&s_cand[par][crank][lane < PAY ? lane : 0]);
-                const uint32_t dstj = lsmem(&s_rowj[par][lane < W ? lane : 0]);
-                for (uint32_t d = warp; d < csize; d += NWARP) {
-                    const uint32_t rbar = mapa(bar, d);
-                    if (lane < PAY) st_async(mapa(dst, d), payload, rbar);
-                    if (crank == 0 && lane < W) st_async(mapa(dstj, d), rowj_payload, rbar);
-                }
+            // every warp finds the CTA's candidate (redundantly) and pushes it to the destination CTAs warp, warp+NWARP, ...
+            const unsigned h2 = lane < NWARP ? s_whi[wb][lane] : 0u, l2 = lane < NWARP ? s_wlo[wb][lane] : 0u;
+            const int r2 = lane < NWARP ? s_wrow[wb][lane] : NOROW;
+            const unsigned MH = __reduce_max_sync(FULL, r2 != NOROW ? h2 : 0u);
+            const unsigned ML = __reduce_max_sync(FULL, (r2 != NOROW && h2 == MH) ? l2 : 0u);
+            const int MR = __reduce_min_sync(FULL, (r2 != NOROW && h2 == MH && l2 == ML) ? r2 : NOROW);
+            const unsigned who = __ballot_sync(FULL, r2 == MR && r2 != NOROW);
+            const int src = who ? __ffs(who) - 1 : 0;
+            double payload = 0.0;
+            if (lane == 0) payload = (double)MR;
+            else if (lane < PAY) payload = (MR == NOROW) ? 0.0 : (lane == 1 ? s_wdata[wb][src][W] : s_wdata[wb][src][lane - 2]);
+            const double rowj_payload = (crank == 0 && lane < W) ? s_myrowj[wb][lane] : 0.0;
+            const uint32_t dst = lsmem(&s_cand[buf][crank][lane < PAY ? lane : 0]);
+            const uint32_t dstj = lsmem(&s_rowj[buf][lane < W ? lane : 0]);
+            for (uint32_t d = warp; d < csize; d += NWARP) {
+                const uint32_t rbar = mapa(bar, d);
+                if (lane < PAY) st_async(mapa(dst, d), payload, rbar);
+                if (crank == 0 && lane < W) st_async(mapa(dstj, d), rowj_payload, rbar);
             }
-            PROF_T(tc2);
-            PROF_ADD(2, tc1, tc2);
-            bar_wait(bar, (jj >> 1) & 1);
+        };
+
+        {
+            double x0[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) x0[k] = v[k][0];
+            candidate_and_push(lc0, x0, false);
+        }
+#pragma unroll 1
+        for (int j = 0; j < w; ++j) {
+            PROF_T(tc0);
+            const int jj = lc0 + j;  // panel-local index of the pivot position
+            const int buf = jj % 3;
+            bar_wait(lsmem(&s_bar[buf]), (jj / 3) & 1);
             PROF_T(tc3);
-            PROF_ADD(3, tc2, tc3);
+            PROF_ADD(3, tc0, tc3);
             // global winner: same decision in every warp (lane d looks at CTA d's candidate)
             int p, wr;
             {
-                const int cr = lane < (int)csize ? (int)s_cand[par][lane][0] : NOROW;
-                const double cv = (lane < (int)csize && cr != NOROW) ? fabs(s_cand[par][lane][2]) : 0.0;
+                const int cr = lane < (int)csize ? (int)s_cand[buf][lane][0] : NOROW;
+                const double cv = (lane < (int)csize && cr != NOROW) ? fabs(s_cand[buf][lane][2]) : 0.0;
                 const bool ok = cr != NOROW;
                 const unsigned long long ck = ok ? (unsigned long long)__double_as_longlong(cv) : 0ull;
                 const unsigned ch = (unsigned)(ck >> 32), cl = (unsigned)ck;
@@ -263,9 +284,9 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
                 const unsigned who = __ballot_sync(FULL, ok && cr == p);
                 wr = who ? __ffs(who) - 1 : 0;
             }
-            const double *pr = &s_cand[par][wr][2];
+            const double *pr = &s_cand[buf][wr][2];
             const double pval = pr[0];
-            const double rcp = s_cand[par][wr][1];
+            const double rcp = s_cand[buf][wr][1];
             if (tid == 0) {
                 s_piv[j] = p;
                 if (crank == 0) {
@@ -277,7 +298,6 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
             PROF_ADD(4, tc3, tc4);
             const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
             const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
-            double pm[W];
 #pragma unroll
             for (int c = 1; c < W; ++c) pm[c] = (c <= last) ? pr[c] : 0.0;
 #pragma unroll
@@ -286,21 +306,32 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
                 if (p != jj) {
                     if (r == p) {  // the pivot row's old slot receives row jj
 #pragma unroll
-                        for (int c = 0; c < W; ++c) v[k][c] = s_rowj[par][c];
+                        for (int c = 0; c < W; ++c) v[k][c] = s_rowj[buf][c];
                     } else if (r == jj) {
 #pragma unroll
                         for (int c = 0; c < W; ++c) v[k][c] = pr[c];
                     }
                 }
                 const bool active = (r > jj && r < m && pval != 0.0);
-                const double l = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
-                const double app = active ? l : v[k][0];
+                l[k] = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
+                app[k] = active ? l[k] : v[k][0];
+            }
+            if (j + 1 < w) {  // look ahead: next column first, its candidates go out before the rest of this update
+                double x0[RPT];
 #pragma unroll
-                for (int c = 1; c < W; ++c) v[k][c - 1] = v[k][c] - l * pm[c];
-                v[k][W - 1] = app;
+                for (int k = 0; k < RPT; ++k) x0[k] = v[k][1] - l[k] * pm[1];
+                candidate_and_push(jj + 1, x0, true);
             }
             PROF_T(tc5);
-            PROF_ADD(5, tc4, tc5);
+            PROF_ADD(1, tc4, tc5);
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+#pragma unroll
+                for (int c = 1; c < W; ++c) v[k][c - 1] = v[k][c] - l[k] * pm[c];
+                v[k][W - 1] = app[k];
+            }
+            PROF_T(tc6);
+            PROF_ADD(5, tc5, tc6);
         }
         PROF_T(tL2);
         // ---- 3. write the leaf back (slot W-w+c holds column c); the multipliers stay in registers for step 9 ----
@@ -569,15 +600,18 @@ int launch_panel(const Mat &A, int i0, int j0, int m, int pw, int32_t *ipiv, lon
     return FM_OK;
 }
 
-// factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch
+// factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch.  One row per thread whenever the cluster
+// (<= 16 CTAs) can cover the panel: the column step is latency/issue bound, so fewer rows per thread is faster.
 int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info) {
-    if (m <= 256) return launch_panel<256, 1>(A, j0, j0, m, pw, ipiv, sp, info, 1);
-    if (m <= 512) return launch_panel<256, 2>(A, j0, j0, m, pw, ipiv, sp, info, 1);
-    int csize = 1;
-    while (csize * 1024 < m) csize *= 2;
-    if (csize > MAXC)
-        return set_error(FM_ERR_ARG, "getrf: panels taller than %d rows are not supported yet (m=%d)", MAXC * 1024, m);
-    return launch_panel<256, 4>(A, j0, j0, m, pw, ipiv, sp, info, csize);
+    auto pow2_ctas = [](int rows, int per_cta) {
+        int cs = 1;
+        while (cs * per_cta < rows) cs *= 2;
+        return cs;
+    };
+    if (m <= 4096) return launch_panel<256, 1>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 256));
+    if (m <= 8192) return launch_panel<256, 2>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 512));
+    if (m <= 16384) return launch_panel<256, 4>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 1024));
+    return set_error(FM_ERR_ARG, "getrf: panels taller than 16384 rows are not supported yet (m=%d)", m);
 }
 
 // apply the pivots [k1, k1+cnt) of one panel to all columns except [skip0, skip1)

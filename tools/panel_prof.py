@@ -5,10 +5,10 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), os.pa
 import torch, sci_b200 as fm
 fm.init(0); lib = fm.load()
 lib.fm_lu_prof.argtypes = [ctypes.c_void_p]
-names = ["leaf load", "col: candidate+publish+sync", "col: warp0 reduce+push", "col: mbarrier wait", "col: winner scan", "col: update",
+names = ["leaf load", "col: pm+swap+l + next candidate/publish/sync/push", "(unused)", "col: mbarrier wait", "col: winner scan", "col: rest of update",
          "leaf store", "swap (cta0)", "cluster barrier 1", "trsm (cta0)", "cluster barrier 2", "stage U", "rest update"]
 buf = (ctypes.c_longlong * 32)()
-for m, w in [(256, 16), (1024, 16), (8192, 16), (256, 128), (1024, 128), (8192, 128)]:
+for m, w in [(1024, 128), (8192, 128)]:
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     t = torch.randn(m * w, dtype=torch.float64, device="cuda", generator=g)
     piv = fm.Pivots(128)
