@@ -21,6 +21,7 @@
 // a plain smem-tiled DMMA kernel: same arithmetic, no fast path.  There is no CPU or library fallback.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace fm {
 namespace {
@@ -87,14 +88,15 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
 // ---------------------------------------------------------------------------------------------
 // TMA + DMMA persistent kernel (NN)
 // ---------------------------------------------------------------------------------------------
-template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
+template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_, int CTAS_PER_SM_ = 1>
 struct GemmCfg {
-    static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_, CTAS_PER_SM = CTAS_PER_SM_;
     static constexpr int NW = WGM * WGN;            // consumer warps
     // Registers are allocated to a CTA in units of 4 warps, so the producer gets a whole warpgroup (3 of its warps exit
     // at once) and hands its registers to the consumers with setmaxnreg, the canonical warp-specialised layout.
     static constexpr int THREADS = (NW + 4) * 32;
-    static constexpr int REG_PRODUCER = 40, REG_CONSUMER = 232;  // 384 threads: 128*40 + 256*232 <= 65536
+    // 384 threads, 1 CTA/SM: 128*40 + 256*232 <= 65536;   256 threads, 2 CTAs/SM: 2*(128*40 + 128*216) = 65536
+    static constexpr int REG_PRODUCER = 40, REG_CONSUMER = CTAS_PER_SM_ == 1 ? 232 : 216;
     static constexpr int WTM = BM / WGM, WTN = BN / WGN;
     static constexpr int MT = WTM / 8, NT = WTN / 8;  // m8n8 tiles per warp
     static constexpr int R = WTM / 16;                // 16-byte A loads per thread per k
@@ -109,7 +111,7 @@ struct GemmCfg {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double *__restrict__ C,
                  long long ldc, long long sc, int M, int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams ep,
                  int vec_ok) {
@@ -236,6 +238,52 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n_base = tn * BN + wn0;
         double *Cz = C + z * sc;
         const long long zoff = z * sc;
+        if (vec_ok && (M & 1) == 0) {
+            // fast path (16-byte pairs everywhere): when beta != 0 all C loads of a batch of two n-tiles are issued before
+            // the first dependent FMA/store -- with load/use/store interleaved per element the stores fence the next load
+            // (possible aliasing) and every load pays a full memory latency: ~27 us per tile for rank-k updates.
+#pragma unroll
+            for (int nb2 = 0; nb2 < NT; nb2 += 2) {
+                double2 old[2][2][R];
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+#pragma unroll
+                    for (int x = 0; x < 2; ++x)
+#pragma unroll
+                        for (int c = 0; c < R; ++c) {
+                            const int n = n_base + 8 * (nb2 + d) + (x ? 4 + t : t), m = m_base + 2 * c * GPB;
+                            old[d][x][c] = (ep.beta != 0.0 && nb2 + d < NT && n < N && m < M)
+                                               ? *reinterpret_cast<const double2 *>(Cz + (long long)n * ldc + m)
+                                               : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+#pragma unroll
+                    for (int x = 0; x < 2; ++x)
+#pragma unroll
+                        for (int c = 0; c < R; ++c) {
+                            const int ni = nb2 + d;
+                            const int n = n_base + 8 * ni + (x ? 4 + t : t), m = m_base + 2 * c * GPB;
+                            if (ni >= NT || n >= N || m >= M) continue;
+                            double v0 = ep.alpha * acc[2 * c][ni][x];
+                            double v1 = ep.alpha * acc[2 * c + 1][ni][x];
+                            if (ep.beta != 0.0) {
+                                v0 += ep.beta * old[d][x][c].x;
+                                v1 += ep.beta * old[d][x][c].y;
+                            }
+                            if (ep.has_diag) {
+                                if (m == n) v0 += ep.diag;
+                                if (m + 1 == n) v1 += ep.diag;
+                            }
+                            *reinterpret_cast<double2 *>(Cz + (long long)n * ldc + m) = make_double2(v0, v1);
+#pragma unroll
+                            for (int r = 0; r < 7; ++r)
+                                if (r < ep.npeers)
+                                    *reinterpret_cast<double2 *>(ep.peer[r] + zoff + (long long)n * ldc + m) = make_double2(v0, v1);
+                        }
+            }
+            continue;
+        }
 #pragma unroll
         for (int ni = 0; ni < NT; ++ni) {
 #pragma unroll
@@ -403,6 +451,10 @@ int make_map(CUtensorMap *map, const double *base, long long rows, long long col
 }
 
 using CfgBig = GemmCfg<128, 128, 16, 2, 4, 6>;
+// 64x128 tiles, 4 consumer warps, two CTAs per SM: twice the tiles for problems that cannot fill 148 SMs with 128x128
+// tiles, and with two independent CTAs on an SM one CTA's epilogue (C read-modify-write) overlaps the other's main loop
+// -- the case of the rank-128/256 updates inside LU and the triangular solves.
+using CfgHalf = GemmCfg<64, 128, 16, 1, 4, 4, 2>;
 
 template <class Cfg>
 int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
@@ -418,7 +470,8 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     const int tiles_m = ceil_div(m, Cfg::BM), tiles_n = ceil_div(n, Cfg::BN);
     const long long total = (long long)tiles_m * tiles_n * batch;
     if (total > 0x7fffffffLL) return set_error(FM_ERR_ARG, "dgemm: too many tiles");
-    const int grid = (int)(total < ctx().sm_count ? total : ctx().sm_count);
+    const long long slots = (long long)ctx().sm_count * Cfg::CTAS_PER_SM;
+    const int grid = (int)(total < slots ? total : slots);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15u) == 0 && (ldc % 2) == 0 && (sc % 2) == 0) ? 1 : 0;
     int vec_all = vec_ok;
     for (int r = 0; r < ep.npeers; ++r)
@@ -428,6 +481,8 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
+
+bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer switch for A/B timing
 
 }  // namespace
 
@@ -456,7 +511,12 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         (batch == 1 || (sa % 2 == 0 && sb % 2 == 0)) && encode_fn() != nullptr;
-    if (tma_ok) return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+    if (tma_ok) {
+        const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
+        const bool half = (big_tiles < 2LL * ctx().sm_count || k <= 256) && g_half_enabled;
+        if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+        return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+    }
 
     dim3 grid(ceil_div(m, GB), ceil_div(n, GB), batch);
     if (grid.y > 65535 || grid.z > 65535) return set_error(FM_ERR_ARG, "dgemm(generic): grid too large");

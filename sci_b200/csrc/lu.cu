@@ -1,42 +1,38 @@
-// lu.cu -- blocked right-looking LU with partial pivoting and the solves built on it: the device side of
+// lu.cu -- recursive blocked LU with partial pivoting and the solves built on it: the device side of
 // dgetrf_ (flomat.rkt:1505, `flomat-lu!` :1525), dgesv_ (:2112, `mldivide` :3289 / `flomat-solve-many` :2145),
 // dgetri_ (:1754, `inv`) and `det` (:1837-1848).  Everything takes a batch dimension (equal strides) so the same
 // kernels serve the batched expm.
 //
 // Structure (B200):
-//   * outer panels of NB=128 columns; the trailing update A22 -= L21*U12 is the TMA/DMMA GEMM of dgemm.cu
-//     (>= 98% of the flops at n=8192);
-//   * a panel is factored recursively (128 -> 64 -> 32 -> 16 columns, like DGETRF2) so that the updates inside
-//     the panel are GEMM/TRSM shaped too;
-//   * the 16-column leaf is ONE kernel on ONE thread-block cluster: every thread owns one matrix row in
-//     registers (16 doubles), the per-column pivot search is a warp-shuffle argmax (lowest index wins ties, like
-//     IDAMAX) + one smem stage + one cluster barrier; the winning row is pushed to every CTA of the cluster
-//     through distributed shared memory, so a column step costs one cluster.sync, not a kernel launch;
-//   * row interchanges (DLASWP) and the small triangular solves run as their own kernels.
+//   * the column range is split recursively (DGETRF2 style) down to panels of NB=128 columns, so ~95% of the flops run
+//     in TMA/DMMA GEMMs (dgemm.cu) with a large inner dimension; triangular solves are recursive as well
+//     (GEMM + 128x128 leaf solves);
+//   * a 128-column panel is ONE kernel on ONE thread-block cluster (up to 16 CTAs): every thread owns matrix rows in
+//     registers, 16 columns at a time; a column step is a warp REDUX argmax -> CTA argmax -> st.async push of every
+//     CTA's candidate row into every CTA's shared memory (data and mbarrier signal travel together) -> the same global
+//     decision everywhere.  Pivoting inside the panel is IMPLICIT: rows never move while the panel is factored (a
+//     pivot row just drops out of play), each row tracks the position LAPACK's interchanges would have given it
+//     (needed for IDAMAX's lowest-index tie rule and for ipiv), and the elimination arithmetic is exactly DGETF2's;
+//   * the panel kernel emits ipiv (1-based, LAPACK) and the panel's NET row permutation as <= 256 (dst, src) pairs;
+//     one gather/scatter kernel applies it to any column range (all loads in flight at once instead of 128 dependent
+//     row swaps).  getrs rebuilds the same maps from ipiv.
 // ipiv is int32, 1-based, global row numbers (flomat.rkt:1457-1463).  info: first exactly-zero pivot, 1-based.
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <cfloat>
 #include <cstdlib>
-
-namespace cg = cooperative_groups;
+#include <algorithm>
 
 namespace fm {
 namespace {
 
-constexpr int NB = 128;       // outer panel width
-constexpr int LEAF = 16;      // columns factored by one leaf kernel
+constexpr int NB = 128;       // panel width
+constexpr int LEAF = 16;      // columns held in registers at a time
 constexpr int MAXC = 16;      // largest cluster
+constexpr int MAPN = 2 * NB;  // (dst, src) pairs per panel: NB pivot rows + up to NB displaced top rows
+constexpr int PAY = LEAF + 2; // candidate payload: packed (position, physical row) | 1/pivot | 16 row values
+constexpr int NOROW = 0x7fffffff;
+constexpr unsigned FULL = 0xffffffffu;
 
-// ---------------------------------------------------------------------------------------------
-// leaf: m x w (w <= 16) panel.  Every thread owns RPT matrix rows in registers; the rows are spread over the CTAs of one
-// thread-block cluster.  One column step costs ONE __syncthreads and ONE mbarrier wait:
-//   warp-shuffle argmax -> each warp publishes (|pivot|, row, the candidate row's 16 values) in smem -> __syncthreads ->
-//   warp 0 picks the CTA's candidate and pushes it into EVERY CTA of the cluster with st.async (DSMEM stores that
-//   complete a transaction count on the destination's mbarrier: data and signal travel together) -> everybody waits on
-//   its own mbarrier, picks the same global winner from its local copy of the candidates and updates its rows.
-// The old contents of row j (needed by the thread whose row is swapped out) ride along in the same push.
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lsmem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -58,88 +54,47 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-
-// Replays the interchanges piv[0..cnt) (absolute row numbers; pivot i swaps rows k1+i and piv[i]) on one column `c` whose
-// top rows k1..k1+15 and distinct far rows are staged in the caller's shared-memory slots S[slot*stride + lane]:
-// every load is issued before the first dependent use, so a group of 16 interchanges costs one memory round trip.
-// `first` = first pivot index to apply (own-leaf columns skip the pivots that were applied in registers).
-__device__ __forceinline__ void swap_group(double *c, int k1, int cnt, const int *other, const int *farrow, double *S, int stride, int lane,
-                                           int first) {
-    // stage through registers so that the (generic-pointer) shared stores cannot serialise the global loads
-    double top[LEAF], far[LEAF];
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j) top[j] = j < cnt ? c[k1 + j] : 0.0;
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j) far[j] = (j >= first && j < cnt && farrow[j] >= 0) ? c[farrow[j]] : 0.0;
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j) {
-        S[j * stride + lane] = top[j];
-        S[(LEAF + j) * stride + lane] = far[j];
-    }
-    for (int j = first; j < cnt; ++j) {
-        const int o = other[j];
-        if (o != j) {
-            const double t = S[j * stride + lane];
-            S[j * stride + lane] = S[o * stride + lane];
-            S[o * stride + lane] = t;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j) {
-        top[j] = S[j * stride + lane];
-        far[j] = S[(LEAF + j) * stride + lane];
-    }
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j)
-        if (j < cnt) c[k1 + j] = top[j];
-#pragma unroll
-    for (int j = 0; j < LEAF; ++j)
-        if (j >= first && j < cnt && farrow[j] >= 0) c[farrow[j]] = far[j];
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 8-byte global -> shared copy; !valid writes zeros without touching global memory
+__device__ __forceinline__ void cp_async8(uint32_t dst, const double *src, bool valid) {
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-// For pivots piv[0..cnt) of rows k1..k1+cnt: other[j] = slot exchanged with top slot j (a top slot, or LEAF + first
-// occurrence of that far row), farrow[j] = far row to load into slot LEAF+j (or -1).  Called by threads j < LEAF.
-__device__ __forceinline__ void swap_plan(int j, int k1, int cnt, const int *piv, int *other, int *farrow) {
-    int o = j, f = -1;
-    if (j < cnt) {
-        const int p = piv[j];
-        if (p < k1 + cnt) o = p - k1;
-        else {
-            int first = j;
-            for (int i = 0; i < j; ++i)
-                if (piv[i] == p) { first = i; break; }
-            o = LEAF + first;
-            if (first == j) f = p;
-        }
-    }
-    other[j] = o;
-    farrow[j] = f;
+// argmax over (key, then lowest position) of one candidate per lane; lanes without a candidate pass valid = false
+// (and key = 0).  Returns true in exactly one lane (the winner), or in none when no lane has a candidate.  The common
+// case (a unique maximum of the high word) costs one REDUX and one vote.
+__device__ __forceinline__ bool warp_argmax(unsigned long long key, int pos, bool valid = true) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned tie = __ballot_sync(FULL, valid && hi == mh);
+    if (__popc(tie) == 1) return valid && hi == mh;
+    if (tie == 0) return false;
+    const unsigned ml = __reduce_max_sync(FULL, (valid && hi == mh) ? lo : 0u);
+    const bool top = valid && hi == mh && lo == ml;
+    const int mp = __reduce_min_sync(FULL, top ? pos : NOROW);
+    return top && pos == mp;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel kernel: factors an m x pw panel (pw <= 128) in ONE launch on ONE cluster.  Leaves of 16 columns are factored
-// in registers (column steps as described above); between leaves, inside the same kernel, the leaf's interchanges are
-// applied to the other panel columns, the 16 x rest block row of U is obtained by a register-level triangular solve,
-// and every thread applies the rank-16 update to its own rows of the remaining panel columns (right-looking).
+// Panel kernel: factors an m x pw panel (pw <= 128) in ONE launch on ONE cluster, rows in their ORIGINAL places.
+// Physical panel row r belongs to CTA r / ROWS, thread (r % ROWS) % NT, slot (r % ROWS) / NT.
+// Per 16-column leaf:
+//   1. load the leaf columns of the rows still in play;
+//   2. 16 column steps (see candidate_and_push / the loop below), software pipelined: the candidates of step q+1 go out
+//      before the remaining 14 FMAs per row of update q are executed;
+//   3. store the leaf columns;
+//   4. every CTA forms U12 = L11^-1 * A[pivot rows, rest columns] redundantly (pivot rows are read through L2; L11 came
+//      with the candidate broadcasts) and applies the rank-16 update to its own rows of the remaining panel columns.
+// U12 is written back to the pivot rows one leaf later (after the cluster barrier that proves every CTA has read the old
+// values).  ipiv gets LAPACK's interchange sequence, map[] the panel's net permutation.
 // ---------------------------------------------------------------------------------------------
-constexpr int PAY = LEAF + 3;
-
-#ifdef FM_LU_PROF
-__device__ long long g_prof[32];
-#define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(slot, t0, t1) do { if (tid == 0 && crank == 0 && blockIdx.y == 0) g_prof[slot] += (t1) - (t0); } while (0)
-#else
-#define PROF_T(var) do {} while (0)
-#define PROF_ADD(slot, t0, t1) do {} while (0)
-#endif
-  // payload of a candidate: |pivot|, row, 1/pivot, the 16 row values
-
 template <int NT, int RPT>
 __global__ void __launch_bounds__(NT, 1)
-lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0, int col0, int32_t *ipiv, long long sp, int32_t *info) {
+lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, int32_t *ipiv, long long sp, int32_t *info, int2 *map,
+                long long smap) {
     constexpr int W = LEAF, NWARP = NT / 32, ROWS = NT * RPT;
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NOROW = 0x7fffffff;
     uint32_t crank, csize;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
@@ -147,259 +102,227 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
     a += item * sa;
     ipiv += item * sp;
     info += item;
+    map += item * smap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rbase = crank * ROWS + tid;  // panel-local rows rbase + k*NT, k < RPT
 
-    extern __shared__ double dyn[];  // 32 x 128 doubles: swap staging, later the U block s_U[t*NB + c]
+    extern __shared__ double dyn[];  // U12 blocks, double buffered: sU[buf][c * 16 + i]
     __shared__ __align__(8) unsigned long long s_bar[3];
-    __shared__ unsigned s_whi[2][NWARP], s_wlo[2][NWARP];
-    __shared__ int s_wrow[2][NWARP];
-    __shared__ double s_wdata[2][NWARP][W + 1];  // candidate row of each warp (+ reciprocal of its pivot)
-    __shared__ double s_cand[3][MAXC][PAY];      // triple buffered: column q uses buffer q % 3 (see the pipelining note below)
-    __shared__ double s_rowj[3][W];
-    __shared__ double s_myrowj[2][W];
-    __shared__ double s_L[W][W + 1];
-    __shared__ int s_piv[W], s_other[W], s_far[W];
+    __shared__ int s_wpos[2][NWARP];                         // position of each warp's candidate (NOROW: none)
+    __shared__ __align__(16) double s_wdata[2][NWARP][PAY];  // each warp's candidate: head | 1/pivot | 16 row values
+    __shared__ __align__(16) double s_cand[3][MAXC][PAY];    // every CTA's candidate; step q uses buffer q % 3
+    __shared__ double s_L[W][W + 1];                         // L11 of the current leaf (row j: multipliers of pivot row j)
+    __shared__ int s_pphys[NB];                              // physical panel row of every pivot
 
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    const uint32_t tx_bytes = csize * PAY * 8 + W * 8;
+    if (tid < 2 * NWARP) (&s_wpos[0][0])[tid] = NOROW;
+    cluster_arrive();
+    cluster_wait();
+    const uint32_t tx_bytes = csize * PAY * 8;
+    // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP (csize <= 16 <= 2 * NWARP): remote addresses of
+    // s_cand[0][crank][lane] and s_bar[0] there
+    uint32_t rcand[2], rbar[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t d = warp + i * NWARP;
+        rcand[i] = mapa(lsmem(&s_cand[0][crank][lane < PAY ? lane : 0]), d < csize ? d : 0);
+        rbar[i] = mapa(lsmem(&s_bar[0]), d < csize ? d : 0);
+    }
+
+    // pos >= 0: the row is in play and LAPACK would hold it at panel row `pos` now;  pos < 0: out of play (~pos = the
+    // pivot index it became, or a large value for rows beyond m)
+    int pos[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) pos[k] = (rbase + k * NT < m) ? rbase + k * NT : ~0x3fffffff;
+
+    int pend_lc0 = -1;  // leaf whose U12 still has to be written to the pivot rows
 
     for (int lc0 = 0; lc0 < pw; lc0 += W) {
         const int w = min(W, pw - lc0);
-        PROF_T(tL0);
         // ---- 1. this thread's rows of the leaf columns ----
         double v[RPT][W];
+        bool live[RPT];
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
+            live[k] = pos[k] >= 0;
             const int r = rbase + k * NT;
 #pragma unroll
-            for (int c = 0; c < W; ++c) v[k][c] = (r >= lc0 && r < m && c < w) ? a[(lc0 + c) * lda + r] : 0.0;
+            for (int c = 0; c < W; ++c) v[k][c] = (live[k] && c < w) ? a[(lc0 + c) * lda + r] : 0.0;
         }
-        PROF_T(tL1);
-        PROF_ADD(0, tL0, tL1);
         // ---- 2. column steps.
         //  * The row is ROTATED one slot per step so that all register indices stay static and the loop is not unrolled:
         //    slot 0 = current column, updated trailing entries move down one slot, the finished value is appended at slot 15.
-        //  * The loop is SOFTWARE PIPELINED: as soon as pivot q is known every thread updates only the next column (one FMA
-        //    per row), the candidates for pivot q+1 are reduced and pushed, and the remaining 14 FMAs per row of update q run
-        //    while that push is in flight.  A CTA may therefore still read the candidates of pivot q while its peers already
-        //    push pivot q+2: candidate buffers and mbarriers are triple buffered (q % 3).
-        double l[RPT], app[RPT], pm[W];
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) { l[k] = 0.0; app[k] = 0.0; }
-#pragma unroll
-        for (int c = 0; c < W; ++c) pm[c] = 0.0;
+        //  * The loop is SOFTWARE PIPELINED: as soon as pivot q is known every thread updates the next column (one FMA per
+        //    row) and the warp reduction for pivot q+1 is issued; the remaining 14 FMAs per row of update q execute while the
+        //    REDUX is in flight, then the winning lanes publish their (already updated) rows.  A CTA may still read the
+        //    candidates of pivot q while its peers already push pivot q+2: candidate buffers and mbarriers are triple
+        //    buffered (q % 3).
 
-        // stage the candidates of panel column q: x0[k] = value of column q in row k of this thread; when `upd` the row to
-        // publish is the row AFTER update q-1 (computed on the fly for the one publishing lane only)
-        auto candidate_and_push = [&](const int q, const double (&x0)[RPT], const bool upd) {
-            const int buf = q % 3, wb = q & 1;
-            const uint32_t bar = lsmem(&s_bar[buf]);
-            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
-            double val = -1.0, piv0 = 1.0;
-            int row = NOROW, kb = 0;
+        // thread-level candidate among this thread's rows in play: largest |x| (x = slot 0), lowest position on ties (IDAMAX).
+        // key = bits(|x|); rows out of play carry position NOROW and never win.
+        auto thread_best = [&](unsigned long long &bkey, int &bpos, int &kb, double &brcp) {
+            bkey = 0ull; bpos = NOROW; kb = 0;
+            double bval = 1.0;
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
-                const int r = rbase + k * NT;
-                const double x = fabs(x0[k]);
-                if (r >= q && r < m && x > val) { val = x; row = r; kb = k; piv0 = x0[k]; }
+                const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v[k][0]));
+                const int pk = pos[k] >= 0 ? pos[k] : NOROW;
+                if (pk != NOROW && (bpos == NOROW || key > bkey || (key == bkey && pk < bpos))) { bkey = key; bpos = pk; kb = k; bval = v[k][0]; }
             }
-            const double myrcp = 1.0 / piv0;  // issued early: its latency hides behind the REDUX chain
-            // warp argmax on the bit pattern of |x| (monotonic for non-negative doubles); lowest row wins ties (IDAMAX)
-            const unsigned long long key = row != NOROW ? (unsigned long long)__double_as_longlong(val) : 0ull;
-            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-            const unsigned mh = __reduce_max_sync(FULL, hi);
-            const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-            const int wrow = __reduce_min_sync(FULL, (hi == mh && lo == ml) ? row : NOROW);
-            auto row_value = [&](int k, int c) -> double {  // slot c of row k after the pending update (if any)
-                if (!upd) return v[k][c];
-                return c < W - 1 ? v[k][c + 1] - l[k] * pm[c + 1] : app[k];
-            };
-            if (row == wrow && row != NOROW) {  // exactly one lane: publish the warp's candidate row
+            brcp = 1.0 / bval;  // issued early: its latency hides behind the reduction
+        };
+        // the warp's winner publishes its row; the CTA's candidate goes to every CTA of the cluster
+        auto publish_and_push = [&](const int q, const bool iwin, const int bpos, const int kb, const double brcp) {
+            const int buf = q % 3, wb = q & 1;
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsmem(&s_bar[buf])), "r"(tx_bytes) : "memory");
+            if (iwin) {  // at most one lane per warp
+                double2 *wd = reinterpret_cast<double2 *>(s_wdata[wb][warp]);
 #pragma unroll
                 for (int k = 0; k < RPT; ++k)
                     if (kb == k) {
+                        wd[0] = make_double2(__longlong_as_double(((long long)bpos << 32) | (long long)(unsigned)(rbase + k * NT)), brcp);
 #pragma unroll
-                        for (int c = 0; c < W; ++c) s_wdata[wb][warp][c] = row_value(k, c);
+                        for (int c = 0; c < W; c += 2) wd[1 + c / 2] = make_double2(v[k][c], v[k][c + 1]);
                     }
-                s_wdata[wb][warp][W] = myrcp;
-            }
-            if (lane == 0) { s_whi[wb][warp] = mh; s_wlo[wb][warp] = ml; s_wrow[wb][warp] = wrow; }
-            if (crank == 0 && tid == q) {  // row q lives in CTA 0, thread q, k = 0 (q < 128 <= NT)
-#pragma unroll
-                for (int c = 0; c < W; ++c) s_myrowj[wb][c] = row_value(0, c);
+                s_wpos[wb][warp] = bpos;
             }
             __syncthreads();
-            // every warp finds the CTA's candidate (redundantly) and pushes it to the destination CTAs warp, warp+NWARP, ...
-            const unsigned h2 = lane < NWARP ? s_whi[wb][lane] : 0u, l2 = lane < NWARP ? s_wlo[wb][lane] : 0u;
-            const int r2 = lane < NWARP ? s_wrow[wb][lane] : NOROW;
-            const unsigned MH = __reduce_max_sync(FULL, r2 != NOROW ? h2 : 0u);
-            const unsigned ML = __reduce_max_sync(FULL, (r2 != NOROW && h2 == MH) ? l2 : 0u);
-            const int MR = __reduce_min_sync(FULL, (r2 != NOROW && h2 == MH && l2 == ML) ? r2 : NOROW);
-            const unsigned who = __ballot_sync(FULL, r2 == MR && r2 != NOROW);
-            const int src = who ? __ffs(who) - 1 : 0;
-            double payload = 0.0;
-            if (lane == 0) payload = (double)MR;
-            else if (lane < PAY) payload = (MR == NOROW) ? 0.0 : (lane == 1 ? s_wdata[wb][src][W] : s_wdata[wb][src][lane - 2]);
-            const double rowj_payload = (crank == 0 && lane < W) ? s_myrowj[wb][lane] : 0.0;
-            const uint32_t dst = lsmem(&s_cand[buf][crank][lane < PAY ? lane : 0]);
-            const uint32_t dstj = lsmem(&s_rowj[buf][lane < W ? lane : 0]);
-            for (uint32_t d = warp; d < csize; d += NWARP) {
-                const uint32_t rbar = mapa(bar, d);
-                if (lane < PAY) st_async(mapa(dst, d), payload, rbar);
-                if (crank == 0 && lane < W) st_async(mapa(dstj, d), rowj_payload, rbar);
+            // every warp finds the CTA's candidate (redundantly) and pushes it to its destination CTAs
+            const int p2 = lane < NWARP ? s_wpos[wb][lane] : NOROW;
+            const unsigned long long k2 = p2 != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_wdata[wb][lane < NWARP ? lane : 0][2])) : 0ull;
+            const unsigned who = __ballot_sync(FULL, warp_argmax(k2, p2, p2 != NOROW));
+            double payload;
+            if (who) payload = s_wdata[wb][__ffs(who) - 1][lane < PAY ? lane : 0];
+            else payload = __longlong_as_double((long long)NOROW << 32);
+            const uint32_t off = buf * (MAXC * PAY * 8), boff = buf * 8;
+            if (lane < PAY) {
+                if (warp < (int)csize) st_async(rcand[0] + off, payload, rbar[0] + boff);
+                if (warp + NWARP < (int)csize) st_async(rcand[1] + off, payload, rbar[1] + boff);
             }
         };
 
         {
-            double x0[RPT];
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) x0[k] = v[k][0];
-            candidate_and_push(lc0, x0, false);
+            unsigned long long bkey; int bpos, kb; double brcp;
+            thread_best(bkey, bpos, kb, brcp);
+            const bool iwin = warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW);
+            publish_and_push(lc0, iwin, bpos, kb, brcp);
         }
 #pragma unroll 1
         for (int j = 0; j < w; ++j) {
-            PROF_T(tc0);
-            const int jj = lc0 + j;  // panel-local index of the pivot position
-            const int buf = jj % 3;
-            bar_wait(lsmem(&s_bar[buf]), (jj / 3) & 1);
-            PROF_T(tc3);
-            PROF_ADD(3, tc0, tc3);
+            const int q = lc0 + j;  // pivot index inside the panel
+            const int buf = q % 3;
+            if (lane == 0) s_wpos[(q + 1) & 1][warp] = NOROW;  // reset for the next publish (last read before the previous barrier)
+            bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
             // global winner: same decision in every warp (lane d looks at CTA d's candidate)
-            int p, wr;
+            int wr;
             {
-                const int cr = lane < (int)csize ? (int)s_cand[buf][lane][0] : NOROW;
-                const double cv = (lane < (int)csize && cr != NOROW) ? fabs(s_cand[buf][lane][2]) : 0.0;
-                const bool ok = cr != NOROW;
-                const unsigned long long ck = ok ? (unsigned long long)__double_as_longlong(cv) : 0ull;
-                const unsigned ch = (unsigned)(ck >> 32), cl = (unsigned)ck;
-                const unsigned GH = __reduce_max_sync(FULL, ch);
-                const unsigned GL = __reduce_max_sync(FULL, (ok && ch == GH) ? cl : 0u);
-                p = __reduce_min_sync(FULL, (ok && ch == GH && cl == GL) ? cr : NOROW);
-                const unsigned who = __ballot_sync(FULL, ok && cr == p);
+                const long long c0 = lane < (int)csize ? __double_as_longlong(s_cand[buf][lane][0]) : ((long long)NOROW << 32);
+                const int cp = (int)(c0 >> 32);
+                const unsigned long long ck = cp != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_cand[buf][lane < (int)csize ? lane : 0][2])) : 0ull;
+                const unsigned who = __ballot_sync(FULL, warp_argmax(ck, cp, cp != NOROW));
                 wr = who ? __ffs(who) - 1 : 0;
             }
-            const double *pr = &s_cand[buf][wr][2];
-            const double pval = pr[0];
-            const double rcp = s_cand[buf][wr][1];
-            if (tid == 0) {
-                s_piv[j] = p;
-                if (crank == 0) {
-                    ipiv[col0 + jj] = row0 + p + 1;
-                    if (pval == 0.0 && *info == 0) *info = col0 + jj + 1;
-                }
+            const double2 *pr2 = reinterpret_cast<const double2 *>(&s_cand[buf][wr][0]);
+            const double2 head = pr2[0];
+            const long long hd = __double_as_longlong(head.x);
+            const int p = (int)(hd >> 32);           // LAPACK position of the pivot row (ipiv)
+            const int pphys = (int)(unsigned)hd;     // where it physically lives
+            const double rcp = head.y;
+            double pm[W];
+#pragma unroll
+            for (int c = 0; c < W; c += 2) {
+                const double2 t = pr2[1 + c / 2];
+                pm[c] = t.x;
+                pm[c + 1] = t.y;
             }
-            PROF_T(tc4);
-            PROF_ADD(4, tc3, tc4);
-            const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
-            const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
-#pragma unroll
-            for (int c = 1; c < W; ++c) pm[c] = (c <= last) ? pr[c] : 0.0;
-#pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                const int r = rbase + k * NT;
-                if (p != jj) {
-                    if (r == p) {  // the pivot row's old slot receives row jj
-#pragma unroll
-                        for (int c = 0; c < W; ++c) v[k][c] = s_rowj[buf][c];
-                    } else if (r == jj) {
-#pragma unroll
-                        for (int c = 0; c < W; ++c) v[k][c] = pr[c];
+            const double pval = pm[0];
+            if (warp == 0) {
+                if (lane < j) s_L[j][lane] = s_cand[buf][wr][2 + W - j + lane];  // multipliers of pivot row j for the leaf's earlier steps
+                if (lane == 0) {
+                    s_pphys[q] = pphys;
+                    if (crank == 0) {
+                        ipiv[j0 + q] = j0 + p + 1;
+                        if (pval == 0.0 && *info == 0) *info = j0 + q + 1;
                     }
                 }
-                const bool active = (r > jj && r < m && pval != 0.0);
-                l[k] = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
-                app[k] = active ? l[k] : v[k][0];
             }
-            if (j + 1 < w) {  // look ahead: next column first, its candidates go out before the rest of this update
-                double x0[RPT];
-#pragma unroll
-                for (int k = 0; k < RPT; ++k) x0[k] = v[k][1] - l[k] * pm[1];
-                candidate_and_push(jj + 1, x0, true);
-            }
-            PROF_T(tc5);
-            PROF_ADD(1, tc4, tc5);
+            const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
+            const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
+            double l[RPT], app[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
-#pragma unroll
-                for (int c = 1; c < W; ++c) v[k][c - 1] = v[k][c] - l[k] * pm[c];
-                v[k][W - 1] = app[k];
+                const bool mine = (pos[k] == p);
+                if (pos[k] == q && !mine) pos[k] = p;  // the row LAPACK swaps out of position q
+                if (mine) pos[k] = ~q;
+                const bool active = (pos[k] >= 0 && pval != 0.0);
+                l[k] = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
+                app[k] = active ? l[k] : v[k][0];
+                v[k][0] = v[k][1] - l[k] * (last >= 1 ? pm[1] : 0.0);  // next column first
             }
-            PROF_T(tc6);
-            PROF_ADD(5, tc5, tc6);
+            // reduction for pivot q+1 on the freshly updated next column, issued before the rest of the update
+            unsigned long long bkey; int bpos, kb; double brcp;
+            thread_best(bkey, bpos, kb, brcp);
+            const bool more = j + 1 < w;
+            const bool iwin = more ? warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW) : false;
+#pragma unroll
+            for (int c = 2; c < W; ++c) {
+                const double pc = (c <= last) ? pm[c] : 0.0;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) v[k][c - 1] = v[k][c] - l[k] * pc;
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) v[k][W - 1] = app[k];
+            if (more) publish_and_push(q + 1, iwin, bpos, kb, brcp);
         }
-        PROF_T(tL2);
-        // ---- 3. write the leaf back (slot W-w+c holds column c); the multipliers stay in registers for step 9 ----
+        // ---- 3. write the leaf back (slot W-w+c holds column c); the multipliers stay in registers for step 4 ----
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const int r = rbase + k * NT;
-            if (r >= lc0 && r < m) {
+            if (live[k]) {
 #pragma unroll
                 for (int c = 0; c < W; ++c)
                     if (c >= W - w) a[(lc0 + c - (W - w)) * lda + r] = v[k][c];
             }
         }
-        PROF_T(tL3);
-        PROF_ADD(6, tL2, tL3);
-        if (pw <= W) break;  // single-leaf panel: nothing else to do (uniform)
-        // ---- 4. CTA 0 applies the leaf's interchanges to the other columns of the panel ----
-        if (crank == 0) {
-            if (tid >= lc0 && tid < lc0 + W) {  // rows lc0..lc0+15 are final: keep L_ii for the triangular solve
-#pragma unroll
-                for (int c = 0; c < W; ++c) s_L[tid - lc0][c] = v[0][c];
-            }
-            __syncthreads();  // s_piv complete (written by tid 0 during the column steps)
-            if (tid < W) swap_plan(tid, lc0, w, s_piv, s_other, s_far);
-            __syncthreads();
-            if (tid < pw && (tid < lc0 || tid >= lc0 + w)) swap_group(a + tid * lda, lc0, w, s_other, s_far, dyn, NB, tid, 0);
-            __threadfence();
-        }
-        PROF_T(tL4);
-        PROF_ADD(7, tL3, tL4);
-        asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        PROF_T(tL5);
-        PROF_ADD(8, tL4, tL5);
         const int rest0 = lc0 + W, ncols = pw - rest0;
         if (ncols <= 0) break;  // last leaf (uniform)
-        // ---- 6. CTA 0: U(lc0:lc0+16, rest) = L_ii^{-1} * A(lc0:lc0+16, rest), one column per thread, in registers ----
-        if (crank == 0) {
-            if (tid >= rest0 && tid < pw) {
-                double x[W];
-                double *col = a + tid * lda + lc0;
+        // ---- 4. U12 and the rank-16 update of the remaining panel columns ----
+        if (lc0 > 0) cluster_wait();  // every CTA finished the previous leaf's update (and its reads of the old pivot rows)
+        __syncthreads();              // s_L, s_pphys of this leaf are complete
+        const int cur = (lc0 / W) & 1;
+        double *sU = dyn + cur * (W * NB);
+        if (pend_lc0 >= 0 && crank == 0) {  // delayed write of the previous leaf's U12 into its pivot rows
+            const double *pU = dyn + (cur ^ 1) * (W * NB);
+            const int pc = pw - (pend_lc0 + W);
+            if (tid < pc) {
 #pragma unroll
-                for (int t = 0; t < W; ++t) x[t] = col[t];
-#pragma unroll
-                for (int t = 0; t < W; ++t)
-#pragma unroll
-                    for (int q = t + 1; q < W; ++q) x[q] -= s_L[q][t] * x[t];
-#pragma unroll
-                for (int t = 0; t < W; ++t) col[t] = x[t];
+                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[tid * W + i];
             }
-            __threadfence();
         }
-        PROF_T(tL6);
-        PROF_ADD(9, tL5, tL6);
-        asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        PROF_T(tL7);
-        PROF_ADD(10, tL6, tL7);
-        // ---- 8. everybody stages the U block row, 9. and applies the rank-16 update to its own rows of the rest columns ----
-        for (int idx = tid; idx < W * ncols; idx += NT) {
-            const int t = idx % W, c = idx / W;
-            dyn[t * NB + c] = a[(rest0 + c) * lda + lc0 + t];
+        pend_lc0 = lc0;
+        if (tid < ncols) {
+            double x[W];
+            const double *col = a + (rest0 + tid) * lda;
+#pragma unroll
+            for (int i = 0; i < W; ++i) x[i] = __ldcg(col + s_pphys[lc0 + i]);
+#pragma unroll
+            for (int t = 0; t < W; ++t)
+#pragma unroll
+                for (int i = t + 1; i < W; ++i) x[i] -= s_L[i][t] * x[t];
+#pragma unroll
+            for (int i = 0; i < W; ++i) sU[tid * W + i] = x[i];
         }
         __syncthreads();
-        PROF_T(tL8);
-        PROF_ADD(11, tL7, tL8);
         {
-            constexpr int CU = 16 / RPT;  // columns per batch: RPT*CU = 16 independent loads in flight per thread
+            constexpr int CU = RPT >= 4 ? 2 : (RPT == 2 ? 4 : 8);  // columns per batch: RPT*CU independent loads in flight
             bool rowok[RPT];
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) rowok[k] = (rbase + k * NT >= rest0) && (rbase + k * NT < m);
+            for (int k = 0; k < RPT; ++k) rowok[k] = pos[k] >= 0;
             for (int c0 = 0; c0 < ncols; c0 += CU) {
                 double x[RPT][CU];
 #pragma unroll
@@ -408,13 +331,18 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
                     for (int u = 0; u < CU; ++u)
                         x[k][u] = (rowok[k] && c0 + u < ncols) ? a[(rest0 + c0 + u) * lda + rbase + k * NT] : 0.0;
 #pragma unroll
-                for (int t = 0; t < W; ++t)
+                for (int u = 0; u < CU; ++u) {
+                    const double2 *up = reinterpret_cast<const double2 *>(sU + (c0 + u) * W);
 #pragma unroll
-                    for (int u = 0; u < CU; ++u) {
-                        const double ut = dyn[t * NB + c0 + u];
+                    for (int t2 = 0; t2 < W / 2; ++t2) {
+                        const double2 uu = up[t2];
 #pragma unroll
-                        for (int k = 0; k < RPT; ++k) x[k][u] -= v[k][t] * ut;
+                        for (int k = 0; k < RPT; ++k) {
+                            x[k][u] -= v[k][2 * t2] * uu.x;
+                            x[k][u] -= v[k][2 * t2 + 1] * uu.y;
+                        }
                     }
+                }
 #pragma unroll
                 for (int k = 0; k < RPT; ++k)
 #pragma unroll
@@ -422,112 +350,256 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int row0,
                         if (rowok[k] && c0 + u < ncols) a[(rest0 + c0 + u) * lda + rbase + k * NT] = x[k][u];
             }
         }
-        __syncthreads();  // dyn is reused by the next leaf's interchanges
-        PROF_T(tL9);
-        PROF_ADD(12, tL8, tL9);
+        cluster_arrive();
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// DLASWP for the cnt (<= 128) pivots of one panel, applied to every column outside [skip0, skip1): one thread per column,
-// the pivots are replayed in groups of 16 (one memory round trip per group, see swap_group).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) laswp_panel_kernel(double *a, long long lda, long long sa, int ncols, int skip0, int skip1, int k1,
-                                                           int cnt, const int32_t *ipiv, long long sp) {
-    extern __shared__ double S[];  // S[slot * 256 + tid], slots 0..15 top rows, 16..31 far rows
-    __shared__ int piv[LEAF], other[LEAF], farrow[LEAF];
-    a += blockIdx.y * sa;
-    ipiv += blockIdx.y * sp;
-    const int tid = threadIdx.x;
-    int col = blockIdx.x * 256 + tid;
-    if (col >= skip0) col += skip1 - skip0;
-    for (int g0 = 0; g0 < cnt; g0 += LEAF) {
-        const int gc = min(LEAF, cnt - g0);
-        __syncthreads();
-        if (tid < LEAF) piv[tid] = tid < gc ? ipiv[k1 + g0 + tid] - 1 : 0;
-        __syncthreads();
-        if (tid < LEAF) swap_plan(tid, k1 + g0, gc, piv, other, farrow);
-        __syncthreads();
-        if (col < ncols) swap_group(a + col * lda, k1 + g0, gc, other, farrow, S, 256, tid, 0);
-    }
-}
-
-// General DLASWP (used by getrs on the right-hand sides): for i in [k1,k2): swap rows i and ipiv[i]-1, thread per column.
-__global__ void __launch_bounds__(256) laswp_kernel(double *a, long long lda, long long sa, int ncols, int k1, int k2, const int32_t *ipiv,
-                                                     long long sp) {
-    __shared__ int piv[NB];
-    a += blockIdx.y * sa;
-    ipiv += blockIdx.y * sp;
-    for (int base = k1; base < k2; base += NB) {
-        const int cnt = min(NB, k2 - base);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) piv[i] = ipiv[base + i] - 1;
-        __syncthreads();
-        const int col = blockIdx.x * blockDim.x + threadIdx.x;
-        if (col < ncols) {
-            double *c = a + col * lda;
-            for (int i = 0; i < cnt; ++i) {
-                const int p = piv[i], r = base + i;
-                if (p != r) {
-                    const double t = c[r];
-                    c[r] = c[p];
-                    c[p] = t;
-                }
+    // ---- the last pending U12 and the panel's net permutation ----
+    if (pend_lc0 >= 0) {
+        cluster_wait();
+        if (crank == 0) {
+            const double *pU = dyn + ((pend_lc0 / W) & 1) * (W * NB);
+            const int pc = pw - (pend_lc0 + W);
+            if (tid < pc) {
+#pragma unroll
+                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[tid * W + i];
             }
         }
     }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int r = rbase + k * NT;
+        if (pos[k] < 0) {
+            const int q = ~pos[k];
+            if (q < pw) map[q] = make_int2(j0 + q, j0 + r);  // final row q comes from physical row r
+        }
+    }
+    if (crank == 0 && tid < NB) {
+        if (tid >= pw) map[tid] = make_int2(-1, -1);
+        // a top row that never became a pivot ends where the interchanges pushed it
+        map[NB + tid] = (pos[0] >= 0 && pos[0] != tid) ? make_int2(j0 + pos[0], j0 + tid) : make_int2(-1, -1);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// small triangular solves, T is nb x nb (nb <= 128) in smem, B is nb x ncols solved in place, 32 columns per CTA
-//   UPPER=false: unit lower (forward substitution)   UPPER=true: upper, non-unit (back substitution with division)
+// Applies the net row permutations of panels [0, npanels) of `map` (in order) to the columns [c0, c0+ncols): per panel
+// all <= 256 source rows of a column are loaded before any destination row is stored.  8 columns per CTA.
 // ---------------------------------------------------------------------------------------------
-constexpr int TRSM_CB = 32;
+constexpr int PERM_PC = 8;
+__global__ void __launch_bounds__(MAPN) permute_rows_kernel(double *a, long long lda, long long sa, int ncols, const int2 *map, long long smap,
+                                                            int npanels) {
+    a += blockIdx.y * sa;
+    map += blockIdx.y * smap;
+    const int tid = threadIdx.x;
+    const int col0 = blockIdx.x * PERM_PC;
+    const int nc = min(PERM_PC, ncols - col0);
+    double *base = a + (long long)col0 * lda;
+    for (int p = 0; p < npanels; ++p) {
+        const int2 e = map[p * MAPN + tid];
+        const bool on = e.x >= 0 && e.x != e.y;
+        double t[PERM_PC];
+#pragma unroll
+        for (int j = 0; j < PERM_PC; ++j) t[j] = (on && j < nc) ? base[j * lda + e.y] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PERM_PC; ++j)
+            if (on && j < nc) base[j * lda + e.x] = t[j];
+        if (p + 1 < npanels) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ipiv -> per-block net permutations (same format the panel kernel emits): one warp replays the <= 128 interchanges of
+// block blockIdx.x on a sparse model (the 128 block rows + the far rows they touch).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) ipiv_to_maps_kernel(int n, const int32_t *ipiv, long long sp, int2 *map, long long smap) {
+    __shared__ int piv[NB], top[NB], fpos[NB], fval[NB];
+    ipiv += blockIdx.y * sp;
+    map += blockIdx.y * smap + (long long)blockIdx.x * MAPN;
+    const int lane = threadIdx.x;
+    const int k0 = blockIdx.x * NB, cnt = min(NB, n - k0);
+    for (int i = lane; i < NB; i += 32) {
+        piv[i] = i < cnt ? ipiv[k0 + i] - 1 : k0 + i;
+        top[i] = k0 + i;
+        fpos[i] = -1;
+        fval[i] = -1;
+    }
+    __syncwarp();
+    int nfar = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int p = piv[i];
+        if (p == k0 + i || p < 0 || p >= n) continue;
+        if (p >= k0 && p < k0 + NB) {
+            if (lane == 0) { const int t = top[i]; top[i] = top[p - k0]; top[p - k0] = t; }
+        } else {
+            unsigned hit = 0;
+            int e_found = -1;
+            for (int e0 = 0; e0 < nfar; e0 += 32) {
+                hit = __ballot_sync(FULL, e0 + lane < nfar && fpos[e0 + lane] == p);
+                if (hit) { e_found = e0 + __ffs(hit) - 1; break; }
+            }
+            if (lane == 0) {
+                if (e_found >= 0) { const int t = top[i]; top[i] = fval[e_found]; fval[e_found] = t; }
+                else { fpos[nfar] = p; fval[nfar] = top[i]; top[i] = p; }
+            }
+            if (e_found < 0) ++nfar;
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < NB; i += 32) {
+        map[i] = (i < cnt && top[i] != k0 + i) ? make_int2(k0 + i, top[i]) : make_int2(-1, -1);
+        map[NB + i] = (i < nfar && fval[i] != fpos[i]) ? make_int2(fpos[i], fval[i]) : make_int2(-1, -1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaf triangular solves: T is nb x nb (nb <= 128), B is nb x ncols, solved in place.
+//   UPPER=false: unit lower (forward substitution)   UPPER=true: upper, non-unit (back substitution)
+// One CTA = 8 warps = 32 columns: lane = column, warp r owns rows 16b + 2r, 2r+1 of every 16-row block b, and keeps
+// them in registers for the whole solve (16 doubles).  T is staged in shared memory as 16x16 blocks (triangle only) laid
+// out so that the 2 rows a warp needs are one broadcast LDS.128 per column; the 16x16 DIAGONAL blocks are inverted
+// in shared memory once per CTA (the standard GPU TRSM formulation: the only place a reciprocal/inverse replaces a
+// division-based substitution), so every block step is the same 2x16 register mat-vec; the 16 solved values of a block
+// step are exchanged between the 8 warps through a small padded smem tile (2 __syncthreads per block step).
+// ---------------------------------------------------------------------------------------------
+constexpr int TR_CB = 32;            // columns per CTA
+constexpr int TR_NT = 256;           // threads per CTA
+constexpr int TR_XLD = 18;           // padded column stride of the exchange tile (conflict-free LDS.128)
+constexpr int TR_SMEM = (36 * 256 + 2 * TR_CB * TR_XLD) * (int)sizeof(double);
 template <bool UPPER>
-__global__ void __launch_bounds__(256) trsm_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
-                                                    long long ldb, long long sb) {
+__global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
+                                                          long long ldb, long long sb) {
     extern __shared__ double sm[];
-    double *Ts = sm;                       // Ts[k*nb + i] = T(i,k)
-    double *Bs = sm + (size_t)nb * nb;     // Bs[col*(nb+1) + i]
-    const int ldbs = nb + 1;
+    double *Ts = sm;             // block (bi, bk), warp r, column j, row i:  Ts[blk*256 + r*32 + j*2 + i] = T(16bi + 2r + i, 16bk + j)
+    double *Xs = sm + 36 * 256;  // two exchange tiles: Xs[buf][col * TR_XLD + row]
     T += blockIdx.y * st;
     B += blockIdx.y * sb;
-    const int c0 = blockIdx.x * TRSM_CB;
-    const int nc = min(TRSM_CB, ncols - c0);
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < nb * nb; idx += 256) {
-        const int i = idx % nb, k = idx / nb;
-        Ts[idx] = T[k * ldt + i];
-    }
-    for (int idx = tid; idx < nb * TRSM_CB; idx += 256) {
-        const int i = idx % nb, c = idx / nb;
-        Bs[c * ldbs + i] = (c < nc) ? B[(c0 + c) * ldb + i] : 0.0;
+    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
+    const int col = blockIdx.x * TR_CB + lane;
+    const bool colok = col < ncols;
+    const int nblk = (nb + 15) / 16;
+    auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
+    // block number -> (larger, smaller) block coordinate of the triangle
+    __shared__ unsigned char tb_big[36], tb_small[36];
+    if (tid < 36) {
+        int big = 0;
+        while ((big + 1) * (big + 2) / 2 <= tid) ++big;
+        tb_big[tid] = (unsigned char)big;
+        tb_small[tid] = (unsigned char)(tid - big * (big + 1) / 2);
     }
     __syncthreads();
-    const int col = tid & 31, wg = tid >> 5;  // lanes = columns, warps stride over rows
-    double *bc = Bs + col * ldbs;
-    if (!UPPER) {
-        for (int k = 0; k < nb; ++k) {
-            const double bk = bc[k];
-            const double *tk = Ts + k * nb;
-            for (int i = k + 1 + wg; i < nb; i += 8) bc[i] -= tk[i] * bk;
-            __syncthreads();
+    // ---- stage T (triangle only) with cp.async: every copy of the CTA is in flight at once; meanwhile load B ----
+    // thread -> (pair of rows i2, column j) of a block: the 16-byte destination is contiguous; the source is when T allows
+    const int ntri = nblk * (nblk + 1) / 2;
+    const bool t16 = ((reinterpret_cast<uintptr_t>(T) & 15u) == 0) && (ldt % 2 == 0);
+    for (int idx = tid; idx < ntri * 128; idx += TR_NT) {
+        const int blk = idx >> 7, e = idx & 127, i2 = e & 7, j = e >> 3;
+        const int bi = UPPER ? tb_small[blk] : tb_big[blk], bk = UPPER ? tb_big[blk] : tb_small[blk];
+        const int gi = bi * 16 + 2 * i2, gj = bk * 16 + j;
+        double *dst = Ts + blk * 256 + i2 * 32 + j * 2;
+        const double *src = T + gj * ldt + gi;
+        if (t16 && gi + 1 < nb && gj < nb) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(lsmem(dst)), "l"(src) : "memory");
+        } else {
+            cp_async8(lsmem(dst), gi < nb && gj < nb ? src : T, gi < nb && gj < nb);
+            cp_async8(lsmem(dst + 1), gi + 1 < nb && gj < nb ? src + 1 : T, gi + 1 < nb && gj < nb);
         }
-    } else {
-        for (int k = nb - 1; k >= 0; --k) {
-            const double *tk = Ts + k * nb;
-            const double bk = bc[k] / tk[k];
-            for (int i = wg; i < k; i += 8) bc[i] -= tk[i] * bk;
-            __syncthreads();
-            if (wg == 0) bc[k] = bk;
-            // row k is never read again in this sweep, so no barrier is needed after the store
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    double y[8][2];
+    double *bcol = B + (long long)col * ldb + 2 * r;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) y[b][i] = (colok && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
+    if (r < 4) {
+        const int d = r * 2 + (lane >> 4);  // 4 warps x 2 half-warps = the (up to) 8 diagonal blocks
+        const bool act = d < nblk;
+        double *tb = Ts + blk_index(act ? d : 0, act ? d : 0) * 256;
+        auto el = [&](int i, int k) -> double & { return tb[(i >> 1) * 32 + k * 2 + (i & 1)]; };
+        const int j = lane & 15;
+        double z[16];
+        if (!UPPER) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < i) acc -= el(i, k) * ((k >= j) ? z[k] : 0.0);
+                z[i] = (i >= j) ? acc : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 15; i >= 0; --i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 15; k >= 0; --k)
+                    if (k > i) acc -= el(i, k) * ((k <= j) ? z[k] : 0.0);
+                const double dg = (16 * d + i < nb) ? el(i, i) : 1.0;
+                z[i] = (i <= j) ? acc / dg : 0.0;
+            }
         }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) el(i, j) = z[i];
+        }
+    }
+    __syncthreads();
+    // ---- block steps ----
+    auto read16 = [&](const double *xs, double (&x)[16]) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const double2 t = *reinterpret_cast<const double2 *>(xs + lane * TR_XLD + 2 * h);
+            x[2 * h] = t.x;
+            x[2 * h + 1] = t.y;
+        }
+    };
+    auto write2 = [&](double *xs, const double (&v2)[2]) {
+        *reinterpret_cast<double2 *>(xs + lane * TR_XLD + 2 * r) = make_double2(v2[0], v2[1]);
+    };
+    // acc[i] += sum_j Tblk[2r+i][j] * x[j]; all 16 T loads are issued before the first FMA
+    auto matvec = [&](const double *tb, const double (&x)[16], double (&acc)[2]) {
+        const double2 *tr = reinterpret_cast<const double2 *>(tb + r * 32);
+        double2 t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = tr[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc[0] += t[j].x * x[j];
+            acc[1] += t[j].y * x[j];
+        }
+    };
+    double *XA = Xs, *XB = Xs + TR_CB * TR_XLD;
+    for (int s = 0; s < nblk; ++s) {
+        const int bk = UPPER ? nblk - 1 - s : s;
+        double x[16], z[2] = {0.0, 0.0};
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (b == bk) write2(XA, y[b]);
         __syncthreads();
+        read16(XA, x);
+        matvec(Ts + blk_index(bk, bk) * 256, x, z);  // x_bk = inv(T_kk) b_k, this warp's 2 rows
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (b == bk) { y[b][0] = z[0]; y[b][1] = z[1]; }
+        write2(XB, z);
+        __syncthreads();
+        read16(XB, x);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = -x[j];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool todo = UPPER ? (b < bk) : (b > bk && b < nblk);
+            if (todo) matvec(Ts + blk_index(b, bk) * 256, x, y[b]);
+        }
     }
-    for (int idx = tid; idx < nb * TRSM_CB; idx += 256) {
-        const int i = idx % nb, c = idx / nb;
-        if (c < nc) B[(c0 + c) * ldb + i] = Bs[c * ldbs + i];
-    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (colok && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[b][i];
 }
 
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
@@ -573,10 +645,36 @@ struct Mat {
     double *at(int i, int j) const { return a + (size_t)j * lda + i; }
 };
 
+// device workspace for the row maps (lives for the life of the library, grown on demand)
+struct MapPool {
+    int2 *buf = nullptr;
+    size_t entries = 0;
+    int2 *get(size_t want) {
+        if (want <= entries) return buf;
+        if (buf) cudaFree(buf);  // implicit device sync: nothing in flight still uses it
+        buf = nullptr;
+        entries = 0;
+        if (cudaMalloc(&buf, want * sizeof(int2)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error(FM_ERR_NOMEM, "LU row-map workspace of %zu bytes failed", want * sizeof(int2));
+            return nullptr;
+        }
+        entries = want;
+        return buf;
+    }
+};
+MapPool g_maps_getrf, g_maps_getrs;
+
+struct Maps {
+    int2 *base;
+    long long item_stride;  // in int2 units
+    int2 *panel(int j0) const { return base + (long long)(j0 / NB) * MAPN; }
+};
+
 constexpr int PANEL_DYN_SMEM = 2 * LEAF * NB * (int)sizeof(double);
 
 template <int NT, int RPT>
-int launch_panel(const Mat &A, int i0, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, int csize) {
+int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize) {
     static bool attr = false;
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -595,72 +693,111 @@ int launch_panel(const Mat &A, int i0, int j0, int m, int pw, int32_t *ipiv, lon
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT>, A.at(i0, j0), (long long)A.lda, A.stride, m, pw, i0, j0, ipiv, sp, info));
+    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT>, A.at(j0, j0), (long long)A.lda, A.stride, m, pw, j0, ipiv, sp, info,
+                               maps.panel(j0), maps.item_stride));
     count_launch();
     return FM_OK;
 }
 
 // factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch.  One row per thread whenever the cluster
-// (<= 16 CTAs) can cover the panel: the column step is latency/issue bound, so fewer rows per thread is faster.
-int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info) {
+// (<= 16 CTAs) can cover the panel: the column step is latency bound, so fewer rows per thread is faster.
+int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps) {
     auto pow2_ctas = [](int rows, int per_cta) {
         int cs = 1;
         while (cs * per_cta < rows) cs *= 2;
         return cs;
     };
-    if (m <= 4096) return launch_panel<256, 1>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 256));
-    if (m <= 8192) return launch_panel<256, 2>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 512));
-    if (m <= 16384) return launch_panel<256, 4>(A, j0, j0, m, pw, ipiv, sp, info, pow2_ctas(m, 1024));
+    if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
+    if (m <= 8192) {
+        static const bool wide = getenv("FLOMAT_LU_PANEL_512") != nullptr;  // developer switch for A/B timing
+        if (wide) return launch_panel<512, 1>(A, j0, m, pw, ipiv, sp, info, maps, 16);
+        return launch_panel<256, 2>(A, j0, m, pw, ipiv, sp, info, maps, 16);
+    }
+    if (m <= 16384) return launch_panel<256, 4>(A, j0, m, pw, ipiv, sp, info, maps, 16);
     return set_error(FM_ERR_ARG, "getrf: panels taller than 16384 rows are not supported yet (m=%d)", m);
 }
 
-// apply the pivots [k1, k1+cnt) of one panel to all columns except [skip0, skip1)
-int laswp_panel(const Mat &A, int ncols_total, int skip0, int skip1, int k1, int cnt, const int32_t *ipiv, long long sp) {
-    const int ncols = ncols_total - (skip1 - skip0);
-    if (ncols <= 0 || cnt <= 0) return FM_OK;
-    static bool attr = false;
-    if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(laswp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LEAF * 256 * (int)sizeof(double)));
-        attr = true;
-    }
-    dim3 grid(ceil_div(ncols, 256), A.batch);
-    laswp_panel_kernel<<<grid, 256, 2 * LEAF * 256 * sizeof(double), ctx().stream>>>(A.a, A.lda, A.stride, ncols_total, skip0, skip1, k1, cnt, ipiv, sp);
-    FM_LAUNCH_CHECK();
-    return FM_OK;
-}
-
-int laswp(const Mat &A, int j0, int ncols, int k1, int k2, const int32_t *ipiv, long long sp) {
-    if (ncols <= 0 || k2 <= k1) return FM_OK;
-    dim3 grid(ceil_div(ncols, 256), A.batch);
-    laswp_kernel<<<grid, 256, 0, ctx().stream>>>(A.at(0, j0), A.lda, A.stride, ncols, k1, k2, ipiv, sp);
+// apply the row permutations of the panels covering pivots [p0, p1) to columns [c0, c0+ncols) of A
+int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int p1) {
+    if (ncols <= 0 || p1 <= p0) return FM_OK;
+    const int npanels = ceil_div(p1, NB) - p0 / NB;
+    dim3 grid(ceil_div(ncols, PERM_PC), A.batch);
+    permute_rows_kernel<<<grid, MAPN, 0, ctx().stream>>>(A.at(0, c0), A.lda, A.stride, ncols, maps.panel(p0), maps.item_stride, npanels);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
 
 template <bool UPPER>
-int trsm(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     if (nb <= 0 || ncols <= 0) return FM_OK;
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(trsm_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((NB * NB + TRSM_CB * (NB + 1)) * sizeof(double))));
+        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
         attr = true;
     }
-    const size_t smem = ((size_t)nb * nb + (size_t)TRSM_CB * (nb + 1)) * sizeof(double);
-    dim3 grid(ceil_div(ncols, TRSM_CB), batch);
-    trsm_kernel<UPPER><<<grid, 256, smem, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
+    dim3 grid(ceil_div(ncols, TR_CB), batch);
+    trsm_leaf_kernel<UPPER><<<grid, TR_NT, TR_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
 
-int gemm_update(const Mat &A, int ci, int cj, int m, int n, int k, int ai, int aj, int bi, int bj) {
-    // A[ci:ci+m, cj:cj+n] -= A[ai:ai+m, aj:aj+k] * A[bi:bi+k, bj:bj+n]
+int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
+               long long sc, int batch) {
     if (m <= 0 || n <= 0 || k <= 0) return FM_OK;
     GemmEpilogue ep;
     ep.alpha = -1.0;
     ep.beta = 1.0;
-    return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, A.at(ai, aj), A.lda, A.stride, A.at(bi, bj), A.lda, A.stride, A.at(ci, cj), A.lda,
-                   A.stride, A.batch, ep);
+    return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+}
+
+int split(int w) { return ((w / 2 + NB - 1) / NB) * NB; }  // first half of a recursive split, a multiple of the panel width
+
+// B := T^-1 B with T the w x w triangle at `T` (unit lower or upper), B w x ncols; recursive: GEMMs with a large inner
+// dimension carry the flops, the 128 x 128 leaves are substitution kernels
+template <bool UPPER>
+int rtrsm(int w, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+    if (w <= 0 || ncols <= 0) return FM_OK;
+    if (w <= NB) return trsm_leaf<UPPER>(w, ncols, T, ldt, st, B, ldb, sb, batch);
+    if (ncols <= 2 * NB) {
+        // few right-hand sides: a recursive split would leave GEMMs with a handful of tiles and a long inner dimension;
+        // the right-looking sweep (rank-128 updates of everything still to be solved) exposes rows/128 tiles per update
+        const int nblk = ceil_div(w, NB);
+        for (int s = 0; s < nblk; ++s) {
+            const int k0 = (UPPER ? nblk - 1 - s : s) * NB, kb = std::min(NB, w - k0);
+            FM_TRY(trsm_leaf<UPPER>(kb, ncols, T + (size_t)k0 * ldt + k0, ldt, st, B + k0, ldb, sb, batch));
+            if (!UPPER) FM_TRY(gemm_minus(w - k0 - kb, ncols, kb, T + (size_t)k0 * ldt + k0 + kb, ldt, st, B + k0, ldb, sb, B + k0 + kb, ldb, sb, batch));
+            else FM_TRY(gemm_minus(k0, ncols, kb, T + (size_t)k0 * ldt, ldt, st, B + k0, ldb, sb, B, ldb, sb, batch));
+        }
+        return FM_OK;
+    }
+    const int w1 = split(w), w2 = w - w1;
+    const double *T11 = T, *T22 = T + (size_t)w1 * ldt + w1;
+    double *B1 = B, *B2 = B + w1;
+    if (!UPPER) {
+        FM_TRY(rtrsm<false>(w1, ncols, T11, ldt, st, B1, ldb, sb, batch));
+        FM_TRY(gemm_minus(w2, ncols, w1, T + w1, ldt, st, B1, ldb, sb, B2, ldb, sb, batch));  // B2 -= T21 B1
+        return rtrsm<false>(w2, ncols, T22, ldt, st, B2, ldb, sb, batch);
+    }
+    FM_TRY(rtrsm<true>(w2, ncols, T22, ldt, st, B2, ldb, sb, batch));
+    FM_TRY(gemm_minus(w1, ncols, w2, T + (size_t)w1 * ldt, ldt, st, B2, ldb, sb, B1, ldb, sb, batch));  // B1 -= T12 B2
+    return rtrsm<true>(w1, ncols, T11, ldt, st, B1, ldb, sb, batch);
+}
+
+// factor columns [j0, j0+w) of the m-row matrix A (all updates from the columns left of j0 already applied).  On return
+// those columns hold L\U with the interchanges of [j0, j0+w) applied to them and to nothing else.
+int rgetrf(const Mat &A, int m, int j0, int w, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps) {
+    if (w <= NB) {
+        FM_TRY(panel_factor(A, j0, m - j0, w, ipiv, sp, info, maps));
+        return permute_rows(A, j0, w, maps, j0, j0 + w);
+    }
+    const int w1 = split(w), w2 = w - w1;
+    const int j1 = j0 + w1;
+    FM_TRY(rgetrf(A, m, j0, w1, ipiv, sp, info, maps));
+    FM_TRY(permute_rows(A, j1, w2, maps, j0, j1));
+    FM_TRY(rtrsm<false>(w1, w2, A.at(j0, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.batch));
+    FM_TRY(gemm_minus(m - j1, w2, w1, A.at(j1, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.at(j1, j1), A.lda, A.stride, A.batch));
+    FM_TRY(rgetrf(A, m, j1, w2, ipiv, sp, info, maps));
+    return permute_rows(A, j0, w1, maps, j1, j0 + w);
 }
 
 }  // namespace
@@ -673,15 +810,15 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     if (m == 0 || n == 0) return FM_OK;
     Mat A{a, lda, sa, batch};
     const int mn = m < n ? m : n;
-    for (int j0 = 0; j0 < mn; j0 += NB) {
-        const int jb = (mn - j0) < NB ? (mn - j0) : NB;
-        FM_TRY(panel_factor(A, j0, m - j0, jb, ipiv, sp, info));
-        FM_TRY(laswp_panel(A, n, j0, j0 + jb, j0, jb, ipiv, sp));
-        const int nr = n - j0 - jb;
-        if (nr > 0) {
-            FM_TRY(trsm<false>(jb, nr, A.at(j0, j0), lda, sa, A.at(j0, j0 + jb), lda, sa, batch));
-            FM_TRY(gemm_update(A, j0 + jb, j0 + jb, m - j0 - jb, nr, jb, j0 + jb, j0, j0, j0 + jb));
-        }
+    const int npanels = ceil_div(mn, NB);
+    Maps maps;
+    maps.item_stride = (long long)npanels * MAPN;
+    maps.base = g_maps_getrf.get((size_t)maps.item_stride * batch);
+    if (!maps.base) return FM_ERR_NOMEM;
+    FM_TRY(rgetrf(A, m, 0, mn, ipiv, sp, info, maps));
+    if (n > mn) {  // wide matrix: U12 = L11^-1 (P A12)
+        FM_TRY(permute_rows(A, mn, n - mn, maps, 0, mn));
+        FM_TRY(rtrsm<false>(mn, n - mn, a, lda, sa, A.at(0, mn), lda, sa, batch));
     }
     return FM_OK;
 }
@@ -691,43 +828,17 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     if (n < 0 || nrhs < 0 || lda < (n > 1 ? n : 1) || ldb < (n > 1 ? n : 1) || batch < 0) return set_error(FM_ERR_ARG, "getrs: bad dimensions");
     if (n == 0 || nrhs == 0 || batch == 0) return FM_OK;
     Mat B{b, ldb, sb, batch};
-    FM_TRY(laswp(B, 0, nrhs, 0, n, ipiv, sp));
-    GemmEpilogue ep;
-    ep.alpha = -1.0;
-    ep.beta = 1.0;
-    // L (unit lower) forward sweep
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        const int kb = (n - k0) < NB ? (n - k0) : NB;
-        FM_TRY(trsm<false>(kb, nrhs, lu + (size_t)k0 * lda + k0, lda, sa, B.at(k0, 0), ldb, sb, batch));
-        const int rest = n - k0 - kb;
-        if (rest > 0)
-            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, rest, nrhs, kb, lu + (size_t)k0 * lda + k0 + kb, lda, sa, B.at(k0, 0), ldb, sb,
-                           B.at(k0 + kb, 0), ldb, sb, batch, ep));
-    }
-    // U (upper) backward sweep
-    const int nblk = ceil_div(n, NB);
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int k0 = blk * NB;
-        const int kb = (n - k0) < NB ? (n - k0) : NB;
-        FM_TRY(trsm<true>(kb, nrhs, lu + (size_t)k0 * lda + k0, lda, sa, B.at(k0, 0), ldb, sb, batch));
-        if (k0 > 0)
-            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, k0, nrhs, kb, lu + (size_t)k0 * lda, lda, sa, B.at(k0, 0), ldb, sb, B.at(0, 0), ldb, sb,
-                           batch, ep));
-    }
-    return FM_OK;
+    const int nblocks = ceil_div(n, NB);
+    Maps maps;
+    maps.item_stride = (long long)nblocks * MAPN;
+    maps.base = g_maps_getrs.get((size_t)maps.item_stride * batch);
+    if (!maps.base) return FM_ERR_NOMEM;
+    ipiv_to_maps_kernel<<<dim3(nblocks, batch), 32, 0, ctx().stream>>>(n, ipiv, sp, maps.base, maps.item_stride);
+    FM_LAUNCH_CHECK();
+    FM_TRY(permute_rows(B, 0, nrhs, maps, 0, n));                          // P B   (DLASWP)
+    FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));          // L y = P B
+    return rtrsm<true>(n, nrhs, lu, lda, sa, b, ldb, sb, batch);            // U x = y
 }
-
-#ifdef FM_LU_PROF
-}  // namespace fm
-extern "C" int fm_lu_prof(long long *out32) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out32, fm::g_prof, sizeof(long long) * 32);
-    long long z[32] = {};
-    cudaMemcpyToSymbol(fm::g_prof, z, sizeof(z));
-    return 0;
-}
-namespace fm {
-#endif
 
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out) {
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "det: bad dimensions");
