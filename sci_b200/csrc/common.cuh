@@ -90,6 +90,8 @@ struct GemmEpilogue {
     int npeers = 0;
     const int32_t *active_until = nullptr;  // batched: item z is skipped when round >= active_until[z]
     int round = 0;
+    int max_sms = 0;             // > 0: use at most this many SMs (look-ahead LU leaves room for the concurrent panel)
+    bool pdl_dependent = false;  // launch as a programmatic dependent of the previous kernel in the stream (TMA path only)
 };
 int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,
             double *c, int ldc, long long sc, int batch, const GemmEpilogue &ep);

@@ -71,6 +71,7 @@ struct EpiParams {
     const int32_t *active_until;  // optional per-item round limit (batched squaring in expm)
     int round;
     unsigned zero;  // always 0; opaque to the compiler (see the stage-release token in the consumer loop)
+    int pdl_wait;   // launched as a programmatic dependent of the previous kernel: wait for it before exiting
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -333,6 +334,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     }
+    // Look-ahead LU launches this kernel as a programmatic dependent of the panel kernel so that both run concurrently.
+    // Nothing here reads the panel's output, but kernels launched after this one rely on stream order for BOTH: by waiting
+    // for the primary grid before exiting, this grid's completion implies the panel's.
+    if (ep.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,7 +463,7 @@ using CfgHalf = GemmCfg<64, 128, 16, 1, 4, 4, 2>;
 
 template <class Cfg>
 int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
-               long long sc, int batch, const EpiParams &ep) {
+               long long sc, int batch, const EpiParams &ep, int max_sms) {
     static bool attr_set = false;
     if (!attr_set) {
         FM_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -470,15 +475,26 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     const int tiles_m = ceil_div(m, Cfg::BM), tiles_n = ceil_div(n, Cfg::BN);
     const long long total = (long long)tiles_m * tiles_n * batch;
     if (total > 0x7fffffffLL) return set_error(FM_ERR_ARG, "dgemm: too many tiles");
-    const long long slots = (long long)ctx().sm_count * Cfg::CTAS_PER_SM;
+    int sms = ctx().sm_count;
+    if (max_sms > 0 && max_sms < sms) sms = max_sms;
+    const long long slots = (long long)sms * Cfg::CTAS_PER_SM;
     const int grid = (int)(total < slots ? total : slots);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15u) == 0 && (ldc % 2) == 0 && (sc % 2) == 0) ? 1 : 0;
     int vec_all = vec_ok;
     for (int r = 0; r < ep.npeers; ++r)
         if (reinterpret_cast<uintptr_t>(ep.peer[r]) & 15u) vec_all = 0;
-    dgemm_tma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx().stream>>>(tmA, tmB, c, ldc, sc, m, n, k, tiles_m, tiles_n,
-                                                                                  (int)total, ep, vec_all);
-    FM_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ep.pdl_wait ? 1 : 0;
+    FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, ep, vec_all));
+    count_launch();
     return FM_OK;
 }
 
@@ -507,6 +523,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.active_until = epi.active_until;
     ep.round = epi.round;
     ep.zero = 0u;
+    ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
@@ -514,8 +531,8 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     if (tma_ok) {
         const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
         const bool half = (big_tiles < 2LL * ctx().sm_count || k <= 256) && g_half_enabled;
-        if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
-        return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
+        if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
+        return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
     }
 
     dim3 grid(ceil_div(m, GB), ceil_div(n, GB), batch);

@@ -120,6 +120,8 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 2 * NWARP) (&s_wpos[0][0])[tid] = NOROW;
+    // look-ahead: the trailing-matrix GEMM queued behind this kernel (launched as a programmatic dependent) may start now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     cluster_arrive();
     cluster_wait();
     const uint32_t tx_bytes = csize * PAY * 8;
@@ -319,20 +321,23 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         }
         __syncthreads();
         {
-            constexpr int CU = RPT >= 4 ? 2 : (RPT == 2 ? 4 : 8);  // columns per batch: RPT*CU independent loads in flight
+            // columns per batch; two batches are in flight (the loads of batch i+1 are issued before the FMAs of batch i):
+            // the update is bound by the L2 round trip of these loads, not by the FP64 pipe
+            constexpr int CU = RPT >= 4 ? 2 : (RPT == 2 ? 4 : 12);
             bool rowok[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; ++k) rowok[k] = pos[k] >= 0;
-            for (int c0 = 0; c0 < ncols; c0 += CU) {
-                double x[RPT][CU];
+            auto load = [&](double (&x)[RPT][CU], int c0) {
 #pragma unroll
                 for (int k = 0; k < RPT; ++k)
 #pragma unroll
                     for (int u = 0; u < CU; ++u)
                         x[k][u] = (rowok[k] && c0 + u < ncols) ? a[(rest0 + c0 + u) * lda + rbase + k * NT] : 0.0;
+            };
+            auto update_store = [&](double (&x)[RPT][CU], int c0) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u) {
-                    const double2 *up = reinterpret_cast<const double2 *>(sU + (c0 + u) * W);
+                    const double2 *up = reinterpret_cast<const double2 *>(sU + (c0 + u < ncols ? c0 + u : 0) * W);
 #pragma unroll
                     for (int t2 = 0; t2 < W / 2; ++t2) {
                         const double2 uu = up[t2];
@@ -348,6 +353,14 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
 #pragma unroll
                     for (int u = 0; u < CU; ++u)
                         if (rowok[k] && c0 + u < ncols) a[(rest0 + c0 + u) * lda + rbase + k * NT] = x[k][u];
+            };
+            double xa[RPT][CU], xb[RPT][CU];
+            load(xa, 0);
+            for (int c0 = 0; c0 < ncols; c0 += 2 * CU) {
+                load(xb, c0 + CU);
+                update_store(xa, c0);
+                load(xa, c0 + 2 * CU);
+                update_store(xb, c0 + CU);
             }
         }
         cluster_arrive();
@@ -475,32 +488,28 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
     const int col = blockIdx.x * TR_CB + lane;
     const bool colok = col < ncols;
-    const int nblk = (nb + 15) / 16;
     auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
-    // block number -> (larger, smaller) block coordinate of the triangle
-    __shared__ unsigned char tb_big[36], tb_small[36];
-    if (tid < 36) {
-        int big = 0;
-        while ((big + 1) * (big + 2) / 2 <= tid) ++big;
-        tb_big[tid] = (unsigned char)big;
-        tb_small[tid] = (unsigned char)(tid - big * (big + 1) / 2);
-    }
-    __syncthreads();
-    // ---- stage T (triangle only) with cp.async: every copy of the CTA is in flight at once; meanwhile load B ----
-    // thread -> (pair of rows i2, column j) of a block: the 16-byte destination is contiguous; the source is when T allows
-    const int ntri = nblk * (nblk + 1) / 2;
+    // ---- stage T (triangle only, all 36 blocks: blocks beyond nb are zero with a unit diagonal) with cp.async: every copy
+    // of the CTA is in flight at once; meanwhile load B.  thread -> (pair of rows i2, column j) of a block: the 16-byte
+    // destination is contiguous, the source is when T allows.  Two blocks per pass: (big, small) advance incrementally.
     const bool t16 = ((reinterpret_cast<uintptr_t>(T) & 15u) == 0) && (ldt % 2 == 0);
-    for (int idx = tid; idx < ntri * 128; idx += TR_NT) {
-        const int blk = idx >> 7, e = idx & 127, i2 = e & 7, j = e >> 3;
-        const int bi = UPPER ? tb_small[blk] : tb_big[blk], bk = UPPER ? tb_big[blk] : tb_small[blk];
-        const int gi = bi * 16 + 2 * i2, gj = bk * 16 + j;
-        double *dst = Ts + blk * 256 + i2 * 32 + j * 2;
-        const double *src = T + gj * ldt + gi;
-        if (t16 && gi + 1 < nb && gj < nb) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(lsmem(dst)), "l"(src) : "memory");
-        } else {
-            cp_async8(lsmem(dst), gi < nb && gj < nb ? src : T, gi < nb && gj < nb);
-            cp_async8(lsmem(dst + 1), gi + 1 < nb && gj < nb ? src + 1 : T, gi + 1 < nb && gj < nb);
+    {
+        int big = 0, small = 0;  // block tid >> 7 of the triangle enumeration (big >= small)
+        if (tid >> 7) { big = 1; small = 0; }
+        const int e = tid & 127, i2 = e & 7, j = e >> 3;
+        for (int blk = tid >> 7; blk < 36; blk += 2) {
+            const int bi = UPPER ? small : big, bk = UPPER ? big : small;
+            const int gi = bi * 16 + 2 * i2, gj = bk * 16 + j;
+            double *dst = Ts + blk * 256 + i2 * 32 + j * 2;
+            const double *src = T + gj * ldt + gi;
+            if (t16 && gi + 1 < nb && gj < nb) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(lsmem(dst)), "l"(src) : "memory");
+            } else {
+                cp_async8(lsmem(dst), gi < nb && gj < nb ? src : T, gi < nb && gj < nb);
+                cp_async8(lsmem(dst + 1), gi + 1 < nb && gj < nb ? src + 1 : T, gi + 1 < nb && gj < nb);
+            }
+            small += 2;
+            while (small > big) { small -= big + 1; ++big; }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
     if (r < 4) {
         const int d = r * 2 + (lane >> 4);  // 4 warps x 2 half-warps = the (up to) 8 diagonal blocks
-        const bool act = d < nblk;
+        const bool act = true;
         double *tb = Ts + blk_index(act ? d : 0, act ? d : 0) * 256;
         auto el = [&](int i, int k) -> double & { return tb[(i >> 1) * 32 + k * 2 + (i & 1)]; };
         const int j = lane & 15;
@@ -559,47 +568,56 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     auto write2 = [&](double *xs, const double (&v2)[2]) {
         *reinterpret_cast<double2 *>(xs + lane * TR_XLD + 2 * r) = make_double2(v2[0], v2[1]);
     };
-    // acc[i] += sum_j Tblk[2r+i][j] * x[j]; all 16 T loads are issued before the first FMA
-    auto matvec = [&](const double *tb, const double (&x)[16], double (&acc)[2]) {
-        const double2 *tr = reinterpret_cast<const double2 *>(tb + r * 32);
-        double2 t[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = tr[j];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            acc[0] += t[j].x * x[j];
-            acc[1] += t[j].y * x[j];
-        }
-    };
     double *XA = Xs, *XB = Xs + TR_CB * TR_XLD;
-    for (int s = 0; s < nblk; ++s) {
-        const int bk = UPPER ? nblk - 1 - s : s;
-        double x[16], z[2] = {0.0, 0.0};
+    // The 8 block steps are fully unrolled (block coordinates are compile-time constants), so the register-resident y[b]
+    // are indexed statically and the updates of all remaining blocks of a step form independent FMA chains.
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-            if (b == bk) write2(XA, y[b]);
+    for (int s = 0; s < 8; ++s) {
+        const int bk = UPPER ? 7 - s : s;
+        double x[16];
+        write2(XA, y[bk]);
         __syncthreads();
         read16(XA, x);
-        matvec(Ts + blk_index(bk, bk) * 256, x, z);  // x_bk = inv(T_kk) b_k, this warp's 2 rows
+        {   // x_bk = inv(T_kk) b_k, this warp's 2 rows; four partial sums shorten the dependent chain
+            const double2 *tr = reinterpret_cast<const double2 *>(Ts + blk_index(bk, bk) * 256 + r * 32);
+            double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-            if (b == bk) { y[b][0] = z[0]; y[b][1] = z[1]; }
-        write2(XB, z);
+            for (int j = 0; j < 16; j += 2) {
+                const double2 ta = tr[j], tb2 = tr[j + 1];
+                z0 += ta.x * x[j];
+                z1 += ta.y * x[j];
+                w0 += tb2.x * x[j + 1];
+                w1 += tb2.y * x[j + 1];
+            }
+            y[bk][0] = z0 + w0;
+            y[bk][1] = z1 + w1;
+        }
+        write2(XB, y[bk]);
         __syncthreads();
+        if (s == 7) break;
         read16(XB, x);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = -x[j];
+        for (int j = 0; j < 16; ++j) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool todo = UPPER ? (b < bk) : (b > bk && b < nblk);
-            if (todo) matvec(Ts + blk_index(b, bk) * 256, x, y[b]);
+            for (int b = 0; b < 8; ++b) {
+                if (UPPER ? (b < bk) : (b > bk)) {
+                    const double2 t = reinterpret_cast<const double2 *>(Ts + blk_index(b, bk) * 256 + r * 32)[j];
+                    y[b][0] -= t.x * x[j];
+                    y[b][1] -= t.y * x[j];
+                }
+            }
         }
     }
+    // ---- transpose through shared memory (T is no longer needed) so that the stores are full 256-byte row segments ----
+    double *Bs = Ts;  // Bs[col * TR_OLD + row]
+    constexpr int TR_OLD = NB + 2;
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (colok && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[b][i];
+    for (int b = 0; b < 8; ++b) *reinterpret_cast<double2 *>(Bs + lane * TR_OLD + 16 * b + 2 * r) = make_double2(y[b][0], y[b][1]);
+    __syncthreads();
+    for (int idx = tid; idx < NB * TR_CB; idx += TR_NT) {
+        const int i = idx & (NB - 1), c = idx >> 7;
+        if (i < nb && blockIdx.x * TR_CB + c < ncols) B[(long long)(blockIdx.x * TR_CB + c) * ldb + i] = Bs[c * TR_OLD + i];
+    }
 }
 
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
@@ -701,12 +719,13 @@ int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
 
 // factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch.  One row per thread whenever the cluster
 // (<= 16 CTAs) can cover the panel: the column step is latency bound, so fewer rows per thread is faster.
-int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps) {
+int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int *csize_out = nullptr) {
     auto pow2_ctas = [](int rows, int per_cta) {
         int cs = 1;
         while (cs * per_cta < rows) cs *= 2;
         return cs;
     };
+    if (csize_out) *csize_out = m <= 4096 ? pow2_ctas(m, 256) : 16;
     if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
     if (m <= 8192) {
         static const bool wide = getenv("FLOMAT_LU_PANEL_512") != nullptr;  // developer switch for A/B timing
@@ -742,11 +761,13 @@ int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double 
 }
 
 int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
-               long long sc, int batch) {
+               long long sc, int batch, int max_sms = 0, bool pdl_dependent = false) {
     if (m <= 0 || n <= 0 || k <= 0) return FM_OK;
     GemmEpilogue ep;
     ep.alpha = -1.0;
     ep.beta = 1.0;
+    ep.max_sms = max_sms;
+    ep.pdl_dependent = pdl_dependent;
     return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
 }
 
@@ -800,6 +821,39 @@ int rgetrf(const Mat &A, int m, int j0, int w, int32_t *ipiv, long long sp, int3
     return permute_rows(A, j0, w1, maps, j1, j0 + w);
 }
 
+// Right-looking blocked LU with one panel of look-ahead: as soon as panel k is applied to the columns of panel k+1, panel
+// k+1 is factored by its cluster while the rest of the trailing matrix is updated on the remaining SMs.  The trailing GEMM
+// is launched as a programmatic dependent of the panel kernel (the panel's CTAs are resident before the GEMM's first CTA
+// is placed, so the two never fight over the 16 SMs of the cluster) and waits for the panel before it exits, which keeps
+// plain stream order valid for everything queued afterwards.
+int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps) {
+    const int mn = m < n ? m : n;
+    const bool overlap = A.batch == 1 && getenv("FLOMAT_LU_NO_LOOKAHEAD") == nullptr;
+    int csize = 1;
+    FM_TRY(panel_factor(A, 0, m, mn < NB ? mn : NB, ipiv, sp, info, maps, &csize));
+    for (int j0 = 0; j0 < mn; j0 += NB) {
+        const int jb = std::min(NB, mn - j0), j1 = j0 + jb;
+        FM_TRY(permute_rows(A, 0, n, maps, j0, j1));  // panel j0 is complete: its interchanges go to every column
+        const int nr = n - j1;
+        if (nr <= 0) break;
+        FM_TRY(trsm_leaf<false>(jb, nr, A.at(j0, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.batch));
+        const int mrest = m - j1;
+        if (mrest <= 0) break;
+        const int jb2 = j1 < mn ? std::min(NB, mn - j1) : 0;
+        if (jb2 > 0) {  // next panel's columns first, then its factorization runs beside the rest of the update
+            FM_TRY(gemm_minus(mrest, jb2, jb, A.at(j1, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.at(j1, j1), A.lda, A.stride, A.batch));
+            FM_TRY(panel_factor(A, j1, mrest, jb2, ipiv, sp, info, maps, &csize));
+        }
+        const int nb_cols = nr - jb2;
+        if (nb_cols > 0) {
+            const bool dep = overlap && jb2 > 0;
+            FM_TRY(gemm_minus(mrest, nb_cols, jb, A.at(j1, j0), A.lda, A.stride, A.at(j0, j1 + jb2), A.lda, A.stride, A.at(j1, j1 + jb2), A.lda,
+                              A.stride, A.batch, dep ? ctx().sm_count - csize : 0, dep));
+        }
+    }
+    return FM_OK;
+}
+
 }  // namespace
 
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch) {
@@ -815,6 +869,8 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     maps.item_stride = (long long)npanels * MAPN;
     maps.base = g_maps_getrf.get((size_t)maps.item_stride * batch);
     if (!maps.base) return FM_ERR_NOMEM;
+    static const bool recursive = getenv("FLOMAT_LU_RECURSIVE") != nullptr;  // developer switch: DGETRF2-style recursion
+    if (!recursive) return getrf_lookahead(A, m, n, ipiv, sp, info, maps);
     FM_TRY(rgetrf(A, m, 0, mn, ipiv, sp, info, maps));
     if (n > mn) {  // wide matrix: U12 = L11^-1 (P A12)
         FM_TRY(permute_rows(A, mn, n - mn, maps, 0, mn));
