@@ -79,7 +79,8 @@ uint64_t fm_kernel_launches(void);       /* number of kernels this library has l
 /* memory: alloc-flomat / free; upload & download are the explicit host sync points */
 double *fm_alloc(int m, int n);                          /* m*n doubles of HBM, lda = m; NULL on failure */
 void *fm_alloc_bytes(size_t bytes);
-int fm_free(void *dev);
+int fm_free(void *dev);                   /* returns the block to the library's cache (no device sync) */
+int fm_trim_cache(void);                  /* cudaFree every cached block */
 int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n);   /* H2D, strided */
 int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n); /* D2H, strided */
 int fm_get(const double *dev, size_t index, double *out);  /* unsafe-ref on a device buffer (syncs) */

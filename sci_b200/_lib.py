@@ -44,6 +44,7 @@ SIGNATURES = {
     "fm_alloc": (c_void_p, [c_int, c_int]),
     "fm_alloc_bytes": (c_void_p, [c_size_t]),
     "fm_free": (c_int, [c_void_p]),
+    "fm_trim_cache": (c_int, []),
     "fm_upload": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
     "fm_download": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
     "fm_get": (c_int, [_DP, c_size_t, POINTER(c_double)]),

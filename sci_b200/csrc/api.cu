@@ -4,6 +4,8 @@
 // Host operands of the compat tier are staged through HBM inside the call; device operands run in place.
 // Nothing here computes on the CPU: every arithmetic result comes from a kernel in this library.
 #include "common.cuh"
+#include <map>
+#include <unordered_map>
 #include <cstdlib>
 #include <vector>
 #include <utility>
@@ -93,7 +95,7 @@ struct Staged {
         host = const_cast<double *>(p); ldh = ldp;
         ld = rows + (rows & 1);  // even leading dimension keeps the TMA/128-bit paths available
         if (ld < 2) ld = 2;
-        if (cudaMalloc(&dev, (size_t)ld * cols * sizeof(double)) != cudaSuccess) {
+        if (!(dev = static_cast<double *>(fm_alloc_bytes((size_t)ld * cols * sizeof(double))))) {
             cudaGetLastError();
             return set_error(FM_ERR_NOMEM, "staging allocation of %zu bytes failed", (size_t)ld * cols * sizeof(double));
         }
@@ -107,7 +109,7 @@ struct Staged {
         FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ld * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
         return FM_OK;
     }
-    ~Staged() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); cudaFree(dev); } }
+    ~Staged() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); fm_free(dev); } }
 };
 
 static void report(const char *who, int rc) {
@@ -123,22 +125,68 @@ extern "C" {
 // =================================== library / device ===================================
 int fm_init(int device) { return init_device(device); }
 int fm_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; } return c; }
-int fm_set_stream(void *s) { FM_TRY(ensure_init()); g_ctx.stream = static_cast<cudaStream_t>(s); return FM_OK; }
+int fm_set_stream(void *s) {
+    FM_TRY(ensure_init());
+    if (g_ctx.stream != static_cast<cudaStream_t>(s)) cudaStreamSynchronize(g_ctx.stream);  // cached blocks are reused in stream order
+    g_ctx.stream = static_cast<cudaStream_t>(s);
+    return FM_OK;
+}
 int fm_sync(void) { FM_TRY(ensure_init()); FM_CUDA(cudaStreamSynchronize(g_ctx.stream)); return FM_OK; }
 const char *fm_last_error(void) { return g_err; }
 const char *fm_version(void) { return "libflomat_cuda 0.1 (sm_100a)"; }
 uint64_t fm_kernel_launches(void) { return g_ctx.launches; }
 
 // =================================== memory ===================================
+// fm_alloc / fm_free sit where the reference has GC'd `malloc` (flomat.rkt:437-441): cheap and called for every
+// intermediate matrix.  cudaMalloc/cudaFree cost milliseconds at these sizes and synchronise the device, so freed blocks
+// are kept in an exact-size cache and handed out again; reuse is safe without a sync because all work of the library is
+// ordered on one stream.  FLOMAT_CUDA_CACHE_MB bounds the cache (default 64 GiB); fm_trim_cache() empties it.
+namespace {
+struct BlockCache {
+    std::multimap<size_t, void *> free_blocks;
+    std::unordered_map<void *, size_t> live;
+    size_t cached_bytes = 0;
+    size_t limit() {
+        static size_t lim = [] {
+            const char *e = getenv("FLOMAT_CUDA_CACHE_MB");
+            return (e ? (size_t)atoll(e) : (size_t)65536) << 20;
+        }();
+        return lim;
+    }
+    void trim() {
+        if (free_blocks.empty()) return;
+        cudaStreamSynchronize(g_ctx.stream);
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+BlockCache g_cache;
+}  // namespace
+
 void *fm_alloc_bytes(size_t bytes) {
     if (ensure_init() != FM_OK) return nullptr;
-    void *p = nullptr;
     if (bytes == 0) bytes = 16;
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = g_cache.free_blocks.find(bytes);
+    if (it != g_cache.free_blocks.end()) {
+        void *p = it->second;
+        g_cache.free_blocks.erase(it);
+        g_cache.cached_bytes -= bytes;
+        g_cache.live[p] = bytes;
+        return p;
+    }
+    void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
-        set_error(FM_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
-        return nullptr;
+        g_cache.trim();  // give the cached blocks back and try once more
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            set_error(FM_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+            return nullptr;
+        }
     }
+    g_cache.live[p] = bytes;
     return p;
 }
 double *fm_alloc(int m, int n) {
@@ -147,7 +195,24 @@ double *fm_alloc(int m, int n) {
 }
 int fm_free(void *dev) {
     if (!dev) return FM_OK;
-    FM_CUDA(cudaFree(dev));
+    auto it = g_cache.live.find(dev);
+    if (it == g_cache.live.end()) {  // not ours (or freed twice): plain cudaFree reports the error
+        FM_CUDA(cudaFree(dev));
+        return FM_OK;
+    }
+    const size_t bytes = it->second;
+    g_cache.live.erase(it);
+    if (g_cache.cached_bytes + bytes > g_cache.limit()) {
+        FM_CUDA(cudaFree(dev));
+        return FM_OK;
+    }
+    g_cache.free_blocks.emplace(bytes, dev);
+    g_cache.cached_bytes += bytes;
+    return FM_OK;
+}
+int fm_trim_cache(void) {
+    FM_TRY(ensure_init());
+    g_cache.trim();
     return FM_OK;
 }
 int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n) {
@@ -271,8 +336,7 @@ int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
     int rc = k_eye(x, ldx, n, n, 0);
     if (rc == FM_OK) rc = k_getrs(n, n, a, lda, 0, ipiv, 0, x, ldx, 0, 1);
     if (rc == FM_OK) rc = k_copy2d(a, lda, x, ldx, n, n);
-    cudaStreamSynchronize(g_ctx.stream);
-    cudaFree(x);
+    fm_free(x);
     return rc;
 }
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
@@ -390,7 +454,7 @@ struct StagedVec {
         if (is_device_ptr(p) || count <= 0) { dev = const_cast<double *>(p); inc = incp; return FM_OK; }
         host = const_cast<double *>(p); inch = incp;
         const int len = (incp == 0) ? 1 : count;
-        if (cudaMalloc(&dev, (size_t)(len < 2 ? 2 : len) * 8) != cudaSuccess) { cudaGetLastError(); return set_error(FM_ERR_NOMEM, "staging allocation failed"); }
+        if (!(dev = static_cast<double *>(fm_alloc_bytes((size_t)(len < 2 ? 2 : len) * 8)))) return set_error(FM_ERR_NOMEM, "staging allocation failed");
         owned = true;
         inc = (incp == 0) ? 0 : 1;
         if (copy_in) {
@@ -412,7 +476,7 @@ struct StagedVec {
         FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
         return FM_OK;
     }
-    ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); cudaFree(dev); } }
+    ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); fm_free(dev); } }
 };
 
 void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY) {
@@ -495,7 +559,7 @@ void dgetrf_(const int *m, const int *n, double *a, const int *lda, int32_t *ipi
         if (rc == FM_OK) rc = fm_download_i32(&hinfo, d_info, 1);
         if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)mn);
         if (rc == FM_OK) *info = hinfo;
-        if (ipiv_dev) { if (d_info) cudaFree(d_info); } else if (d_ipiv) cudaFree(d_ipiv);
+        if (ipiv_dev) { if (d_info) fm_free(d_info); } else if (d_ipiv) fm_free(d_ipiv);
     }
     report("dgetrf_", rc);
     if (rc != FM_OK) *info = rc;
@@ -530,7 +594,7 @@ void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *i
         if (rc == FM_OK && hinfo == 0) rc = B.out();
         if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)*n);
         if (rc == FM_OK) { cudaStreamSynchronize(g_ctx.stream); *info = hinfo; }
-        if (ipiv_dev) { if (d_info) cudaFree(d_info); } else if (d_ipiv) cudaFree(d_ipiv);
+        if (ipiv_dev) { if (d_info) fm_free(d_info); } else if (d_ipiv) fm_free(d_ipiv);
     }
     report("dgesv_", rc);
     if (rc != FM_OK) *info = rc;
@@ -568,7 +632,7 @@ void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, doubl
         if (rc == FM_OK && *info == 0) rc = fm_getri(*n, A.dev, A.ld, d_ipiv, nullptr);
         if (rc == FM_OK && *info == 0) rc = A.out();
         if (rc == FM_OK) cudaStreamSynchronize(g_ctx.stream);
-        if (!ipiv_dev && d_ipiv) cudaFree(d_ipiv);
+        if (!ipiv_dev && d_ipiv) fm_free(d_ipiv);
     }
     report("dgetri_", rc);
     if (rc != FM_OK) *info = rc;

@@ -90,8 +90,8 @@ __device__ __forceinline__ bool warp_argmax(unsigned long long key, int pos, boo
 // U12 is written back to the pivot rows one leaf later (after the cluster barrier that proves every CTA has read the old
 // values).  ipiv gets LAPACK's interchange sequence, map[] the panel's net permutation.
 // ---------------------------------------------------------------------------------------------
-template <int NT, int RPT>
-__global__ void __launch_bounds__(NT, 1)
+template <int NT, int RPT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB)
 lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, int32_t *ipiv, long long sp, int32_t *info, int2 *map,
                 long long smap) {
     constexpr int W = LEAF, NWARP = NT / 32, ROWS = NT * RPT;
@@ -323,7 +323,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         {
             // columns per batch; two batches are in flight (the loads of batch i+1 are issued before the FMAs of batch i):
             // the update is bound by the L2 round trip of these loads, not by the FP64 pipe
-            constexpr int CU = RPT >= 4 ? 2 : (RPT == 2 ? 4 : 12);
+            constexpr int CU = MINB > 1 ? 2 : (RPT >= 4 ? 2 : (RPT == 2 ? 4 : 12));
             bool rowok[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; ++k) rowok[k] = pos[k] >= 0;
@@ -691,12 +691,12 @@ struct Maps {
 
 constexpr int PANEL_DYN_SMEM = 2 * LEAF * NB * (int)sizeof(double);
 
-template <int NT, int RPT>
+template <int NT, int RPT, int MINB = 1>
 int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize) {
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_DYN_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_DYN_SMEM));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -711,7 +711,7 @@ int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT>, A.at(j0, j0), (long long)A.lda, A.stride, m, pw, j0, ipiv, sp, info,
+    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT, MINB>, A.at(j0, j0), (long long)A.lda, A.stride, m, pw, j0, ipiv, sp, info,
                                maps.panel(j0), maps.item_stride));
     count_launch();
     return FM_OK;
@@ -726,6 +726,8 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
         return cs;
     };
     if (csize_out) *csize_out = m <= 4096 ? pow2_ctas(m, 256) : 16;
+    // many small independent panels (batched expm): a lean 128-thread variant, four CTAs per SM, one wave for 592 items
+    if (A.batch >= 64 && m <= 256) return launch_panel<128, 2, 4>(A, j0, m, pw, ipiv, sp, info, maps, 1);
     if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
     if (m <= 8192) {
         static const bool wide = getenv("FLOMAT_LU_PANEL_512") != nullptr;  // developer switch for A/B timing
