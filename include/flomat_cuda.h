@@ -36,6 +36,19 @@ extern "C" {
 #define FM_COL_MAJOR 102
 #define FM_NO_TRANS 111
 #define FM_TRANS 112
+/* fm_ewise ops / fm_map functions */
+#define FM_OP_ADD 0
+#define FM_OP_SUB 1
+#define FM_OP_MUL 2
+#define FM_OP_DIV 3
+#define FM_OP_EXPT 4
+#define FM_MAP_SIN 5
+#define FM_MAP_COS 6
+#define FM_MAP_TAN 7
+#define FM_MAP_SQR 8
+#define FM_MAP_SQRT 9
+#define FM_MAP_LOG 10
+#define FM_MAP_EXP 11
 
 /* ------------------------------------------------------------------------------------------------
  * Tier 1: compat symbols -- exact names and C signatures implied by the reference `_fun` types.
@@ -61,6 +74,20 @@ void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *i
             int *info);
 /* flomat.rkt:1754-1768, call site :1778; work/lwork are accepted and ignored (workspace is device-side) */
 void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, double *work, const int *lwork, int *info);
+/* --- neighbours of the hot path: same host-or-device convention --- */
+/* flomat.rkt:934-947, call site :949 (flomat*vector :957-978); order is always 102 */
+void cblas_dgemv(int order, int transA, int M, int N, double alpha, const double *A, int lda, const double *X, int incX,
+                 double beta, double *Y, int incY);
+/* flomat.rkt:1916-1921, call sites :1924 and `unsafe-sum` :2074 (incY = 0 against a single 1.0) */
+double cblas_ddot(int n, const double *X, int incX, const double *Y, int incY);
+/* flomat.rkt:1299-1302, call site :1943 */
+double cblas_dnrm2(int n, const double *X, int incX);
+/* flomat.rkt:1156-1160, call sites :1167-1176; 0-based index of the first largest |x| (CBLAS convention) */
+int cblas_idamax(int n, const double *X, int incX);
+/* flomat.rkt:1074-1079, call sites :1088 (rows, inc = lda) and :1103 (columns) */
+void cblas_dswap(int n, double *X, int incX, double *Y, int incY);
+/* flomat.rkt:2798-2803, call sites :2818-2850 (`rand` idist 1, `randn` idist 3); iseed: 4 ints in 0..4095, updated */
+void dlarnv_(const int *idist, int32_t *iseed, const int *n, double *x);
 
 /* ------------------------------------------------------------------------------------------------
  * Tier 2: device-resident flomat buffers (replaces alloc-flomat :437, copy-flomat :516, make-flomat :538,
@@ -126,6 +153,31 @@ int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int l
 int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info); /* a := inv from its LU */
 /* flomat-determinant-from-plu (flomat.rkt:1837): sign(ipiv) * left-to-right product of diag(LU); syncs */
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out);
+
+/* ---- neighbours of the hot path kept on the device ---- */
+/* B (n x m) := A' ; flomat-transpose flomat.rkt:1360-1369 (a Racket loop in the reference) */
+int fm_transpose(int m, int n, const double *a, int lda, double *b, int ldb);
+/* B (m x n) := triangle of A, zeros outside, optionally ones on the diagonal:
+ * flomat-extract-upper :1540 (lower=0), flomat-extract-lower :1566 (lower=1), flomat-extract-lower/ones :1553 (unit=1) */
+int fm_tri(int lower, int unit_diag, int m, int n, const double *a, int lda, double *b, int ldb);
+/* P (k x k) := the permutation matrix of an LU's pivots; pivots->flomat flomat.rkt:1471-1484 (ipiv 1-based, device) */
+int fm_pivots_to_matrix(int k, const int32_t *ipiv, double *p, int ldp);
+/* C := f(A) elementwise, fn = FM_MAP_*: the `.sin .cos .tan .sqr .sqrt .log .exp` family, flomat.rkt:2990-3019;
+ * `.expt` is fm_ewise with FM_OP_EXPT (flomat.rkt:3076) */
+int fm_map(int fn, int m, int n, const double *a, int lda, double *c, int ldc);
+/* y := alpha op(A) x + beta y (device operands); constant*matrix*vector+constant*vector! flomat.rkt:949-959 */
+int fm_gemv(int trans, int m, int n, double alpha, const double *a, int lda, const double *x, int incx, double beta,
+            double *y, int incy);
+int fm_dot(int n, const double *x, int incx, const double *y, int incy, double *out);   /* cblas_ddot, syncs */
+int fm_nrm2(int n, const double *x, int incx, double *out);                             /* cblas_dnrm2, syncs */
+int fm_iamax(int n, const double *x, int incx, int *out);                               /* cblas_idamax (0-based), syncs */
+int fm_swap(int n, double *x, int incx, double *y, int incy);                           /* cblas_dswap */
+/* out[j] = sum_i A(i,j) / out[i] = sum_j A(i,j): flomat-column-sums :2094, flomat-row-sums :2101 (n or m ddots there) */
+int fm_colsums(int m, int n, const double *a, int lda, double *out);
+int fm_rowsums(int m, int n, const double *a, int lda, double *out);
+/* dlarnv on the device: x[0..n) from LAPACK's 48-bit multiplicative generator (bit-identical uniforms; normals by the same
+ * Box-Muller pairing, within a few ulp of libm); iseed (host, 4 ints in 0..4095) is advanced exactly like DLARNV does */
+int fm_larnv(int idist, int32_t *iseed, long long n, double *x);
 
 /* expm (expm.rkt:203): out := exp(A) by Pade [8/8] scaling-and-squaring, everything on device.
  * *s_out receives the scaling exponent 1+ceil(log2 ||A||_1) the reference computes (may be <= 0).

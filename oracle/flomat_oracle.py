@@ -393,6 +393,139 @@ class Flomat:
             prod = prod * float(lu[i, i])
         return sign * prod
 
+    # -- neighbours of the hot path: restated from the Racket loops / BLAS call sites ----------
+    @staticmethod
+    def transpose(a):
+        """flomat-transpose (flomat.rkt:1360-1369): AT[j, i] = A[i, j]."""
+        return fortran(np.asarray(a).T.copy())
+
+    def mrdivide(self, b, a):
+        """mrdivide (flomat.rkt:3293-3295): (transpose (mldivide (transpose A) (transpose B)))."""
+        return self.transpose(self.mldivide(self.transpose(a), self.transpose(b)))
+
+    @staticmethod
+    def extract_upper(a):
+        """flomat-extract-upper (flomat.rkt:1540-1551): k x k, entries with i <= j."""
+        k = min(a.shape)
+        u = np.zeros((k, k), order="F")
+        for j in range(k):
+            for i in range(min(j + 1, k)):
+                u[i, j] = a[i, j]
+        return u
+
+    @staticmethod
+    def extract_lower(a, ones=False):
+        """flomat-extract-lower (flomat.rkt:1566-1573) / flomat-extract-lower/ones (:1553-1564)."""
+        l = fortran(np.array(a, dtype=np.float64))
+        m, n = l.shape
+        for j in range(n):
+            for i in range(min(j, m)):
+                l[i, j] = 0.0
+        if ones:
+            for j in range(min(m, n)):
+                l[j, j] = 1.0
+        return l
+
+    @staticmethod
+    def pivots_to_matrix(ipiv):
+        """pivots->flomat (flomat.rkt:1471-1484): identity, then for i = k-1 .. 0 swap rows i and ipiv[i] (0-based there)."""
+        k = len(ipiv)
+        p = np.zeros((k, k), order="F")
+        for i in range(k):
+            p[i, i] = 1.0
+        for i in range(k - 1, -1, -1):
+            i2 = int(ipiv[i]) - 1
+            if i != i2:
+                p[[i, i2], :] = p[[i2, i], :]
+        return p
+
+    def plu(self, a):
+        """flomat-plu (flomat.rkt:1529-1536)."""
+        lu, ipiv, _ = self.lu(a)
+        return self.pivots_to_matrix(ipiv[: min(a.shape)]), self.extract_lower(lu, ones=True), self.extract_upper(lu)
+
+    @staticmethod
+    def times_vector(a, x, y=None, alpha=1.0, beta=1.0, transpose_a=False):
+        """flomat*vector (flomat.rkt:970-978) -> cblas_dgemv (:949): Y := alpha op(A) X + beta Y, Y = zeros when omitted."""
+        op = a.T if transpose_a else a
+        x = np.asarray(x, dtype=np.float64).reshape(-1)
+        acc = np.zeros(op.shape[0])
+        for j in range(op.shape[1]):  # reference DGEMV (no-transpose form): column sweeps
+            acc += op[:, j] * x[j]
+        y0 = np.zeros(op.shape[0]) if y is None else np.asarray(y, dtype=np.float64).reshape(-1)
+        return fortran((alpha * acc + beta * y0).reshape(-1, 1))
+
+    @staticmethod
+    def dot(x, y):
+        """dot / flcolumn-dot (flomat.rkt:3216, :1926) -> cblas_ddot: sequential sum of products."""
+        acc = 0.0
+        for u, v in zip(np.asarray(x).reshape(-1), np.asarray(y).reshape(-1)):
+            acc += float(u) * float(v)
+        return acc
+
+    @staticmethod
+    def column_norm(v):
+        """flcolumn-norm (flomat.rkt:1941) -> cblas_dnrm2 (scaled sum of squares)."""
+        x = np.abs(np.asarray(v, dtype=np.float64).reshape(-1))
+        s = x.max() if x.size else 0.0
+        return float(s * math.sqrt(((x / s) ** 2).sum())) if s > 0 else 0.0
+
+    @staticmethod
+    def max_abs_index(a):
+        """flomat-max-abs-index (flomat.rkt:1163-1178): idamax over the column-major buffer, first maximum wins."""
+        flat = np.abs(np.asarray(a, dtype=np.float64)).reshape(-1, order="F")
+        idx = int(np.argmax(flat))
+        return idx % a.shape[0], idx // a.shape[0]
+
+    def colsums(self, a):
+        """flomat-column-sums (flomat.rkt:2094): 1 x n, each entry `unsafe-sum` = ddot against a 1.0 with stride 0 (:2066)."""
+        return fortran(np.array([[self.dot(a[:, j], np.ones(a.shape[0])) for j in range(a.shape[1])]]))
+
+    def rowsums(self, a):
+        """flomat-row-sums (flomat.rkt:2101): m x 1."""
+        return fortran(np.array([[self.dot(a[i, :], np.ones(a.shape[1]))] for i in range(a.shape[0])]))
+
+    @staticmethod
+    def pointwise(fn, a, b=None):
+        """define-pointwise-unaries / -binaries (flomat.rkt:2990-3076): f applied per element with the C library's libm
+        (Racket's flsin, flcos, ... call it), `sqr` = x*x, `expt` = pow."""
+        f = {"sin": math.sin, "cos": math.cos, "tan": math.tan, "sqr": lambda x: x * x, "sqrt": math.sqrt, "log": math.log,
+             "exp": math.exp, "expt": math.pow}[fn]
+        a = np.asarray(a, dtype=np.float64)
+        out = np.empty(a.shape, order="F")
+        if b is None:
+            for idx in np.ndindex(a.shape):
+                out[idx] = f(float(a[idx]))
+        else:
+            bb = np.broadcast_to(np.asarray(b, dtype=np.float64), a.shape)
+            for idx in np.ndindex(a.shape):
+                out[idx] = f(float(a[idx]), float(bb[idx]))
+        return out
+
+    # -- dlarnv (flomat.rkt:2798-2852): LAPACK's DLARUV multiplicative congruential generator restated in exact integers ----
+    LCG_A = 33952834046453  # dlaruv.f: MM(1,:) = (494, 322, 2508, 2549) in base 4096; row i of the table is a^i mod 2^48
+
+    @classmethod
+    def dlarnv(cls, idist, iseed, n):
+        """DLARNV: returns (x, new_iseed).  x_k = (s0 a^k mod 2^48) 2^-48 (DLARUV), idist 2: 2u-1, idist 3:
+        sqrt(-2 ln u_{2k-1}) cos(2 pi u_{2k}); the seed advances by one multiplication per uniform drawn."""
+        s = (int(iseed[0]) << 36) | (int(iseed[1]) << 24) | (int(iseed[2]) << 12) | int(iseed[3])
+        mask = (1 << 48) - 1
+        x = np.empty(n)
+        twopi = 6.28318530717958647692528676655900576839
+        for k in range(n):
+            s = (s * cls.LCG_A) & mask
+            u = s * 2.0 ** -48
+            if idist == 1:
+                x[k] = u
+            elif idist == 2:
+                x[k] = 2.0 * u - 1.0
+            else:
+                s = (s * cls.LCG_A) & mask
+                u2 = s * 2.0 ** -48
+                x[k] = math.sqrt(-2.0 * math.log(u)) * math.cos(twopi * u2)
+        return x, np.array([(s >> 36) & 4095, (s >> 24) & 4095, (s >> 12) & 4095, s & 4095], dtype=np.int32)
+
     # -- expm: expm.rkt:167-215 ----------------------------------------------------------------------------
     def mpoly(self, cs, a):
         """mpoly (expm.rkt:167-177): Horner seeded with the zero matrix; (plus (.* c I) (times A rest))."""

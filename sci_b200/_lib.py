@@ -33,6 +33,12 @@ SIGNATURES = {
     "dgetrf_": (None, [POINTER(c_int), POINTER(c_int), _DP, POINTER(c_int), _IP, POINTER(c_int)]),
     "dgesv_": (None, [POINTER(c_int), POINTER(c_int), _DP, POINTER(c_int), _IP, _DP, POINTER(c_int), POINTER(c_int)]),
     "dgetri_": (None, [POINTER(c_int), _DP, POINTER(c_int), _IP, _DP, POINTER(c_int), POINTER(c_int)]),
+    "cblas_dgemv": (None, [c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
+    "cblas_ddot": (c_double, [c_int, _DP, c_int, _DP, c_int]),
+    "cblas_dnrm2": (c_double, [c_int, _DP, c_int]),
+    "cblas_idamax": (c_int, [c_int, _DP, c_int]),
+    "cblas_dswap": (None, [c_int, _DP, c_int, _DP, c_int]),
+    "dlarnv_": (None, [POINTER(c_int), _IP, POINTER(c_int), _DP]),
     # tier 2
     "fm_init": (c_int, [c_int]),
     "fm_device_count": (c_int, []),
@@ -59,6 +65,18 @@ SIGNATURES = {
     "fm_scal2d": (c_int, [c_int, c_int, c_double, _DP, c_int]),
     "fm_addsub": (c_int, [c_int, c_int, _DP, c_int, _DP, c_int, _DP, c_int, _DP, c_int]),
     "fm_norm": (c_int, [c_char, c_int, c_int, _DP, c_int, POINTER(c_double)]),
+    "fm_transpose": (c_int, [c_int, c_int, _DP, c_int, _DP, c_int]),
+    "fm_tri": (c_int, [c_int, c_int, c_int, c_int, _DP, c_int, _DP, c_int]),
+    "fm_pivots_to_matrix": (c_int, [c_int, _IP, _DP, c_int]),
+    "fm_map": (c_int, [c_int, c_int, c_int, _DP, c_int, _DP, c_int]),
+    "fm_gemv": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
+    "fm_dot": (c_int, [c_int, _DP, c_int, _DP, c_int, POINTER(c_double)]),
+    "fm_nrm2": (c_int, [c_int, _DP, c_int, POINTER(c_double)]),
+    "fm_iamax": (c_int, [c_int, _DP, c_int, POINTER(c_int)]),
+    "fm_swap": (c_int, [c_int, _DP, c_int, _DP, c_int]),
+    "fm_colsums": (c_int, [c_int, c_int, _DP, c_int, _DP]),
+    "fm_rowsums": (c_int, [c_int, c_int, _DP, c_int, _DP]),
+    "fm_larnv": (c_int, [c_int, _IP, c_longlong, _DP]),
     "fm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
     "fm_dgemm_diag": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_double]),
     "fm_dgemm_batched": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_double, _DP, c_int,

@@ -348,6 +348,80 @@ int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
     return FM_OK;
 }
 
+// =================================== neighbours of the hot path (N2-N4) ===================================
+int fm_transpose(int m, int n, const double *a, int lda, double *b, int ldb) {
+    FM_TRY(ensure_init());
+    return k_transpose(m, n, a, lda, b, ldb);
+}
+int fm_tri(int lower, int unit_diag, int m, int n, const double *a, int lda, double *b, int ldb) {
+    FM_TRY(ensure_init());
+    return k_tri(lower, unit_diag, m, n, a, lda, b, ldb);
+}
+int fm_pivots_to_matrix(int k, const int32_t *ipiv, double *p, int ldp) {
+    FM_TRY(ensure_init());
+    return k_pivots_to_matrix(k, ipiv, p, ldp);
+}
+int fm_map(int fn, int m, int n, const double *a, int lda, double *c, int ldc) {
+    FM_TRY(ensure_init());
+    if (fn < 5 || fn > 11) return set_error(FM_ERR_ARG, "fm_map: fn %d not in FM_MAP_SIN..FM_MAP_EXP", fn);
+    return k_ewise(fn, m, n, a, lda, 0.0, nullptr, 0, 0.0, c, ldc);
+}
+int fm_gemv(int trans, int m, int n, double alpha, const double *a, int lda, const double *x, int incx, double beta, double *y, int incy) {
+    FM_TRY(ensure_init());
+    if (trans != FM_TRANS && trans != FM_NO_TRANS) return set_error(FM_ERR_ARG, "fm_gemv: trans must be 111 or 112");
+    if (incx <= 0 || incy <= 0) return set_error(FM_ERR_ARG, "fm_gemv: increments must be positive");
+    if (!x) return set_error(FM_ERR_ARG, "fm_gemv: x is NULL");
+    return k_gemv(trans == FM_TRANS, m, n, alpha, a, lda, x, incx, beta, y, incy);
+}
+static int scalar_back(double *out) {
+    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    *out = g_ctx.h_scalar[0];
+    return FM_OK;
+}
+int fm_dot(int n, const double *x, int incx, const double *y, int incy, double *out) {
+    FM_TRY(ensure_init());
+    if (incx < 0 || incy < 0) return set_error(FM_ERR_ARG, "fm_dot: negative increments are not used by flomat and not supported");
+    FM_TRY(k_dot_device(n, x, incx, y, incy, g_ctx.d_scalar));
+    return scalar_back(out);
+}
+int fm_nrm2(int n, const double *x, int incx, double *out) {
+    FM_TRY(ensure_init());
+    if (incx <= 0) { *out = 0.0; return FM_OK; }
+    FM_TRY(k_nrm2_device(n, x, incx, g_ctx.d_scalar));
+    return scalar_back(out);
+}
+int fm_iamax(int n, const double *x, int incx, int *out) {
+    FM_TRY(ensure_init());
+    *out = 0;
+    if (n <= 0 || incx <= 0) return FM_OK;
+    FM_TRY(k_iamax_device(n, x, incx, reinterpret_cast<long long *>(g_ctx.d_scalar)));
+    double raw;
+    FM_TRY(scalar_back(&raw));
+    long long idx;
+    memcpy(&idx, &raw, sizeof(idx));
+    *out = (int)idx;
+    return FM_OK;
+}
+int fm_swap(int n, double *x, int incx, double *y, int incy) {
+    FM_TRY(ensure_init());
+    if (incx < 0 || incy < 0) return set_error(FM_ERR_ARG, "fm_swap: negative increments are not used by flomat and not supported");
+    return k_swap(n, x, incx, y, incy);
+}
+int fm_colsums(int m, int n, const double *a, int lda, double *out) {  // out[j] = sum_i A(i,j): A' * ones
+    FM_TRY(ensure_init());
+    return k_gemv(1, m, n, 1.0, a, lda, nullptr, 0, 0.0, out, 1);
+}
+int fm_rowsums(int m, int n, const double *a, int lda, double *out) {  // out[i] = sum_j A(i,j): A * ones
+    FM_TRY(ensure_init());
+    return k_gemv(0, m, n, 1.0, a, lda, nullptr, 0, 0.0, out, 1);
+}
+int fm_larnv(int idist, int32_t *iseed, long long n, double *x) {
+    FM_TRY(ensure_init());
+    if (!iseed) return set_error(FM_ERR_ARG, "fm_larnv: iseed is NULL");
+    return k_larnv(idist, iseed, n, x);
+}
+
 // =================================== expm ===================================
 int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host) {
     FM_TRY(ensure_init());
@@ -515,6 +589,87 @@ void cblas_dscal(int n, double alpha, double *X, int incX) {
         if (rc == FM_OK) rc = x.out();
     }
     report("cblas_dscal", rc);
+}
+
+void cblas_dgemv(int order, int transA, int M, int N, double alpha, const double *A, int lda, const double *X, int incX, double beta,
+                 double *Y, int incY) {
+    if (M <= 0 || N <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK && order != 102) rc = set_error(FM_ERR_ARG, "cblas_dgemv: only CblasColMajor (102) is used by flomat (flomat.rkt:949)");
+    if (rc == FM_OK && (incX <= 0 || incY <= 0)) rc = set_error(FM_ERR_ARG, "cblas_dgemv: increments must be positive");
+    if (rc == FM_OK) {
+        const bool t = transA != FM_NO_TRANS;
+        Staged a;
+        StagedVec x, y;
+        rc = a.in(A, lda, M, N, true);
+        if (rc == FM_OK) rc = x.in(X, incX, t ? M : N, true);
+        if (rc == FM_OK) rc = y.in(Y, incY, t ? N : M, true);
+        if (rc == FM_OK) rc = k_gemv(t, M, N, alpha, a.dev, a.ld, x.dev, x.inc, beta, y.dev, y.inc);
+        if (rc == FM_OK) rc = y.out();
+    }
+    report("cblas_dgemv", rc);
+}
+double cblas_ddot(int n, const double *X, int incX, const double *Y, int incY) {
+    if (n <= 0) return 0.0;
+    double out = 0.0;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        StagedVec x, y;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = y.in(Y, incY, n, true);
+        if (rc == FM_OK) rc = fm_dot(n, x.dev, (int)x.inc, y.dev, (int)y.inc, &out);
+    }
+    report("cblas_ddot", rc);
+    return rc == FM_OK ? out : nan("");
+}
+double cblas_dnrm2(int n, const double *X, int incX) {
+    if (n <= 0 || incX <= 0) return 0.0;
+    double out = 0.0;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        StagedVec x;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = fm_nrm2(n, x.dev, (int)x.inc, &out);
+    }
+    report("cblas_dnrm2", rc);
+    return rc == FM_OK ? out : nan("");
+}
+int cblas_idamax(int n, const double *X, int incX) {
+    if (n <= 0 || incX <= 0) return 0;
+    int out = 0;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        StagedVec x;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = fm_iamax(n, x.dev, (int)x.inc, &out);
+    }
+    report("cblas_idamax", rc);
+    return out;
+}
+void cblas_dswap(int n, double *X, int incX, double *Y, int incY) {
+    if (n <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK && (incX <= 0 || incY <= 0)) rc = set_error(FM_ERR_ARG, "cblas_dswap: increments must be positive");
+    if (rc == FM_OK) {
+        StagedVec x, y;
+        rc = x.in(X, incX, n, true);
+        if (rc == FM_OK) rc = y.in(Y, incY, n, true);
+        if (rc == FM_OK) rc = k_swap(n, x.dev, x.inc, y.dev, y.inc);
+        if (rc == FM_OK) rc = x.out();
+        if (rc == FM_OK) rc = y.out();
+    }
+    report("cblas_dswap", rc);
+}
+void dlarnv_(const int *idist, int32_t *iseed, const int *n, double *x) {
+    if (*n <= 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        StagedVec v;
+        rc = v.in(x, 1, *n, false);
+        if (rc == FM_OK) rc = k_larnv(*idist, iseed, *n, v.dev);
+        if (rc == FM_OK) rc = v.out();
+    }
+    report("dlarnv_", rc);
 }
 
 double dlange_(const char *norm, const int *m, const int *n, const double *a, const int *lda, double *work) {

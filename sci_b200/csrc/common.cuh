@@ -99,6 +99,16 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);
+// level12.cu
+int k_transpose(int m, int n, const double *a, int lda, double *b, int ldb);
+int k_tri(int lower, int unit, int m, int n, const double *a, int lda, double *b, int ldb);
+int k_pivots_to_matrix(int k, const int32_t *ipiv, double *p, int ldp);
+int k_dot_device(long long n, const double *x, long long incx, const double *y, long long incy, double *d_out);
+int k_nrm2_device(long long n, const double *x, long long incx, double *d_out);
+int k_iamax_device(long long n, const double *x, long long incx, long long *d_out);
+int k_swap(long long n, double *x, long long incx, double *y, long long incy);
+int k_gemv(int trans, int m, int n, double alpha, const double *a, int lda, const double *x, long long incx, double beta, double *y, long long incy);
+int k_larnv(int idist, int32_t *iseed_host, long long n, double *x);
 // expm.cu
 int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
 int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out);

@@ -19,7 +19,17 @@ __device__ __forceinline__ double apply_op(int op, double x, double y) {
         case 0: return x + y;
         case 1: return x - y;
         case 2: return x * y;
-        default: return x / y;
+        case 3: return x / y;
+        // the rest of the pointwise family (flomat.rkt:3019 `define-pointwise-unaries sin cos tan sqr sqrt log exp`, :3076 `expt`);
+        // unary maps ignore y.  sqr and sqrt are correctly rounded; the transcendental ones are CUDA libdevice (<= 2 ulp).
+        case 4: return pow(x, y);
+        case 5: return sin(x);
+        case 6: return cos(x);
+        case 7: return tan(x);
+        case 8: return x * x;
+        case 9: return sqrt(x);
+        case 10: return log(x);
+        default: return exp(x);
     }
 }
 
@@ -283,7 +293,8 @@ void dispatch_mode(int mode, const Shape &s, const double *a, int lda, double sa
 }  // namespace
 
 int k_ewise(int op, int m, int n, const double *a, int lda, double sa, const double *b, int ldb, double sb, double *c, int ldc) {
-    if (op < 0 || op > 3) return set_error(FM_ERR_ARG, "fm_ewise: op %d not in 0..3", op);
+    if (op < 0 || op > 11) return set_error(FM_ERR_ARG, "fm_ewise: op %d not in 0..11", op);
+    if (op >= 5 && !a) return set_error(FM_ERR_ARG, "fm_ewise: a unary map needs a matrix operand A");
     if (m < 0 || n < 0) return set_error(FM_ERR_ARG, "fm_ewise: negative dimension");
     if (!a && !b) return set_error(FM_ERR_ARG, "fm_ewise: at least one operand must be a matrix");
     if (!c) return set_error(FM_ERR_ARG, "fm_ewise: C is NULL");
@@ -292,12 +303,20 @@ int k_ewise(int op, int m, int n, const double *a, int lda, double sa, const dou
     const void *ptrs[3] = {a, b, c};
     const int lds[3] = {lda, ldb, ldc};
     Shape s = plan(m, n, ptrs, lds, 3);
-    const int mode = (a && b) ? 0 : (a ? 1 : 2);
+    const int mode = (a && b && op < 5) ? 0 : (a ? 1 : 2);
     switch (op) {
         case 0: dispatch_mode<0>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
         case 1: dispatch_mode<1>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
         case 2: dispatch_mode<2>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
-        default: dispatch_mode<3>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 3: dispatch_mode<3>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 4: dispatch_mode<4>(mode, s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 5: launch_ewise<5, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 6: launch_ewise<6, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 7: launch_ewise<7, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 8: launch_ewise<8, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 9: launch_ewise<9, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        case 10: launch_ewise<10, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
+        default: launch_ewise<11, 1>(s, a, lda, sa, b, ldb, sb, c, ldc); break;
     }
     FM_LAUNCH_CHECK();
     return FM_OK;

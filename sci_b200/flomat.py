@@ -26,7 +26,8 @@ from . import _lib
 from ._lib import FlomatCudaError, check
 
 NO_TRANS, TRANS = 111, 112
-OP_ADD, OP_SUB, OP_MUL, OP_DIV = 0, 1, 2, 3
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_EXPT = 0, 1, 2, 3, 4
+MAP_SIN, MAP_COS, MAP_TAN, MAP_SQR, MAP_SQRT, MAP_LOG, MAP_EXP = 5, 6, 7, 8, 9, 10, 11
 
 
 def _L():
@@ -425,6 +426,204 @@ def det(a: Flomat) -> float:
     out = c_double()
     check(_L().fm_det(a.m, lu.a, lu.lda, piv.ptr, byref(out)), "fm_det")
     return out.value
+
+
+# --------------------------------------------------------------------------------------------------
+# neighbours of the hot path kept on the device
+# --------------------------------------------------------------------------------------------------
+def transpose(a: Flomat) -> Flomat:
+    """`transpose` / flomat-transpose (flomat.rkt:1360): a fresh n x m matrix."""
+    out = Flomat.alloc(a.n, a.m)
+    check(_L().fm_transpose(a.m, a.n, a.a, a.lda, out.a, out.lda), "fm_transpose")
+    return out
+
+
+def mrdivide(b: Flomat, a: Flomat) -> Flomat:
+    """`mrdivide` (flomat.rkt:3293): B/A = (A'\\B')'."""
+    return transpose(mldivide(transpose(a), transpose(b)))
+
+
+def flomat_extract_upper(a: Flomat) -> Flomat:
+    """flomat-extract-upper (flomat.rkt:1540): the k x k upper triangle (k = min(m, n)), diagonal included."""
+    k = min(a.m, a.n)
+    out = Flomat.alloc(k, k)
+    check(_L().fm_tri(0, 0, k, k, a.a, a.lda, out.a, out.lda), "fm_tri")
+    return out
+
+
+def flomat_extract_lower(a: Flomat) -> Flomat:
+    """flomat-extract-lower (flomat.rkt:1566): copy with everything above the diagonal zeroed."""
+    out = Flomat.alloc(a.m, a.n)
+    check(_L().fm_tri(1, 0, a.m, a.n, a.a, a.lda, out.a, out.lda), "fm_tri")
+    return out
+
+
+def flomat_extract_lower_ones(a: Flomat) -> Flomat:
+    """flomat-extract-lower/ones (flomat.rkt:1553): strictly lower part with ones on the diagonal."""
+    out = Flomat.alloc(a.m, a.n)
+    check(_L().fm_tri(1, 1, a.m, a.n, a.a, a.lda, out.a, out.lda), "fm_tri")
+    return out
+
+
+def pivots_to_flomat(ps: "Pivots") -> Flomat:
+    """pivots->flomat (flomat.rkt:1471): the permutation matrix P with A = P L U."""
+    out = Flomat.alloc(ps.n, ps.n)
+    check(_L().fm_pivots_to_matrix(ps.n, ps.ptr, out.a, out.lda), "fm_pivots_to_matrix")
+    return out
+
+
+def flomat_plu(a: Flomat):
+    """flomat-plu (flomat.rkt:1529): copy, dgetrf, then P, L (unit lower), U."""
+    b = copy_flomat(a)
+    ps, _info = flomat_lu_bang(b)
+    return pivots_to_flomat(ps), flomat_extract_lower_ones(b), flomat_extract_upper(b)
+
+
+def flomat_times_vector(a: Flomat, x: Flomat, y: Flomat | None = None, alpha: float = 1.0, beta: float = 1.0,
+                        transpose_a: bool = False) -> Flomat:
+    """flomat*vector (flomat.rkt:970): Y := alpha op(A) X + beta Y via dgemv; without Y a zero column is allocated."""
+    rows, cols = (a.n, a.m) if transpose_a else (a.m, a.n)
+    if x.n != 1 or x.m != cols:
+        raise ValueError(f"constant*matrix*vector+constant*vector!: expected a column of {cols} rows, got {x.m}x{x.n}")
+    if y is None:
+        y, beta = make_flomat(rows, 1, 0.0), 1.0
+    elif y.n != 1 or y.m != rows:
+        raise ValueError(f"constant*matrix*vector+constant*vector!: expected a column of {rows} rows, got {y.m}x{y.n}")
+    check(_L().fm_gemv(TRANS if transpose_a else NO_TRANS, a.m, a.n, float(alpha), a.a, a.lda, x.a, 1, float(beta), y.a, 1), "fm_gemv")
+    return y
+
+
+def dot(x: Flomat, y: Flomat) -> float:
+    """`dot` / flcolumn-dot (flomat.rkt:3216, :1926): ddot of two m x 1 columns."""
+    if x.n != 1 or y.n != 1 or x.m != y.m:
+        raise ValueError(f"column-dot: expected two mx1 matrices with same number of rows, got {x.m}x{x.n} and {y.m}x{y.n}")
+    out = c_double()
+    check(_L().fm_dot(x.m, x.a, 1, y.a, 1, byref(out)), "fm_dot")
+    return out.value
+
+
+def flcolumn_norm(v: Flomat) -> float:
+    """flcolumn-norm (flomat.rkt:1941): dnrm2 of the first column."""
+    out = c_double()
+    check(_L().fm_nrm2(v.m, v.a, 1, byref(out)), "fm_nrm2")
+    return out.value
+
+
+def flomat_max_abs_index(a: Flomat):
+    """flomat-max-abs-index (flomat.rkt:1163): (i, j) of the first entry of largest magnitude (column-major order)."""
+    idx = ctypes.c_int()
+    if a.lda == a.m or a.n == 1:
+        check(_L().fm_iamax(a.m * a.n, a.a, 1, byref(idx)), "fm_iamax")
+        return idx.value % max(a.m, 1), idx.value // max(a.m, 1)
+    best = None
+    for j in range(a.n):  # a view: one idamax per column, as the reference does (:1173-1178)
+        check(_L().fm_iamax(a.m, a.a + 8 * j * a.lda, 1, byref(idx)), "fm_iamax")
+        v = abs(a.ref(idx.value, j))
+        if best is None or v > best[0]:
+            best = (v, idx.value, j)
+    return best[1], best[2]
+
+
+def flomat_max_abs_value(a: Flomat) -> float:
+    i, j = flomat_max_abs_index(a)
+    return a.ref(i, j)
+
+
+def flomat_swap_rows_bang(a: Flomat, i1: int, i2: int) -> Flomat:
+    """flomat-swap-rows! (flomat.rkt:1081): dswap with stride lda."""
+    if not (0 <= i1 < a.m and 0 <= i2 < a.m):
+        raise IndexError("flomat-swap-rows!: row index out of range")
+    if i1 != i2:
+        check(_L().fm_swap(a.n, a.a + 8 * i1, a.lda, a.a + 8 * i2, a.lda), "fm_swap")
+    return a
+
+
+def flomat_swap_columns_bang(a: Flomat, j1: int, j2: int) -> Flomat:
+    """flomat-swap-columns! (flomat.rkt:1096)."""
+    if not (0 <= j1 < a.n and 0 <= j2 < a.n):
+        raise IndexError("flomat-swap-columns!: column index out of range")
+    if j1 != j2:
+        check(_L().fm_swap(a.m, a.a + 8 * j1 * a.lda, 1, a.a + 8 * j2 * a.lda, 1), "fm_swap")
+    return a
+
+
+def colsums(a: Flomat) -> Flomat:
+    """`colsums` / flomat-column-sums (flomat.rkt:2094): 1 x n row of column sums (n ddots against 1.0 in the reference)."""
+    out = Flomat.alloc(1, a.n)
+    check(_L().fm_colsums(a.m, a.n, a.a, a.lda, out.a), "fm_colsums")
+    return out
+
+
+def rowsums(a: Flomat) -> Flomat:
+    """`rowsums` / flomat-row-sums (flomat.rkt:2101): m x 1 column of row sums."""
+    out = Flomat.alloc(a.m, 1)
+    check(_L().fm_rowsums(a.m, a.n, a.a, a.lda, out.a), "fm_rowsums")
+    return out
+
+
+def _map(fn: int, a: Flomat, c: Flomat | None, who: str) -> Flomat:
+    if c is None:
+        c = Flomat.alloc(a.m, a.n)
+    else:
+        _check_same(a, c, who)
+    check(_L().fm_map(fn, a.m, a.n, a.a, a.lda, c.a, c.lda), who)
+    return c
+
+
+def dot_sin(a: Flomat, c: Flomat | None = None) -> Flomat:
+    """`.sin` (`define-pointwise-unaries`, flomat.rkt:3019); pass c=a for `.sin!`."""
+    return _map(MAP_SIN, a, c, ".sin")
+
+
+def dot_cos(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_COS, a, c, ".cos")
+
+
+def dot_tan(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_TAN, a, c, ".tan")
+
+
+def dot_sqr(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_SQR, a, c, ".sqr")
+
+
+def dot_sqrt(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_SQRT, a, c, ".sqrt")
+
+
+def dot_log(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_LOG, a, c, ".log")
+
+
+def dot_exp(a: Flomat, c: Flomat | None = None) -> Flomat:
+    return _map(MAP_EXP, a, c, ".exp")
+
+
+def dot_expt(a, b, c: Flomat | None = None) -> Flomat:
+    """`.expt` (`define-pointwise-binaries`, flomat.rkt:3076): matrix^matrix, matrix^number or number^matrix."""
+    return _ewise(OP_EXPT, a, b, c, ".expt")
+
+
+the_iseed = np.array([1, 2, 3, 5], dtype=np.int32)  # the package-wide LAPACK seed (the reference keeps one `the-iseed`)
+
+
+def _larnv(idist: int, m: int, n: int, iseed) -> Flomat:
+    seed = the_iseed if iseed is None else iseed
+    if seed.dtype != np.int32 or seed.shape != (4,):
+        raise ValueError("iseed: expected an int32 array of 4 entries")
+    out = Flomat.alloc(m, n)
+    check(_L().fm_larnv(idist, seed.ctypes.data, m * n, out.a), "fm_larnv")
+    return out
+
+
+def rand(m: int, n: int | None = None, iseed=None) -> Flomat:
+    """`rand` (flomat.rkt:2814): uniform (0,1) from LAPACK's dlarnv generator, generated on the device."""
+    return _larnv(1, m, m if n is None else n, iseed)
+
+
+def randn(m: int, n: int | None = None, iseed=None) -> Flomat:
+    """`randn` (flomat.rkt:2835): standard normal (dlarnv idist = 3)."""
+    return _larnv(3, m, m if n is None else n, iseed)
 
 
 # --------------------------------------------------------------------------------------------------

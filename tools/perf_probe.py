@@ -25,7 +25,7 @@ def randmat(n, m=None, scale=1.0, seed=0):
     lib.fm_copy2d(out.a, n, t.data_ptr(), n, n, m); fm.sync()
     return out
 
-what = sys.argv[1:] or ["ewise", "lu", "expm", "batched"]
+what = sys.argv[1:] or ["ewise", "level12", "lu", "expm", "batched"]
 res = {}
 if "ewise" in what:
     for n in (8192,):
@@ -38,6 +38,26 @@ if "ewise" in what:
             print(f"ewise {name} n={n}: {ms:.3f} ms  {bpe*n*n/ms/1e6:.0f} GB/s", flush=True)
             res[f"ewise_{name}_{n}"] = bpe * n * n / ms / 1e6
         del A, B, C
+if "level12" in what:
+    n = 8192
+    A = randmat(n, seed=11); B = fm.Flomat.alloc(n, n); x = randmat(n, 1, seed=12); y = fm.Flomat.alloc(n, 1)
+    iseed = np.array([1, 2, 3, 5], dtype=np.int32)
+    for name, fn, bpe in [("transpose", lambda: lib.fm_transpose(n, n, A.a, n, B.a, n), 16),
+                          ("triu", lambda: lib.fm_tri(0, 0, n, n, A.a, n, B.a, n), 16),
+                          (".exp", lambda: lib.fm_map(11, n, n, A.a, n, B.a, n), 16),
+                          (".sin", lambda: lib.fm_map(5, n, n, A.a, n, B.a, n), 16),
+                          (".sqrt", lambda: lib.fm_map(9, n, n, A.a, n, B.a, n), 16),
+                          ("gemv N", lambda: lib.fm_gemv(111, n, n, 1.0, A.a, n, x.a, 1, 0.0, y.a, 1), 8),
+                          ("gemv T", lambda: lib.fm_gemv(112, n, n, 1.0, A.a, n, x.a, 1, 0.0, y.a, 1), 8),
+                          ("colsums", lambda: lib.fm_colsums(n, n, A.a, n, y.a), 8),
+                          ("rowsums", lambda: lib.fm_rowsums(n, n, A.a, n, y.a), 8),
+                          ("nrm2 (n^2)", lambda: fm.flcolumn_norm(fm.Flomat(n * n, 1, A.a, n * n, A._buf)), 8),
+                          ("rand", lambda: lib.fm_larnv(1, iseed.ctypes.data, n * n, B.a), 8),
+                          ("randn", lambda: lib.fm_larnv(3, iseed.ctypes.data, n * n, B.a), 8)]:
+        ms = timeit(fn, reps=5, warm=2)
+        print(f"level12 {name} n={n}: {ms:.3f} ms  {bpe*n*n/ms/1e6:.0f} GB/s", flush=True)
+        res[f"l12_{name}"] = bpe * n * n / ms / 1e6
+    del A, B, x, y
 if "lu" in what:
     for n in [int(x) for x in os.environ.get("LU_N", "1024,2048,4096,8192").split(",")]:
         A0 = randmat(n, seed=3); A = fm.Flomat.alloc(n, n)
