@@ -104,39 +104,44 @@ __global__ void __launch_bounds__(RT) sum_final_kernel(int cnt, const double *pa
     if (threadIdx.x == 0) out[0] = r;
 }
 
-// dnrm2 without overflow: per CTA (scale, ssq) with ssq = sum (x/scale)^2 (the DLASSQ recurrence), combined pairwise
-__device__ __forceinline__ void ssq_combine(double &s, double &q, double s2, double q2) {
-    if (s2 == 0.0) return;
-    if (s >= s2) { const double r = s2 / s; q += q2 * r * r; }
-    else { const double r = s / s2; q = q2 + q * r * r; s = s2; }
-}
-__global__ void __launch_bounds__(RT) nrm2_partial_kernel(long long n, const double *__restrict__ x, long long incx, double *part /*2 per CTA*/) {
-    __shared__ double shs[RT], shq[RT];
-    double s = 0.0, q = 0.0;
+// dnrm2 without overflow or a division per element: Blue's three-accumulator sum of squares (the algorithm of LAPACK >= 3.10's
+// DNRM2): values above 2^486 are accumulated scaled by 2^-538, values below 2^-511 scaled by 2^537, the rest plainly.
+constexpr double NRM_TSML = 0x1p-511, NRM_TBIG = 0x1p486, NRM_SSML = 0x1p537, NRM_SBIG = 0x1p-538;
+__global__ void __launch_bounds__(RT) nrm2_partial_kernel(long long n, const double *__restrict__ x, long long incx, double *part /*3 per CTA*/) {
+    __shared__ double sh[32];
+    double amed = 0.0, asml = 0.0, abig = 0.0;
     for (long long i = (long long)blockIdx.x * RT + threadIdx.x; i < n; i += (long long)gridDim.x * RT) {
         const double v = fabs(x[i * incx]);
-        if (v != 0.0) {
-            if (s < v) { const double r = s / v; q = 1.0 + q * r * r; s = v; }
-            else { const double r = v / s; q += r * r; }
-        }
+        if (v > NRM_TBIG) { const double t = v * NRM_SBIG; abig += t * t; }
+        else if (v < NRM_TSML) { const double t = v * NRM_SSML; asml += t * t; }
+        else amed += v * v;
     }
-    shs[threadIdx.x] = s; shq[threadIdx.x] = q;
-    __syncthreads();
-    for (int o = RT / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            double s1 = shs[threadIdx.x], q1 = shq[threadIdx.x];
-            ssq_combine(s1, q1, shs[threadIdx.x + o], shq[threadIdx.x + o]);
-            shs[threadIdx.x] = s1; shq[threadIdx.x] = q1;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { part[2 * blockIdx.x] = shs[0]; part[2 * blockIdx.x + 1] = shq[0]; }
+    const double m = block_sum(amed, sh), sm = block_sum(asml, sh), bg = block_sum(abig, sh);
+    if (threadIdx.x == 0) { part[3 * blockIdx.x] = m; part[3 * blockIdx.x + 1] = sm; part[3 * blockIdx.x + 2] = bg; }
 }
 __global__ void nrm2_final_kernel(int cnt, const double *part, double *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < cnt; ++i) ssq_combine(s, q, part[2 * i], part[2 * i + 1]);
-    out[0] = s * sqrt(q);
+    double amed = 0.0, asml = 0.0, abig = 0.0;
+    for (int i = 0; i < cnt; ++i) { amed += part[3 * i]; asml += part[3 * i + 1]; abig += part[3 * i + 2]; }
+    double scl = 1.0, sumsq;
+    if (abig > 0.0) {  // combine abig and amed
+        if (amed > 0.0 || amed != amed) abig += (amed * NRM_SBIG) * NRM_SBIG;
+        scl = 1.0 / NRM_SBIG;
+        sumsq = abig;
+    } else if (asml > 0.0) {  // combine amed and asml
+        if (amed > 0.0 || amed != amed) {
+            const double ym = sqrt(amed), ys = sqrt(asml) / NRM_SSML;
+            const double ymin = ym < ys ? ym : ys, ymax = ym < ys ? ys : ym;
+            scl = 1.0;
+            sumsq = ymax * ymax * (1.0 + (ymin / ymax) * (ymin / ymax));
+        } else {
+            scl = 1.0 / NRM_SSML;
+            sumsq = asml;
+        }
+    } else {
+        sumsq = amed;
+    }
+    out[0] = scl * sqrt(sumsq);
 }
 
 // idamax: first index of the largest |x| (0-based, CBLAS).  key = (bits(|x|), ~index) so that max picks the lowest index.
@@ -185,20 +190,41 @@ __global__ void __launch_bounds__(256) swap_kernel(long long n, double *x, long 
 // gemv.  N: y_i = sum_j A(i,j) x_j -- thread per row, columns split over gridDim.y chunks (partials), then a finishing pass.
 //        T: y_j = sum_i A(i,j) x_i -- one CTA per column, coalesced down the column.
 // ---------------------------------------------------------------------------------------------
+template <int V>  // V = rows per thread (2: 16-byte loads, needs an aligned A with even lda)
 __global__ void __launch_bounds__(256) gemv_n_partial_kernel(int m, int n, const double *__restrict__ a, long long lda, const double *__restrict__ x,
                                                               long long incx, int chunk, double *part /* gridDim.y x m */) {
     const int j0 = blockIdx.y * chunk, j1 = min(n, j0 + chunk);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        int j = j0;
-        for (; j + 3 < j1; j += 4) {
-            acc0 += a[(long long)j * lda + i] * (x ? x[j * incx] : 1.0);
-            acc1 += a[(long long)(j + 1) * lda + i] * (x ? x[(j + 1) * incx] : 1.0);
-            acc2 += a[(long long)(j + 2) * lda + i] * (x ? x[(j + 2) * incx] : 1.0);
-            acc3 += a[(long long)(j + 3) * lda + i] * (x ? x[(j + 3) * incx] : 1.0);
+    constexpr int U = 8;  // columns in flight per thread
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * V; i < m; i += gridDim.x * blockDim.x * V) {
+        double acc[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[u][v] = 0.0;
+        for (int j = j0; j < j1; j += U) {
+            double t[U][V], xs[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = j + u < j1;
+                const double *p = a + (long long)(ok ? j + u : j) * lda + i;
+                if (V == 2) {
+                    if (i + 1 < m) { const double2 d = *reinterpret_cast<const double2 *>(p); t[u][0] = d.x; t[u][V - 1] = d.y; }
+                    else { t[u][0] = *p; t[u][V - 1] = 0.0; }
+                } else t[u][0] = *p;
+                xs[u] = ok ? (x ? x[(j + u) * incx] : 1.0) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[u][v] += t[u][v] * xs[u];
         }
-        for (; j < j1; ++j) acc0 += a[(long long)j * lda + i] * (x ? x[j * incx] : 1.0);
-        part[(long long)blockIdx.y * m + i] = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            double r = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) r += acc[u][v];
+            if (i + v < m) part[(long long)blockIdx.y * m + i + v] = r;
+        }
     }
 }
 __global__ void __launch_bounds__(256) gemv_finish_kernel(int len, int nparts, const double *part, double alpha, double beta, double *y, long long incy) {
@@ -323,7 +349,7 @@ int k_dot_device(long long n, const double *x, long long incx, const double *y, 
 int k_nrm2_device(long long n, const double *x, long long incx, double *d_out) {
     if (n < 0) return set_error(FM_ERR_ARG, "nrm2: negative length");
     const int nb = blocks_for(n, RT * 8);
-    double *part = static_cast<double *>(scratch((size_t)nb * 2 * sizeof(double)));
+    double *part = static_cast<double *>(scratch((size_t)nb * 3 * sizeof(double)));
     if (!part) return FM_ERR_NOMEM;
     nrm2_partial_kernel<<<nb, RT, 0, ctx().stream>>>(n, x, incx, part);
     FM_LAUNCH_CHECK();
@@ -363,7 +389,8 @@ int k_gemv(int trans, int m, int n, double alpha, const double *a, int lda, cons
         FM_LAUNCH_CHECK();
         return FM_OK;
     }
-    const int rb = ceil_div(m, 256);
+    const bool v2 = ((reinterpret_cast<uintptr_t>(a) & 15u) == 0) && (lda % 2 == 0);
+    const int rb = ceil_div(m, v2 ? 512 : 256);
     int splits = (ctx().sm_count * 4 + rb - 1) / rb;
     if (splits > ceil_div(n, 16)) splits = ceil_div(n, 16);
     if (splits < 1) splits = 1;
@@ -371,9 +398,10 @@ int k_gemv(int trans, int m, int n, double alpha, const double *a, int lda, cons
     splits = n > 0 ? ceil_div(n, chunk) : 1;
     double *part = static_cast<double *>(scratch((size_t)splits * m * sizeof(double)));
     if (!part) return FM_ERR_NOMEM;
-    gemv_n_partial_kernel<<<dim3(rb, splits), 256, 0, ctx().stream>>>(m, n, a, lda, x, incx, chunk, part);
+    if (v2) gemv_n_partial_kernel<2><<<dim3(rb, splits), 256, 0, ctx().stream>>>(m, n, a, lda, x, incx, chunk, part);
+    else gemv_n_partial_kernel<1><<<dim3(rb, splits), 256, 0, ctx().stream>>>(m, n, a, lda, x, incx, chunk, part);
     FM_LAUNCH_CHECK();
-    gemv_finish_kernel<<<rb, 256, 0, ctx().stream>>>(m, splits, part, alpha, beta, y, incy);
+    gemv_finish_kernel<<<ceil_div(m, 256), 256, 0, ctx().stream>>>(m, splits, part, alpha, beta, y, incy);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
