@@ -72,6 +72,8 @@ struct EpiParams {
     int round;
     unsigned zero;  // always 0; opaque to the compiler (see the stage-release token in the consumer loop)
     int pdl_wait;   // launched as a programmatic dependent of the previous kernel: wait for it before exiting
+    int ksplit;     // > 1: the k range is cut into ksplit slices, slice s of tile t writes its raw partial product to C + s * kstride
+    long long kstride;
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -142,10 +144,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int tm, tn, z;
-                decode_tile(tile, tiles_m, tiles_n, tm, tn, z);
+                const int ks = tile % ep.ksplit;
+                decode_tile(tile / ep.ksplit, tiles_m, tiles_n, tm, tn, z);
                 if (ep.active_until && ep.round >= ep.active_until[z]) continue;
                 const int m0 = tm * BM, n0 = tn * BN;
-                for (int kt = 0; kt < KT; ++kt) {
+                const int kt_per = (KT + ep.ksplit - 1) / ep.ksplit, kt_end = min(KT, (ks + 1) * kt_per);
+                for (int kt = ks * kt_per; kt < kt_end; ++kt) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t fb = full_bar(stage);
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
@@ -185,15 +189,17 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int tm, tn, z;
-        decode_tile(tile, tiles_m, tiles_n, tm, tn, z);
+        const int ks = tile % ep.ksplit;
+        decode_tile(tile / ep.ksplit, tiles_m, tiles_n, tm, tn, z);
         if (ep.active_until && ep.round >= ep.active_until[z]) continue;
+        const int kt_per = (KT + ep.ksplit - 1) / ep.ksplit, kt_begin = ks * kt_per, kt_end = min(KT, (ks + 1) * kt_per);
         double acc[MT][NT][2];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        for (int kt = 0; kt < KT; ++kt) {
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
             mbar_wait(full_bar(stage), phase);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + Cfg::A_STAGE;
@@ -237,7 +243,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---------------- epilogue: registers -> global ----------------
         const int m_base = tm * BM + wm0 + 16 * (g / GPB) + 2 * a_chunk0;
         const int n_base = tn * BN + wn0;
-        double *Cz = C + z * sc;
+        double *Cz = C + z * sc + ks * ep.kstride;
         const long long zoff = z * sc;
         if (vec_ok && (M & 1) == 0) {
             // fast path (16-byte pairs everywhere): when beta != 0 all C loads of a batch of two n-tiles are issued before
@@ -455,6 +461,23 @@ int make_map(CUtensorMap *map, const double *base, long long rows, long long col
     return FM_OK;
 }
 
+// split-K second pass: C := alpha * sum_s W_s + beta * C (+ diag on the diagonal), fixed summation order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(int m, int n, int ksplit, const double *__restrict__ w, long long ldw, long long wz,
+                                                             long long kstride, double *c, long long ldc, long long sc, double alpha, double beta,
+                                                             double diag, int has_diag) {
+    const int z = blockIdx.z;
+    for (int j = blockIdx.y; j < n; j += gridDim.y)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+            double acc = 0.0;
+            for (int s = 0; s < ksplit; ++s) acc += w[s * kstride + z * wz + j * ldw + i];
+            double v = alpha * acc;
+            double *p = c + z * sc + j * ldc + i;
+            if (beta != 0.0) v += beta * *p;
+            if (has_diag && i == j) v += diag;
+            *p = v;
+        }
+}
+
 using CfgBig = GemmCfg<128, 128, 16, 2, 4, 6>;
 // 64x128 tiles, 4 consumer warps, two CTAs per SM: twice the tiles for problems that cannot fill 148 SMs with 128x128
 // tiles, and with two independent CTAs on an SM one CTA's epilogue (C read-modify-write) overlaps the other's main loop
@@ -473,7 +496,7 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     FM_TRY(make_map(&tmA, a, m, k, lda, sa, batch, 16, Cfg::BK));
     FM_TRY(make_map(&tmB, b, k, n, ldb, sb, batch, 16, Cfg::BN));
     const int tiles_m = ceil_div(m, Cfg::BM), tiles_n = ceil_div(n, Cfg::BN);
-    const long long total = (long long)tiles_m * tiles_n * batch;
+    const long long total = (long long)tiles_m * tiles_n * batch * ep.ksplit;
     if (total > 0x7fffffffLL) return set_error(FM_ERR_ARG, "dgemm: too many tiles");
     int sms = ctx().sm_count;
     if (max_sms > 0 && max_sms < sms) sms = max_sms;
@@ -498,7 +521,8 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     return FM_OK;
 }
 
-bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer switch for A/B timing
+bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer switches for A/B timing
+bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
 
 }  // namespace
 
@@ -524,6 +548,8 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.round = epi.round;
     ep.zero = 0u;
     ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
+    ep.ksplit = 1;
+    ep.kstride = 0;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
@@ -531,6 +557,27 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     if (tma_ok) {
         const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
         const bool half = (big_tiles < 2LL * ctx().sm_count || k <= 256) && g_half_enabled;
+        // Few tiles and a long inner dimension (n <= ~700): one 64x128 tile per CTA leaves most SMs idle while each warp walks
+        // k/16 steps alone.  Cut k into slices (one CTA each, raw partial products to a workspace) and reduce in a second pass.
+        const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
+        if (half && g_splitk_enabled && half_tiles * 2 <= ctx().sm_count && k >= 256 && epi.npeers == 0 && !epi.active_until) {
+            int ksplit = (int)((2LL * ctx().sm_count) / half_tiles);
+            if (ksplit > k / 128) ksplit = k / 128;
+            if (ksplit > 16) ksplit = 16;
+            if (ksplit >= 2) {
+                const long long ldw = m + (m & 1), wz = ldw * n, kstride = wz * batch;
+                double *w = static_cast<double *>(scratch((size_t)kstride * ksplit * sizeof(double)));
+                if (!w) return FM_ERR_NOMEM;
+                EpiParams e2 = ep;
+                e2.alpha = 1.0; e2.beta = 0.0; e2.has_diag = 0; e2.diag = 0.0;
+                e2.ksplit = ksplit; e2.kstride = kstride;
+                FM_TRY((launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, w, (int)ldw, wz, batch, e2, epi.max_sms)));
+                dim3 grid(ceil_div(m, 256), n < 1024 ? n : 1024, batch);
+                splitk_reduce_kernel<<<grid, 256, 0, ctx().stream>>>(m, n, ksplit, w, ldw, wz, kstride, c, ldc, sc, ep.alpha, ep.beta, ep.diag, ep.has_diag);
+                FM_LAUNCH_CHECK();
+                return FM_OK;
+            }
+        }
         if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
         return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
     }

@@ -486,8 +486,10 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     T += blockIdx.y * st;
     B += blockIdx.y * sb;
     const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
-    const int col = blockIdx.x * TR_CB + lane;
-    const bool colok = col < ncols;
+    const int ngroups = (ncols + TR_CB - 1) / TR_CB;  // a CTA walks the column groups blockIdx.x, blockIdx.x + gridDim.x, ...
+    int grp = blockIdx.x;
+    int col = grp * TR_CB + lane;
+    bool colok = col < ncols;
     auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
     // ---- stage T (triangle only, all 36 blocks: blocks beyond nb are zero with a unit diagonal) with cp.async: every copy
     // of the CTA is in flight at once; meanwhile load B.  thread -> (pair of rows i2, column j) of a block: the 16-byte
@@ -515,10 +517,13 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     asm volatile("cp.async.commit_group;" ::: "memory");
     double y[8][2];
     double *bcol = B + (long long)col * ldb + 2 * r;
+    auto load_y = [&]() {
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
+        for (int b = 0; b < 8; ++b)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) y[b][i] = (colok && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+            for (int i = 0; i < 2; ++i) y[b][i] = (colok && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+    };
+    load_y();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
@@ -569,6 +574,7 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
         *reinterpret_cast<double2 *>(xs + lane * TR_XLD + 2 * r) = make_double2(v2[0], v2[1]);
     };
     double *XA = Xs, *XB = Xs + TR_CB * TR_XLD;
+  for (;;) {  // column groups of this CTA (T and the inverted diagonal blocks are staged once)
     // The 8 block steps are fully unrolled (block coordinates are compile-time constants), so the register-resident y[b]
     // are indexed statically and the updates of all remaining blocks of a step form independent FMA chains.
 #pragma unroll
@@ -608,7 +614,21 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
             }
         }
     }
-    // ---- transpose through shared memory (T is no longer needed) so that the stores are full 256-byte row segments ----
+    const int next = grp + gridDim.x;
+    if (next < ngroups) {  // more groups to come: T stays staged, plain stores (one 16-byte piece per block and thread)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (colok && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[b][i];
+        grp = next;
+        col = grp * TR_CB + lane;
+        colok = col < ncols;
+        bcol = B + (long long)col * ldb + 2 * r;
+        load_y();
+        continue;
+    }
+    // ---- last group: transpose through shared memory (T is no longer needed) so that the stores are full 256-byte row segments ----
     double *Bs = Ts;  // Bs[col * TR_OLD + row]
     constexpr int TR_OLD = NB + 2;
 #pragma unroll
@@ -616,8 +636,10 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     __syncthreads();
     for (int idx = tid; idx < NB * TR_CB; idx += TR_NT) {
         const int i = idx & (NB - 1), c = idx >> 7;
-        if (i < nb && blockIdx.x * TR_CB + c < ncols) B[(long long)(blockIdx.x * TR_CB + c) * ldb + i] = Bs[c * TR_OLD + i];
+        if (i < nb && grp * TR_CB + c < ncols) B[(long long)(grp * TR_CB + c) * ldb + i] = Bs[c * TR_OLD + i];
     }
+    break;
+  }
 }
 
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
@@ -756,7 +778,12 @@ int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double 
         FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
         attr = true;
     }
-    dim3 grid(ceil_div(ncols, TR_CB), batch);
+    // enough CTAs to fill the machine (2 per SM); beyond that a CTA walks several column groups with T staged once
+    const int groups = ceil_div(ncols, TR_CB);
+    int gx = ceil_div(2 * ctx().sm_count, batch);
+    if (gx > groups) gx = groups;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, batch);
     trsm_leaf_kernel<UPPER><<<grid, TR_NT, TR_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
     FM_LAUNCH_CHECK();
     return FM_OK;
