@@ -32,6 +32,21 @@ constexpr int MAPN = 2 * NB;  // (dst, src) pairs per panel: NB pivot rows + up 
 constexpr int PAY = LEAF + 2; // candidate payload: packed (position, physical row) | 1/pivot | 16 row values
 constexpr int NOROW = 0x7fffffff;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int UP = NB + 4;    // row stride of the U12 block in shared memory (k-major): 8 words mod 32, conflict-free DMMA B fragments
+constexpr int LP = LEAF + 4;  // row stride of the multiplier tile: conflict-free DMMA A fragments
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// -DFM_LU_PROF: clock64 phase counters of warp 0 / CTA 0 of the panel kernel (developer build, tools/build_prof.sh)
+#ifdef FM_LU_PROF
+__device__ long long g_prof[32];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0, t1) do { if (tid == 0 && crank == 0 && blockIdx.y == 0) g_prof[slot] += (t1) - (t0); } while (0)
+#else
+#define PROF_T(var) do {} while (0)
+#define PROF_ADD(slot, t0, t1) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t lsmem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
@@ -106,7 +121,9 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rbase = crank * ROWS + tid;  // panel-local rows rbase + k*NT, k < RPT
 
-    extern __shared__ double dyn[];  // U12 blocks, double buffered: sU[buf][c * 16 + i]
+    // dynamic smem: the U12 blocks, double buffered, U(i, c) at sU[buf][i * UP + c]; then (MINB == 1) the multiplier tile
+    // sLm[local row * LP + k] of the DMMA rank-16 update
+    extern __shared__ double dyn[];
     __shared__ __align__(8) unsigned long long s_bar[3];
     __shared__ int s_wpos[2][NWARP];                         // position of each warp's candidate (NOROW: none)
     __shared__ __align__(16) double s_wdata[2][NWARP][PAY];  // each warp's candidate: head | 1/pivot | 16 row values
@@ -125,11 +142,12 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     cluster_arrive();
     cluster_wait();
     const uint32_t tx_bytes = csize * PAY * 8;
-    // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP (csize <= 16 <= 2 * NWARP): remote addresses of
-    // s_cand[0][crank][lane] and s_bar[0] there
-    uint32_t rcand[2], rbar[2];
+    // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP, ...: remote addresses of s_cand[0][crank][lane] and
+    // s_bar[0] there
+    constexpr int NDEST = (MAXC + NWARP - 1) / NWARP;
+    uint32_t rcand[NDEST], rbar[NDEST];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NDEST; ++i) {
         const uint32_t d = warp + i * NWARP;
         rcand[i] = mapa(lsmem(&s_cand[0][crank][lane < PAY ? lane : 0]), d < csize ? d : 0);
         rbar[i] = mapa(lsmem(&s_bar[0]), d < csize ? d : 0);
@@ -145,6 +163,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
 
     for (int lc0 = 0; lc0 < pw; lc0 += W) {
         const int w = min(W, pw - lc0);
+        PROF_T(tl0);
         // ---- 1. this thread's rows of the leaf columns ----
         double v[RPT][W];
         bool live[RPT];
@@ -164,6 +183,8 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         //    candidates of pivot q while its peers already push pivot q+2: candidate buffers and mbarriers are triple
         //    buffered (q % 3).
 
+        PROF_T(tl1);
+        PROF_ADD(8, tl0, tl1);
         // thread-level candidate among this thread's rows in play: largest |x| (x = slot 0), lowest position on ties (IDAMAX).
         // key = bits(|x|); rows out of play carry position NOROW and never win.
         auto thread_best = [&](unsigned long long &bkey, int &bpos, int &kb, double &brcp) {
@@ -180,6 +201,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         // the warp's winner publishes its row; the CTA's candidate goes to every CTA of the cluster
         auto publish_and_push = [&](const int q, const bool iwin, const int bpos, const int kb, const double brcp) {
             const int buf = q % 3, wb = q & 1;
+            PROF_T(tp0);
             if (tid == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsmem(&s_bar[buf])), "r"(tx_bytes) : "memory");
             if (iwin) {  // at most one lane per warp
@@ -193,7 +215,11 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
                     }
                 s_wpos[wb][warp] = bpos;
             }
+            PROF_T(tp1);
+            PROF_ADD(4, tp0, tp1);
             __syncthreads();
+            PROF_T(tp2);
+            PROF_ADD(5, tp1, tp2);
             // every warp finds the CTA's candidate (redundantly) and pushes it to its destination CTAs
             const int p2 = lane < NWARP ? s_wpos[wb][lane] : NOROW;
             const unsigned long long k2 = p2 != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_wdata[wb][lane < NWARP ? lane : 0][2])) : 0ull;
@@ -203,9 +229,12 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             else payload = __longlong_as_double((long long)NOROW << 32);
             const uint32_t off = buf * (MAXC * PAY * 8), boff = buf * 8;
             if (lane < PAY) {
-                if (warp < (int)csize) st_async(rcand[0] + off, payload, rbar[0] + boff);
-                if (warp + NWARP < (int)csize) st_async(rcand[1] + off, payload, rbar[1] + boff);
+#pragma unroll
+                for (int i = 0; i < NDEST; ++i)
+                    if (warp + i * NWARP < (int)csize) st_async(rcand[i] + off, payload, rbar[i] + boff);
             }
+            PROF_T(tp3);
+            PROF_ADD(6, tp2, tp3);
         };
 
         {
@@ -219,7 +248,10 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             const int q = lc0 + j;  // pivot index inside the panel
             const int buf = q % 3;
             if (lane == 0) s_wpos[(q + 1) & 1][warp] = NOROW;  // reset for the next publish (last read before the previous barrier)
+            PROF_T(tc0);
             bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
+            PROF_T(tc1);
+            PROF_ADD(0, tc0, tc1);
             // global winner: same decision in every warp (lane d looks at CTA d's candidate)
             int wr;
             {
@@ -253,6 +285,8 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
                     }
                 }
             }
+            PROF_T(tc2);
+            PROF_ADD(1, tc1, tc2);
             const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
             const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
             double l[RPT], app[RPT];
@@ -270,6 +304,8 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             unsigned long long bkey; int bpos, kb; double brcp;
             thread_best(bkey, bpos, kb, brcp);
             const bool more = j + 1 < w;
+            PROF_T(tc3);
+            PROF_ADD(2, tc2, tc3);
             const bool iwin = more ? warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW) : false;
 #pragma unroll
             for (int c = 2; c < W; ++c) {
@@ -279,8 +315,12 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             }
 #pragma unroll
             for (int k = 0; k < RPT; ++k) v[k][W - 1] = app[k];
+            PROF_T(tc4);
+            PROF_ADD(3, tc3, tc4);
             if (more) publish_and_push(q + 1, iwin, bpos, kb, brcp);
         }
+        PROF_T(tl2);
+        PROF_ADD(9, tl1, tl2);
         // ---- 3. write the leaf back (slot W-w+c holds column c); the multipliers stay in registers for step 4 ----
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
@@ -294,19 +334,23 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         const int rest0 = lc0 + W, ncols = pw - rest0;
         if (ncols <= 0) break;  // last leaf (uniform)
         // ---- 4. U12 and the rank-16 update of the remaining panel columns ----
+        PROF_T(tl3);
+        PROF_ADD(10, tl2, tl3);
         if (lc0 > 0) cluster_wait();  // every CTA finished the previous leaf's update (and its reads of the old pivot rows)
         __syncthreads();              // s_L, s_pphys of this leaf are complete
         const int cur = (lc0 / W) & 1;
-        double *sU = dyn + cur * (W * NB);
+        double *sU = dyn + cur * (W * UP);
         if (pend_lc0 >= 0 && crank == 0) {  // delayed write of the previous leaf's U12 into its pivot rows
-            const double *pU = dyn + (cur ^ 1) * (W * NB);
+            const double *pU = dyn + (cur ^ 1) * (W * UP);
             const int pc = pw - (pend_lc0 + W);
             if (tid < pc) {
 #pragma unroll
-                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[tid * W + i];
+                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[i * UP + tid];
             }
         }
         pend_lc0 = lc0;
+        PROF_T(tl4);
+        PROF_ADD(11, tl3, tl4);
         if (tid < ncols) {
             double x[W];
             const double *col = a + (rest0 + tid) * lda;
@@ -317,9 +361,76 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
 #pragma unroll
                 for (int i = t + 1; i < W; ++i) x[i] -= s_L[i][t] * x[t];
 #pragma unroll
-            for (int i = 0; i < W; ++i) sU[tid * W + i] = x[i];
+            for (int i = 0; i < W; ++i) sU[i * UP + tid] = x[i];
         }
         __syncthreads();
+        PROF_T(tl5);
+        PROF_ADD(12, tl4, tl5);
+        if constexpr (MINB == 1) {
+            // Rank-16 update on the FP64 tensor pipe: C(rows of this warp, 8 columns) -= L(rows, 16) U(16, 8 columns) as 4 DMMAs
+            // per 8 x 8 tile.  With plain FMAs every U value is a broadcast LDS per two FMAs and the update is bound by the
+            // shared-memory pipe (19k cycles per leaf against 7k of FP64 work); here the operands are distributed fragments.
+            double *sLm = dyn + 2 * W * UP;
+            unsigned act[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                double *lr = sLm + (k * NT + tid) * LP;
+#pragma unroll
+                for (int c = 0; c < W; c += 2) *reinterpret_cast<double2 *>(lr + c) = make_double2(-v[k][c], -v[k][c + 1]);
+                act[k] = __ballot_sync(FULL, pos[k] >= 0);
+            }
+            __syncwarp();  // a warp consumes exactly the rows its own lanes own
+            const int g = lane >> 2, t = lane & 3;
+            double afr[RPT * 4][4];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int sk = 0; sk < 4; ++sk) afr[k * 4 + mt][sk] = sLm[(k * NT + 32 * warp + 8 * mt + g) * LP + 4 * sk + t];
+            constexpr int NTL = RPT >= 4 ? 1 : (RPT == 2 ? 2 : 4);  // n-tiles per pass: all their C loads are issued before the first DMMA (L2 latency is the bound)
+            for (int n0 = 0; n0 < ncols; n0 += 8 * NTL) {
+                double bfr[NTL][4];
+                double cf[NTL][RPT * 4][2];
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const int nb0 = n0 + 8 * nt, c0 = nb0 + 2 * t;
+#pragma unroll
+                    for (int sk = 0; sk < 4; ++sk) bfr[nt][sk] = (nb0 + g < ncols) ? sU[(4 * sk + t) * UP + nb0 + g] : 0.0;
+                    const double *col0 = a + (rest0 + c0) * lda + crank * ROWS + 32 * warp + g;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k)
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const bool ok = (act[k] >> (8 * mt + g)) & 1u;
+                            const double *p = col0 + k * NT + 8 * mt;
+                            cf[nt][k * 4 + mt][0] = (ok && c0 < ncols) ? p[0] : 0.0;
+                            cf[nt][k * 4 + mt][1] = (ok && c0 + 1 < ncols) ? p[lda] : 0.0;
+                        }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+                    for (int i = 0; i < RPT * 4; ++i)
+#pragma unroll
+                        for (int sk = 0; sk < 4; ++sk) dmma884(cf[nt][i][0], cf[nt][i][1], afr[i][sk], bfr[nt][sk]);
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const int c0 = n0 + 8 * nt + 2 * t;
+                    double *col0 = a + (rest0 + c0) * lda + crank * ROWS + 32 * warp + g;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k)
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const bool ok = (act[k] >> (8 * mt + g)) & 1u;
+                            double *p = col0 + k * NT + 8 * mt;
+                            if (ok && c0 < ncols) p[0] = cf[nt][k * 4 + mt][0];
+                            if (ok && c0 + 1 < ncols) p[lda] = cf[nt][k * 4 + mt][1];
+                        }
+                }
+            }
+            __syncwarp();
+        } else
         {
             // columns per batch; two batches are in flight (the loads of batch i+1 are issued before the FMAs of batch i):
             // the update is bound by the L2 round trip of these loads, not by the FP64 pipe
@@ -337,15 +448,12 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             auto update_store = [&](double (&x)[RPT][CU], int c0) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u) {
-                    const double2 *up = reinterpret_cast<const double2 *>(sU + (c0 + u < ncols ? c0 + u : 0) * W);
+                    const double *up = sU + (c0 + u < ncols ? c0 + u : 0);
 #pragma unroll
-                    for (int t2 = 0; t2 < W / 2; ++t2) {
-                        const double2 uu = up[t2];
+                    for (int t2 = 0; t2 < W; ++t2) {
+                        const double uu = up[t2 * UP];
 #pragma unroll
-                        for (int k = 0; k < RPT; ++k) {
-                            x[k][u] -= v[k][2 * t2] * uu.x;
-                            x[k][u] -= v[k][2 * t2 + 1] * uu.y;
-                        }
+                        for (int k = 0; k < RPT; ++k) x[k][u] -= v[k][t2] * uu;
                     }
                 }
 #pragma unroll
@@ -363,17 +471,19 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
                 update_store(xb, c0 + CU);
             }
         }
+        PROF_T(tl6);
+        PROF_ADD(13, tl5, tl6);
         cluster_arrive();
     }
     // ---- the last pending U12 and the panel's net permutation ----
     if (pend_lc0 >= 0) {
         cluster_wait();
         if (crank == 0) {
-            const double *pU = dyn + ((pend_lc0 / W) & 1) * (W * NB);
+            const double *pU = dyn + ((pend_lc0 / W) & 1) * (W * UP);
             const int pc = pw - (pend_lc0 + W);
             if (tid < pc) {
 #pragma unroll
-                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[tid * W + i];
+                for (int i = 0; i < W; ++i) a[(pend_lc0 + W + tid) * lda + s_pphys[pend_lc0 + i]] = pU[i * UP + tid];
             }
         }
     }
@@ -385,10 +495,17 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             if (q < pw) map[q] = make_int2(j0 + q, j0 + r);  // final row q comes from physical row r
         }
     }
-    if (crank == 0 && tid < NB) {
-        if (tid >= pw) map[tid] = make_int2(-1, -1);
-        // a top row that never became a pivot ends where the interchanges pushed it
-        map[NB + tid] = (pos[0] >= 0 && pos[0] != tid) ? make_int2(j0 + pos[0], j0 + tid) : make_int2(-1, -1);
+    if (crank == 0) {
+        // a top row (physical row < 128: thread r % NT, slot r / NT of CTA 0) that never became a pivot ends where the
+        // interchanges pushed it
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = tid + k * NT;
+            if (r < NB) {
+                if (r >= pw) map[r] = make_int2(-1, -1);
+                map[NB + r] = (pos[k] >= 0 && pos[k] != r) ? make_int2(j0 + pos[k], j0 + r) : make_int2(-1, -1);
+            }
+        }
     }
 }
 
@@ -711,20 +828,21 @@ struct Maps {
     int2 *panel(int j0) const { return base + (long long)(j0 / NB) * MAPN; }
 };
 
-constexpr int PANEL_DYN_SMEM = 2 * LEAF * NB * (int)sizeof(double);
+template <int NT, int RPT, int MINB>
+constexpr int panel_dyn_smem() { return (2 * LEAF * UP + (MINB == 1 ? NT * RPT * LP : 0)) * (int)sizeof(double); }
 
 template <int NT, int RPT, int MINB = 1>
 int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize) {
     static bool attr = false;
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_DYN_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_dyn_smem<NT, RPT, MINB>()));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(csize, A.batch, 1);
     cfg.blockDim = dim3(NT, 1, 1);
-    cfg.dynamicSmemBytes = PANEL_DYN_SMEM;
+    cfg.dynamicSmemBytes = panel_dyn_smem<NT, RPT, MINB>();
     cfg.stream = ctx().stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -752,8 +870,9 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
     if (A.batch >= 64 && m <= 256) return launch_panel<128, 2, 4>(A, j0, m, pw, ipiv, sp, info, maps, 1);
     if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
     if (m <= 8192) {
-        static const bool wide = getenv("FLOMAT_LU_PANEL_512") != nullptr;  // developer switch for A/B timing
-        if (wide) return launch_panel<512, 1>(A, j0, m, pw, ipiv, sp, info, maps, 16);
+        static const char *variant = getenv("FLOMAT_LU_PANEL");  // developer switch for A/B timing: 512 | 128
+        if (variant && atoi(variant) == 512) return launch_panel<512, 1>(A, j0, m, pw, ipiv, sp, info, maps, 16);
+        if (variant && atoi(variant) == 128) return launch_panel<128, 4>(A, j0, m, pw, ipiv, sp, info, maps, 16);
         return launch_panel<256, 2>(A, j0, m, pw, ipiv, sp, info, maps, 16);
     }
     if (m <= 16384) return launch_panel<256, 4>(A, j0, m, pw, ipiv, sp, info, maps, 16);
@@ -924,6 +1043,18 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));          // L y = P B
     return rtrsm<true>(n, nrhs, lu, lda, sa, b, ldb, sb, batch);            // U x = y
 }
+
+#ifdef FM_LU_PROF
+}  // namespace fm
+extern "C" int fm_lu_prof(long long *out32) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, fm::g_prof, sizeof(long long) * 32);
+    long long z[32] = {};
+    cudaMemcpyToSymbol(fm::g_prof, z, sizeof(z));
+    return 0;
+}
+namespace fm {
+#endif
 
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out) {
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "det: bad dimensions");
