@@ -514,15 +514,17 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
 // all <= 256 source rows of a column are loaded before any destination row is stored.  8 columns per CTA.
 // ---------------------------------------------------------------------------------------------
 constexpr int PERM_PC = 8;
+// `lower_cols` (the deferred pass over the L part of a finished factorization): panel p only touches the columns left of
+// it, i.e. a column group starts at the first panel behind its own columns.
 __global__ void __launch_bounds__(MAPN) permute_rows_kernel(double *a, long long lda, long long sa, int ncols, const int2 *map, long long smap,
-                                                            int npanels) {
+                                                            int npanels, int lower_cols) {
     a += blockIdx.y * sa;
     map += blockIdx.y * smap;
     const int tid = threadIdx.x;
     const int col0 = blockIdx.x * PERM_PC;
     const int nc = min(PERM_PC, ncols - col0);
     double *base = a + (long long)col0 * lda;
-    for (int p = 0; p < npanels; ++p) {
+    for (int p = lower_cols ? (col0 + nc - 1) / NB + 1 : 0; p < npanels; ++p) {
         const int2 e = map[p * MAPN + tid];
         const bool on = e.x >= 0 && e.x != e.y;
         double t[PERM_PC];
@@ -880,11 +882,12 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
 }
 
 // apply the row permutations of the panels covering pivots [p0, p1) to columns [c0, c0+ncols) of A
-int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int p1) {
+int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int p1, bool lower_cols = false) {
     if (ncols <= 0 || p1 <= p0) return FM_OK;
     const int npanels = ceil_div(p1, NB) - p0 / NB;
     dim3 grid(ceil_div(ncols, PERM_PC), A.batch);
-    permute_rows_kernel<<<grid, MAPN, 0, ctx().stream>>>(A.at(0, c0), A.lda, A.stride, ncols, maps.panel(p0), maps.item_stride, npanels);
+    permute_rows_kernel<<<grid, MAPN, 0, ctx().stream>>>(A.at(0, c0), A.lda, A.stride, ncols, maps.panel(p0), maps.item_stride, npanels,
+                                                         lower_cols ? 1 : 0);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -981,7 +984,9 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
     FM_TRY(panel_factor(A, 0, m, mn < NB ? mn : NB, ipiv, sp, info, maps, &csize));
     for (int j0 = 0; j0 < mn; j0 += NB) {
         const int jb = std::min(NB, mn - j0), j1 = j0 + jb;
-        FM_TRY(permute_rows(A, 0, n, maps, j0, j1));  // panel j0 is complete: its interchanges go to every column
+        // panel j0 is complete: its interchanges go to its own and to the trailing columns now; the columns to its left (L)
+        // are off the critical chain and get all their interchanges in one pass at the end
+        FM_TRY(permute_rows(A, j0, n - j0, maps, j0, j1));
         const int nr = n - j1;
         if (nr <= 0) break;
         FM_TRY(trsm_leaf<false>(jb, nr, A.at(j0, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.batch));
@@ -999,7 +1004,7 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
                               A.stride, A.batch, dep ? ctx().sm_count - csize : 0, dep));
         }
     }
-    return FM_OK;
+    return permute_rows(A, 0, mn, maps, 0, mn, true);  // L part: column c receives the interchanges of every panel right of it
 }
 
 }  // namespace
