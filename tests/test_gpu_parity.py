@@ -179,6 +179,25 @@ def test_dgemm_exact_integers_large(fm):
     assert np.array_equal(fm.times(up(fm, a), up(fm, b)).to_numpy(), a @ b)
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 256, 256), (384, 200, 1536), (512, 512, 512), (130, 70, 2000)])
+def test_dgemm_split_k_alpha_beta_diag(fm, ref, m, n, k):
+    """Few tiles and a long inner dimension take the split-K path (partials + fixed-order reduce): same result contract,
+    including alpha/beta and the fused `+ c I` of mpoly (expm.rkt:176), and exact on integer data."""
+    lib = fm.load()
+    a, b, c = rnd(60, m, k), rnd(61, k, n), rnd(62, m, n)
+    C = up(fm, c)
+    fm.flomat_times(up(fm, a), up(fm, b), C, alpha=-0.75, beta=0.5)
+    want = ref.gemm(a, b, c.copy(order="F"), alpha=-0.75, beta=0.5)
+    assert normwise_rel_err(C.to_numpy(), want) <= tol(max(m, n, k))
+    A, B, D = up(fm, a), up(fm, b), fm.Flomat.alloc(m, n)
+    fm._lib.check(lib.fm_dgemm_diag(m, n, k, 1.0, A.a, A.lda, B.a, B.lda, 0.0, D.a, D.lda, 2.5), "fm_dgemm_diag")
+    assert normwise_rel_err(D.to_numpy(), a @ b + 2.5 * np.eye(m, n)) <= tol(max(m, n, k))
+    rng = np.random.default_rng(63)
+    ai = np.asfortranarray(rng.integers(-8, 9, (m, k)).astype(float))
+    bi = np.asfortranarray(rng.integers(-8, 9, (k, n)).astype(float))
+    assert np.array_equal(fm.times(up(fm, ai), up(fm, bi)).to_numpy(), ai @ bi)
+
+
 def test_dgemm_linearity_at_full_size(fm):
     """BASELINE config size n=4096..8192: (A1+A2)B == A1 B + A2 B within tolerance; no CPU product needed."""
     n = 4096
@@ -290,6 +309,20 @@ def test_solve_roundtrip_at_config_size(fm):
     X = fm.mldivide(A, B)
     R = fm.minus(fm.times(A, X), B)
     assert fm.norm(R, 1) / (fm.norm(A, 1) * fm.norm(X, 1)) <= tol(n)
+
+
+@pytest.mark.parametrize("n,nrhs", [(8192, 64), (9100, 8)])
+def test_solve_roundtrip_full_size_on_device(fm, n, nrhs):
+    """BASELINE config 3 at its full size (n = 8192, 64 right-hand sides) and one size past 8192 rows (the 1024-rows-per-CTA
+    panel configuration): inputs from LAPACK's generator on the device, backward error ||AX - B||_1 / (||A||_1 ||X||_1)."""
+    iseed = np.array([n % 4096, 7, 11, 13], dtype=np.int32)
+    A, B = fm.randn(n, n, iseed=iseed), fm.randn(n, nrhs, iseed=iseed)
+    X = fm.mldivide(A, B)
+    R = fm.minus(fm.times(A, X), B)
+    assert fm.norm(R, 1) / (fm.norm(A, 1) * fm.norm(X, 1)) <= tol(n)
+    P, L, U = fm.flomat_plu(A)  # A = P L U at full size: ||P L U - A||_1 / ||A||_1
+    R2 = fm.minus(fm.times(P, fm.times(L, U)), A)
+    assert fm.norm(R2, 1) / fm.norm(A, 1) <= tol(n)
 
 
 # ---------------------------------------------------------------- expm
