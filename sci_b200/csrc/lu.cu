@@ -592,13 +592,16 @@ __global__ void __launch_bounds__(32) ipiv_to_maps_kernel(int n, const int32_t *
 // division-based substitution), so every block step is the same 2x16 register mat-vec; the 16 solved values of a block
 // step are exchanged between the 8 warps through a small padded smem tile (2 __syncthreads per block step).
 // ---------------------------------------------------------------------------------------------
-constexpr int TR_CB = 32;            // columns per CTA
 constexpr int TR_NT = 256;           // threads per CTA
 constexpr int TR_XLD = 18;           // padded column stride of the exchange tile (conflict-free LDS.128)
-constexpr int TR_SMEM = (36 * 256 + 2 * TR_CB * TR_XLD) * (int)sizeof(double);
-template <bool UPPER>
+template <int CPT>
+constexpr int tr_smem() { return (36 * 256 + 2 * 32 * CPT * TR_XLD) * (int)sizeof(double); }
+// CPT = columns per thread (a CTA covers 32 * CPT columns).  With CPT = 2 every broadcast T load feeds two columns: half the
+// shared-memory traffic per column, used when there are enough columns to fill the machine with 64-column CTAs.
+template <bool UPPER, int CPT>
 __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
                                                           long long ldb, long long sb) {
+    constexpr int TR_CB = 32 * CPT;
     extern __shared__ double sm[];
     double *Ts = sm;             // block (bi, bk), warp r, column j, row i:  Ts[blk*256 + r*32 + j*2 + i] = T(16bi + 2r + i, 16bk + j)
     double *Xs = sm + 36 * 256;  // two exchange tiles: Xs[buf][col * TR_XLD + row]
@@ -607,8 +610,6 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;
     const int ngroups = (ncols + TR_CB - 1) / TR_CB;  // a CTA walks the column groups blockIdx.x, blockIdx.x + gridDim.x, ...
     int grp = blockIdx.x;
-    int col = grp * TR_CB + lane;
-    bool colok = col < ncols;
     auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
     // ---- stage T (triangle only, all 36 blocks: blocks beyond nb are zero with a unit diagonal) with cp.async: every copy
     // of the CTA is in flight at once; meanwhile load B.  thread -> (pair of rows i2, column j) of a block: the 16-byte
@@ -634,22 +635,26 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    double y[8][2];
-    double *bcol = B + (long long)col * ldb + 2 * r;
+    double y[CPT][8][2];
+    auto column = [&](int cp) { return grp * TR_CB + 32 * cp + lane; };
     auto load_y = [&]() {
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
+        for (int cp = 0; cp < CPT; ++cp) {
+            const int col = column(cp);
+            const double *bcol = B + (long long)col * ldb + 2 * r;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) y[b][i] = (colok && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) y[cp][b][i] = (col < ncols && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+        }
     };
     load_y();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
     if (r < 4) {
-        const int d = r * 2 + (lane >> 4);  // 4 warps x 2 half-warps = the (up to) 8 diagonal blocks
-        const bool act = true;
-        double *tb = Ts + blk_index(act ? d : 0, act ? d : 0) * 256;
+        const int d = r * 2 + (lane >> 4);  // 4 warps x 2 half-warps = the 8 diagonal blocks
+        double *tb = Ts + blk_index(d, d) * 256;
         auto el = [&](int i, int k) -> double & { return tb[(i >> 1) * 32 + k * 2 + (i & 1)]; };
         const int j = lane & 15;
         double z[16];
@@ -674,23 +679,25 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
             }
         }
         __syncwarp();
-        if (act) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) el(i, j) = z[i];
-        }
+        for (int i = 0; i < 16; ++i) el(i, j) = z[i];
     }
     __syncthreads();
     // ---- block steps ----
-    auto read16 = [&](const double *xs, double (&x)[16]) {
+    auto read16 = [&](const double *xs, double (&x)[CPT][16]) {
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            const double2 t = *reinterpret_cast<const double2 *>(xs + lane * TR_XLD + 2 * h);
-            x[2 * h] = t.x;
-            x[2 * h + 1] = t.y;
-        }
+        for (int cp = 0; cp < CPT; ++cp)
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const double2 t = *reinterpret_cast<const double2 *>(xs + (32 * cp + lane) * TR_XLD + 2 * h);
+                x[cp][2 * h] = t.x;
+                x[cp][2 * h + 1] = t.y;
+            }
     };
-    auto write2 = [&](double *xs, const double (&v2)[2]) {
-        *reinterpret_cast<double2 *>(xs + lane * TR_XLD + 2 * r) = make_double2(v2[0], v2[1]);
+    auto write2 = [&](double *xs, int bk) {
+#pragma unroll
+        for (int cp = 0; cp < CPT; ++cp)
+            *reinterpret_cast<double2 *>(xs + (32 * cp + lane) * TR_XLD + 2 * r) = make_double2(y[cp][bk][0], y[cp][bk][1]);
     };
     double *XA = Xs, *XB = Xs + TR_CB * TR_XLD;
   for (;;) {  // column groups of this CTA (T and the inverted diagonal blocks are staged once)
@@ -699,25 +706,33 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const int bk = UPPER ? 7 - s : s;
-        double x[16];
-        write2(XA, y[bk]);
+        double x[CPT][16];
+        write2(XA, bk);
         __syncthreads();
         read16(XA, x);
         {   // x_bk = inv(T_kk) b_k, this warp's 2 rows; four partial sums shorten the dependent chain
             const double2 *tr = reinterpret_cast<const double2 *>(Ts + blk_index(bk, bk) * 256 + r * 32);
-            double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0;
+            double z0[CPT], z1[CPT], w0[CPT], w1[CPT];
+#pragma unroll
+            for (int cp = 0; cp < CPT; ++cp) z0[cp] = z1[cp] = w0[cp] = w1[cp] = 0.0;
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 const double2 ta = tr[j], tb2 = tr[j + 1];
-                z0 += ta.x * x[j];
-                z1 += ta.y * x[j];
-                w0 += tb2.x * x[j + 1];
-                w1 += tb2.y * x[j + 1];
+#pragma unroll
+                for (int cp = 0; cp < CPT; ++cp) {
+                    z0[cp] += ta.x * x[cp][j];
+                    z1[cp] += ta.y * x[cp][j];
+                    w0[cp] += tb2.x * x[cp][j + 1];
+                    w1[cp] += tb2.y * x[cp][j + 1];
+                }
             }
-            y[bk][0] = z0 + w0;
-            y[bk][1] = z1 + w1;
+#pragma unroll
+            for (int cp = 0; cp < CPT; ++cp) {
+                y[cp][bk][0] = z0[cp] + w0[cp];
+                y[cp][bk][1] = z1[cp] + w1[cp];
+            }
         }
-        write2(XB, y[bk]);
+        write2(XB, bk);
         __syncthreads();
         if (s == 7) break;
         read16(XB, x);
@@ -727,8 +742,11 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
             for (int b = 0; b < 8; ++b) {
                 if (UPPER ? (b < bk) : (b > bk)) {
                     const double2 t = reinterpret_cast<const double2 *>(Ts + blk_index(b, bk) * 256 + r * 32)[j];
-                    y[b][0] -= t.x * x[j];
-                    y[b][1] -= t.y * x[j];
+#pragma unroll
+                    for (int cp = 0; cp < CPT; ++cp) {
+                        y[cp][b][0] -= t.x * x[cp][j];
+                        y[cp][b][1] -= t.y * x[cp][j];
+                    }
                 }
             }
         }
@@ -736,14 +754,16 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     const int next = grp + gridDim.x;
     if (next < ngroups) {  // more groups to come: T stays staged, plain stores (one 16-byte piece per block and thread)
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
+        for (int cp = 0; cp < CPT; ++cp) {
+            const int col = column(cp);
+            double *bcol = B + (long long)col * ldb + 2 * r;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-                if (colok && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[b][i];
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (col < ncols && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[cp][b][i];
+        }
         grp = next;
-        col = grp * TR_CB + lane;
-        colok = col < ncols;
-        bcol = B + (long long)col * ldb + 2 * r;
         load_y();
         continue;
     }
@@ -751,7 +771,10 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
     double *Bs = Ts;  // Bs[col * TR_OLD + row]
     constexpr int TR_OLD = NB + 2;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) *reinterpret_cast<double2 *>(Bs + lane * TR_OLD + 16 * b + 2 * r) = make_double2(y[b][0], y[b][1]);
+    for (int cp = 0; cp < CPT; ++cp)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            *reinterpret_cast<double2 *>(Bs + (32 * cp + lane) * TR_OLD + 16 * b + 2 * r) = make_double2(y[cp][b][0], y[cp][b][1]);
     __syncthreads();
     for (int idx = tid; idx < NB * TR_CB; idx += TR_NT) {
         const int i = idx & (NB - 1), c = idx >> 7;
@@ -892,23 +915,31 @@ int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int 
     return FM_OK;
 }
 
-template <bool UPPER>
-int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
-    if (nb <= 0 || ncols <= 0) return FM_OK;
+template <bool UPPER, int CPT>
+int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<CPT>()));
         attr = true;
     }
     // enough CTAs to fill the machine (2 per SM); beyond that a CTA walks several column groups with T staged once
-    const int groups = ceil_div(ncols, TR_CB);
+    const int groups = ceil_div(ncols, 32 * CPT);
     int gx = ceil_div(2 * ctx().sm_count, batch);
     if (gx > groups) gx = groups;
     if (gx < 1) gx = 1;
     dim3 grid(gx, batch);
-    trsm_leaf_kernel<UPPER><<<grid, TR_NT, TR_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
+    trsm_leaf_kernel<UPPER, CPT><<<grid, TR_NT, tr_smem<CPT>(), ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
     FM_LAUNCH_CHECK();
     return FM_OK;
+}
+
+template <bool UPPER>
+int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+    if (nb <= 0 || ncols <= 0) return FM_OK;
+    // two columns per thread once 64-column CTAs already fill the machine (half the shared-memory traffic per column)
+    const long long groups64 = (long long)ceil_div(ncols, 64) * batch;
+    if (groups64 >= ctx().sm_count / 2) return trsm_leaf_launch<UPPER, 2>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
+    return trsm_leaf_launch<UPPER, 1>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
 }
 
 int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
