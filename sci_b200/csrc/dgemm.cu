@@ -557,10 +557,10 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     if (tma_ok) {
         const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
         const bool half = (big_tiles < 2LL * ctx().sm_count || k <= 256) && g_half_enabled;
-        // Few tiles and a long inner dimension (n <= ~700): one 64x128 tile per CTA leaves most SMs idle while each warp walks
+        // Few tiles and a long inner dimension (n <= ~1100): one 64x128 tile per CTA leaves most SMs idle while each warp walks
         // k/16 steps alone.  Cut k into slices (one CTA each, raw partial products to a workspace) and reduce in a second pass.
         const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
-        if (half && g_splitk_enabled && half_tiles * 2 <= ctx().sm_count && k >= 256 && epi.npeers == 0 && !epi.active_until) {
+        if (half && g_splitk_enabled && half_tiles <= ctx().sm_count && k >= 256 && epi.npeers == 0 && !epi.active_until) {
             int ksplit = (int)((2LL * ctx().sm_count) / half_tiles);
             if (ksplit > k / 128) ksplit = k / 128;
             if (ksplit > 16) ksplit = 16;
