@@ -86,6 +86,8 @@ double cblas_dnrm2(int n, const double *X, int incX);
 int cblas_idamax(int n, const double *X, int incX);
 /* flomat.rkt:1074-1079, call sites :1088 (rows, inc = lda) and :1103 (columns) */
 void cblas_dswap(int n, double *X, int incX, double *Y, int incY);
+/* flomat.rkt:1794-1809, call site :1818 (flomat-cholesky!); the triangle that is not selected by uplo is left untouched */
+void dpotrf_(const char *uplo, const int *n, double *a, const int *lda, int *info);
 /* flomat.rkt:2798-2803, call sites :2818-2850 (`rand` idist 1, `randn` idist 3); iseed: 4 ints in 0..4095, updated */
 void dlarnv_(const int *idist, int32_t *iseed, const int *n, double *x);
 
@@ -175,6 +177,8 @@ int fm_swap(int n, double *x, int incx, double *y, int incy);                   
 /* out[j] = sum_i A(i,j) / out[i] = sum_j A(i,j): flomat-column-sums :2094, flomat-row-sums :2101 (n or m ddots there) */
 int fm_colsums(int m, int n, const double *a, int lda, double *out);
 int fm_rowsums(int m, int n, const double *a, int lda, double *out);
+/* Cholesky in place (device operands, info = device int32): uplo 'L' A = L L^T / 'U' A = U^T U; flomat-cholesky! :1815 */
+int fm_potrf(char uplo, int n, double *a, int lda, int32_t *info);
 /* dlarnv on the device: x[0..n) from LAPACK's 48-bit multiplicative generator (bit-identical uniforms; normals by the same
  * Box-Muller pairing, within a few ulp of libm); iseed (host, 4 ints in 0..4095) is advanced exactly like DLARNV does */
 int fm_larnv(int idist, int32_t *iseed, long long n, double *x);

@@ -502,6 +502,24 @@ class Flomat:
                 out[idx] = f(float(a[idx]), float(bb[idx]))
         return out
 
+    @staticmethod
+    def cholesky(a, upper=False):
+        """flomat-cholesky (flomat.rkt:1821-1826) -> dpotrf_: unblocked DPOTF2 restated (lower form; upper = its transpose),
+        then the requested triangle is extracted.  Returns (factor, info)."""
+        n = a.shape[0]
+        l = np.tril(np.array(a.T if upper else a, dtype=np.float64))
+        info = 0
+        for j in range(n):
+            d = l[j, j]
+            if not d > 0.0:
+                info = j + 1
+                break
+            l[j, j] = math.sqrt(d)
+            l[j + 1:, j] /= l[j, j]
+            for c in range(j + 1, n):
+                l[c:, c] -= l[c:, j] * l[c, j]
+        return (fortran(l.T.copy()) if upper else fortran(l)), info
+
     # -- dlarnv (flomat.rkt:2798-2852): LAPACK's DLARUV multiplicative congruential generator restated in exact integers ----
     LCG_A = 33952834046453  # dlaruv.f: MM(1,:) = (494, 322, 2508, 2549) in base 4096; row i of the table is a^i mod 2^48
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "cblas_idamax": (c_int, [c_int, _DP, c_int]),
     "cblas_dswap": (None, [c_int, _DP, c_int, _DP, c_int]),
     "dlarnv_": (None, [POINTER(c_int), _IP, POINTER(c_int), _DP]),
+    "dpotrf_": (None, [c_char_p, POINTER(c_int), _DP, POINTER(c_int), POINTER(c_int)]),
     # tier 2
     "fm_init": (c_int, [c_int]),
     "fm_device_count": (c_int, []),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "fm_colsums": (c_int, [c_int, c_int, _DP, c_int, _DP]),
     "fm_rowsums": (c_int, [c_int, c_int, _DP, c_int, _DP]),
     "fm_larnv": (c_int, [c_int, _IP, c_longlong, _DP]),
+    "fm_potrf": (c_int, [c_char, c_int, _DP, c_int, _IP]),
     "fm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
     "fm_dgemm_diag": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_double]),
     "fm_dgemm_batched": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_double, _DP, c_int,

@@ -416,6 +416,11 @@ int fm_rowsums(int m, int n, const double *a, int lda, double *out) {  // out[i]
     FM_TRY(ensure_init());
     return k_gemv(0, m, n, 1.0, a, lda, nullptr, 0, 0.0, out, 1);
 }
+int fm_potrf(char uplo, int n, double *a, int lda, int32_t *info) {
+    FM_TRY(ensure_init());
+    if (!info) return set_error(FM_ERR_ARG, "fm_potrf: info is NULL");
+    return k_potrf(uplo, n, a, lda, info);
+}
 int fm_larnv(int idist, int32_t *iseed, long long n, double *x) {
     FM_TRY(ensure_init());
     if (!iseed) return set_error(FM_ERR_ARG, "fm_larnv: iseed is NULL");
@@ -659,6 +664,28 @@ void cblas_dswap(int n, double *X, int incX, double *Y, int incY) {
         if (rc == FM_OK) rc = y.out();
     }
     report("cblas_dswap", rc);
+}
+void dpotrf_(const char *uplo, const int *n, double *a, const int *lda, int *info) {
+    const char u = uplo ? uplo[0] : 'L';
+    *info = 0;
+    if (u != 'U' && u != 'u' && u != 'L' && u != 'l') { *info = -1; return; }
+    if (*n < 0) { *info = -2; return; }
+    if (*lda < (*n > 1 ? *n : 1)) { *info = -4; return; }
+    if (*n == 0) return;
+    int rc = ensure_init();
+    if (rc == FM_OK) {
+        Staged A;
+        rc = A.in(a, *lda, *n, *n, true);
+        int32_t *d_info = rc == FM_OK ? static_cast<int32_t *>(fm_alloc_bytes(16)) : nullptr;
+        if (rc == FM_OK && !d_info) rc = FM_ERR_NOMEM;
+        if (rc == FM_OK) rc = k_potrf(u, *n, A.dev, A.ld, d_info);
+        if (rc == FM_OK) rc = A.out();
+        int32_t hinfo = 0;
+        if (rc == FM_OK) rc = fm_download_i32(&hinfo, d_info, 1);
+        if (rc == FM_OK) *info = hinfo;
+        if (d_info) fm_free(d_info);
+    }
+    report("dpotrf_", rc);
 }
 void dlarnv_(const int *idist, int32_t *iseed, const int *n, double *x) {
     if (*n <= 0) return;

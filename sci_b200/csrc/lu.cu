@@ -598,10 +598,14 @@ template <int CPT>
 constexpr int tr_smem() { return (36 * 256 + 2 * 32 * CPT * TR_XLD) * (int)sizeof(double); }
 // CPT = columns per thread (a CTA covers 32 * CPT columns).  With CPT = 2 every broadcast T load feeds two columns: half the
 // shared-memory traffic per column, used when there are enough columns to fill the machine with 64-column CTAs.
-template <bool UPPER, int CPT>
+// RSIDE (with UPPER = false): the right-side solve X T^T = B with T lower and NON-unit -- every ROW of B is a right-hand side
+// (B is `ncols` rows x nb columns; the step L21 = A21 L11^-T of the blocked Cholesky).  Same kernel with the roles of the
+// two indices of B swapped; those loads and stores are coalesced as they are.
+template <bool UPPER, int CPT, bool RSIDE = false>
 __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
                                                           long long ldb, long long sb) {
     constexpr int TR_CB = 32 * CPT;
+    constexpr bool UNIT = !UPPER && !RSIDE;
     extern __shared__ double sm[];
     double *Ts = sm;             // block (bi, bk), warp r, column j, row i:  Ts[blk*256 + r*32 + j*2 + i] = T(16bi + 2r + i, 16bk + j)
     double *Xs = sm + 36 * 256;  // two exchange tiles: Xs[buf][col * TR_XLD + row]
@@ -641,11 +645,12 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
 #pragma unroll
         for (int cp = 0; cp < CPT; ++cp) {
             const int col = column(cp);
-            const double *bcol = B + (long long)col * ldb + 2 * r;
+            const double *bcol = RSIDE ? B + col + (long long)(2 * r) * ldb : B + (long long)col * ldb + 2 * r;
+            const long long rs = RSIDE ? ldb : 1;  // stride between consecutive unknowns of one right-hand side
 #pragma unroll
             for (int b = 0; b < 8; ++b)
 #pragma unroll
-                for (int i = 0; i < 2; ++i) y[cp][b][i] = (col < ncols && 16 * b + 2 * r + i < nb) ? bcol[16 * b + i] : 0.0;
+                for (int i = 0; i < 2; ++i) y[cp][b][i] = (col < ncols && 16 * b + 2 * r + i < nb) ? bcol[(16 * b + i) * rs] : 0.0;
         }
     };
     load_y();
@@ -665,7 +670,8 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
                     if (k < i) acc -= el(i, k) * ((k >= j) ? z[k] : 0.0);
-                z[i] = (i >= j) ? acc : 0.0;
+                const double dg = (UNIT || 16 * d + i >= nb) ? 1.0 : el(i, i);
+                z[i] = (i >= j) ? (UNIT ? acc : acc / dg) : 0.0;
             }
         } else {
 #pragma unroll
@@ -756,16 +762,30 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
 #pragma unroll
         for (int cp = 0; cp < CPT; ++cp) {
             const int col = column(cp);
-            double *bcol = B + (long long)col * ldb + 2 * r;
+            double *bcol = RSIDE ? B + col + (long long)(2 * r) * ldb : B + (long long)col * ldb + 2 * r;
+            const long long rs = RSIDE ? ldb : 1;
 #pragma unroll
             for (int b = 0; b < 8; ++b)
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                    if (col < ncols && 16 * b + 2 * r + i < nb) bcol[16 * b + i] = y[cp][b][i];
+                    if (col < ncols && 16 * b + 2 * r + i < nb) bcol[(16 * b + i) * rs] = y[cp][b][i];
         }
         grp = next;
         load_y();
         continue;
+    }
+    if (RSIDE) {  // rows of B: the plain stores are already coalesced across the lanes
+#pragma unroll
+        for (int cp = 0; cp < CPT; ++cp) {
+            const int col = column(cp);
+            double *bcol = B + col + (long long)(2 * r) * ldb;
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (col < ncols && 16 * b + 2 * r + i < nb) bcol[(long long)(16 * b + i) * ldb] = y[cp][b][i];
+        }
+        break;
     }
     // ---- last group: transpose through shared memory (T is no longer needed) so that the stores are full 256-byte row segments ----
     double *Bs = Ts;  // Bs[col * TR_OLD + row]
@@ -915,11 +935,11 @@ int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int 
     return FM_OK;
 }
 
-template <bool UPPER, int CPT>
+template <bool UPPER, int CPT, bool RSIDE = false>
 int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<CPT>()));
+        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER, CPT, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<CPT>()));
         attr = true;
     }
     // enough CTAs to fill the machine (2 per SM); beyond that a CTA walks several column groups with T staged once
@@ -928,7 +948,7 @@ int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, 
     if (gx > groups) gx = groups;
     if (gx < 1) gx = 1;
     dim3 grid(gx, batch);
-    trsm_leaf_kernel<UPPER, CPT><<<grid, TR_NT, tr_smem<CPT>(), ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
+    trsm_leaf_kernel<UPPER, CPT, RSIDE><<<grid, TR_NT, tr_smem<CPT>(), ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -1038,6 +1058,78 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
     return permute_rows(A, 0, mn, maps, 0, mn, true);  // L part: column c receives the interchanges of every panel right of it
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cholesky (dpotrf_, flomat.rkt:1794; flomat-cholesky(!) :1815-1826), lower form A = L L^T, blocked right-looking on a
+// scratch copy W of A:   potf2(W_kk) -> W21 := W21 L11^-T (leaf TRSM, right side) -> W22 -= W21 W21^T (the DMMA GEMM on the
+// whole trailing square with W21^T formed by the transpose kernel: 2x the flops of a SYRK, no new kernel) -> ... ; finally only
+// the requested triangle is written back, so the other triangle of A stays untouched as LAPACK promises.
+// ---------------------------------------------------------------------------------------------
+// unblocked Cholesky of one nb x nb block (nb <= 128) in shared memory; info = global 1-based index of the first non-positive pivot
+__global__ void __launch_bounds__(256) potf2_kernel(int nb, double *a, long long lda, int32_t *info, int j0) {
+    extern __shared__ double S[];  // S[j * (NB + 1) + i]
+    constexpr int LD = NB + 1;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nb * nb; idx += 256) {
+        const int i = idx % nb, j = idx / nb;
+        S[j * LD + i] = a[j * lda + i];
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        const double d = S[j * LD + j];
+        if (!(d > 0.0)) {  // not positive definite (or NaN): DPOTF2 stops here
+            if (tid == 0 && *info == 0) *info = j0 + j + 1;
+            break;
+        }
+        const double rd = sqrt(d);
+        __syncthreads();
+        for (int i = j + tid; i < nb; i += 256) S[j * LD + i] = (i == j) ? rd : S[j * LD + i] / rd;
+        __syncthreads();
+        // trailing update of the lower triangle: S(i, c) -= S(i, j) S(c, j) for j < c <= i
+        const int rem = nb - j - 1;
+        for (int idx = tid; idx < rem * rem; idx += 256) {
+            const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
+            if (i >= c) S[c * LD + i] -= S[j * LD + i] * S[j * LD + c];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * nb; idx += 256) {
+        const int i = idx % nb, j = idx / nb;
+        if (i >= j) a[j * lda + i] = S[j * LD + i];
+    }
+}
+// dst triangle := src triangle (lower: i >= j); with `flip` dst(j, i) := src(i, j) (the upper factor U = L^T)
+__global__ void __launch_bounds__(256) tri_copy_kernel(int n, const double *__restrict__ src, long long lds, double *dst, long long ldd, int flip) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nt = (n + 31) / 32;
+    for (long long t = blockIdx.x; t < (long long)nt * nt; t += gridDim.x) {
+        const int ti = (int)(t % nt), tj = (int)(t / nt);
+        if (ti < tj) continue;  // tiles strictly above the diagonal hold nothing of the lower triangle (uniform per CTA)
+        const int i0 = ti * 32, j0 = tj * 32;
+        if (!flip) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = i0 + tx, j = j0 + ty + 8 * r;
+                if (i < n && j < n && i >= j) dst[j * ldd + i] = src[j * lds + i];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = i0 + tx, j = j0 + ty + 8 * r;
+                tile[ty + 8 * r][tx] = (i < n && j < n && i >= j) ? src[j * lds + i] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = j0 + tx, i = i0 + ty + 8 * r;  // dst(j, i) = src(i, j): row j, column i, j <= i
+                if (i < n && j < n && i >= j) dst[i * ldd + j] = tile[tx][ty + 8 * r];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
 
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch) {
@@ -1078,6 +1170,49 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     FM_TRY(permute_rows(B, 0, nrhs, maps, 0, n));                          // P B   (DLASWP)
     FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));          // L y = P B
     return rtrsm<true>(n, nrhs, lu, lda, sa, b, ldb, sb, batch);            // U x = y
+}
+
+// dpotrf: uplo 'L' (A = L L^T, lower triangle overwritten) or 'U' (A = U^T U, upper triangle overwritten)
+int k_potrf(char uplo, int n, double *a, int lda, int32_t *info) {
+    if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "potrf: bad dimensions");
+    const bool upper = (uplo == 'U' || uplo == 'u');
+    if (!upper && uplo != 'L' && uplo != 'l') return set_error(FM_ERR_ARG, "potrf: uplo must be 'U' or 'L'");
+    zero_info_kernel<<<1, 32, 0, ctx().stream>>>(info, 1);
+    FM_LAUNCH_CHECK();
+    if (n == 0) return FM_OK;
+    const int ldw = n + (n & 1);
+    double *w = static_cast<double *>(fm_alloc_bytes(((size_t)ldw * n + (size_t)ldw * NB) * sizeof(double)));
+    if (!w) return FM_ERR_NOMEM;
+    double *wt = w + (size_t)ldw * n;  // W21^T of the current step: NB x rows, leading dimension NB
+    int rc = upper ? k_transpose(n, n, a, lda, w, ldw) : k_copy2d(w, ldw, a, lda, n, n);  // the lower triangle of W holds the data
+    static bool attr = false;
+    if (rc == FM_OK && !attr) {
+        cudaError_t e = cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB * (NB + 1) * (int)sizeof(double));
+        if (e != cudaSuccess) rc = set_error(FM_ERR_CUDA, "potrf: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    for (int j0 = 0; rc == FM_OK && j0 < n; j0 += NB) {
+        const int jb = std::min(NB, n - j0), j1 = j0 + jb, rest = n - j1;
+        double *wkk = w + (size_t)j0 * ldw + j0;
+        potf2_kernel<<<1, 256, NB * (NB + 1) * sizeof(double), ctx().stream>>>(jb, wkk, ldw, info, j0);
+        rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "potf2 launch failed");
+        count_launch();
+        if (rest <= 0 || rc != FM_OK) break;
+        double *w21 = wkk + jb;  // rest x jb
+        if (rest >= 64 * (ctx().sm_count / 2)) rc = trsm_leaf_launch<false, 2, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        else rc = trsm_leaf_launch<false, 1, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        if (rc == FM_OK) rc = k_transpose(rest, jb, w21, ldw, wt, NB);
+        if (rc == FM_OK) rc = gemm_minus(rest, rest, jb, w21, ldw, 0, wt, NB, 0, w + (size_t)j1 * ldw + j1, ldw, 0, 1);
+    }
+    if (rc == FM_OK) {
+        const long long tiles = (long long)ceil_div(n, 32) * ceil_div(n, 32);
+        const long long cap = (long long)ctx().sm_count * 16;
+        tri_copy_kernel<<<(int)(tiles < cap ? tiles : cap), 256, 0, ctx().stream>>>(n, w, ldw, a, lda, upper ? 1 : 0);
+        rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "potrf: triangle copy launch failed");
+        count_launch();
+    }
+    fm_free(w);
+    return rc;
 }
 
 #ifdef FM_LU_PROF

@@ -561,6 +561,22 @@ def rowsums(a: Flomat) -> Flomat:
     return out
 
 
+def flomat_cholesky_bang(a: Flomat, upper: bool = False) -> int:
+    """flomat-cholesky! (flomat.rkt:1815): dpotrf in place, returns LAPACK's info (0, or the order of the first leading minor
+    that is not positive definite).  Only the selected triangle of A is overwritten."""
+    _check_square(a, "flomat-cholesky!")
+    info = Pivots(0)
+    check(_L().fm_potrf(b"U" if upper else b"L", a.m, a.a, a.lda, info.info_ptr), "fm_potrf")
+    return info.info()
+
+
+def flomat_cholesky(a: Flomat, upper: bool = False) -> Flomat:
+    """flomat-cholesky (flomat.rkt:1821): copy, factor, extract the requested triangle."""
+    b = copy_flomat(a)
+    flomat_cholesky_bang(b, upper)
+    return flomat_extract_upper(b) if upper else flomat_extract_lower(b)
+
+
 def _map(fn: int, a: Flomat, c: Flomat | None, who: str) -> Flomat:
     if c is None:
         c = Flomat.alloc(a.m, a.n)

@@ -233,3 +233,66 @@ def test_compat_level12_symbols_host_pointers(fm, ref):
     lib.dlarnv_(ctypes.byref(ctypes.c_int(1)), iseed.ctypes.data, ctypes.byref(ctypes.c_int(77)), out.ctypes.data)
     want, seed_after = ref.dlarnv(1, [1, 2, 3, 5], 77)
     assert np.array_equal(out, want) and np.array_equal(iseed, seed_after)
+
+
+# ------------------------------------------------------------------------------------------ Cholesky (dpotrf_, flomat.rkt:1794-1826)
+def _spd(seed, n):
+    m = rnd(seed, n, n)
+    return np.asfortranarray(m @ m.T + n * np.eye(n))
+
+
+def test_oracle_cholesky_matches_numpy():
+    for n in (1, 5, 40):
+        a = _spd(70 + n, n)
+        l, info = Oracle.cholesky(a)
+        assert info == 0 and np.abs(l - np.linalg.cholesky(a)).max() <= 1e-13
+        u, info = Oracle.cholesky(a, upper=True)
+        assert info == 0 and np.abs(u - np.linalg.cholesky(a).T).max() <= 1e-13
+    bad = np.asfortranarray(np.array([[4.0, 2.0, 1.0], [2.0, 1.0, 3.0], [1.0, 3.0, -1.0]]))  # second leading minor is singular
+    assert Oracle.cholesky(bad)[1] == 2
+
+
+@gpu
+@pytest.mark.parametrize("n", [1, 2, 17, 128, 129, 300, 1000])
+@pytest.mark.parametrize("upper", [False, True])
+def test_cholesky_parity(fm, ref, n, upper):
+    a = _spd(80 + n, n)
+    want, _ = ref.cholesky(a, upper=upper)
+    got = fm.flomat_cholesky(up(fm, a), upper).to_numpy()
+    assert np.abs(got - want).sum(axis=0).max() / np.abs(want).sum(axis=0).max() <= 64 * n * EPS
+    rec = got.T @ got if upper else got @ got.T
+    assert np.abs(rec - a).sum(axis=0).max() / np.abs(a).sum(axis=0).max() <= 64 * n * EPS
+    # in-place form: the other triangle of A is left exactly as it was (LAPACK's contract), info = 0
+    A = up(fm, a)
+    assert fm.flomat_cholesky_bang(A, upper) == 0
+    after = A.to_numpy()
+    other = np.tril(after, -1) if upper else np.triu(after, 1)
+    assert np.array_equal(other, np.tril(a, -1) if upper else np.triu(a, 1))
+
+
+@gpu
+def test_cholesky_not_positive_definite_and_compat(fm):
+    bad = np.asfortranarray(np.array([[4.0, 2.0, 1.0], [2.0, 1.0, 3.0], [1.0, 3.0, -1.0]]))
+    assert fm.flomat_cholesky_bang(up(fm, bad)) == 2
+    n = 200
+    a = _spd(90, n)
+    big = a.copy(order="F")
+    big[150, 150] = -1e6  # breaks positive definiteness inside the second 128-block
+    assert fm.flomat_cholesky_bang(up(fm, big)) == 151
+    lib = fm.load()
+    h = a.copy(order="F")
+    info = ctypes.c_int(-7)
+    lib.dpotrf_(b"L", ctypes.byref(ctypes.c_int(n)), h.ctypes.data, ctypes.byref(ctypes.c_int(n)), ctypes.byref(info))  # host buffer
+    assert info.value == 0
+    assert np.abs(np.tril(h) - np.linalg.cholesky(a)).max() <= 1e-10 and np.array_equal(np.triu(h, 1), np.triu(a, 1))
+
+
+@gpu
+def test_cholesky_large_property(fm):
+    n = 4096
+    iseed = np.array([5, 6, 7, 9], dtype=np.int32)
+    M = fm.randn(n, n, iseed=iseed)
+    A = fm.plus(fm.times(M, fm.transpose(M)), fm.dot_times(fm.eye(n), float(n)))
+    L = fm.flomat_cholesky(A)
+    R = fm.minus(fm.times(L, fm.transpose(L)), A)
+    assert fm.norm(R, 1) / fm.norm(A, 1) <= 64 * n * EPS

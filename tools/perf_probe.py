@@ -80,6 +80,18 @@ if "lu" in what:
         print(f"mldivide n={n} nrhs=64 (copies+gesv): {ms:.3f} ms  {w/ms/1e9:.2f} TFLOP/s ({w/ms/1e9/PEAK*100:.1f}%)", flush=True)
         res[f"mldivide_{n}"] = ms
         del A0, A, Bm, X
+if "chol" in what:
+    for n in [int(x) for x in os.environ.get("CHOL_N", "4096,8192").split(",")]:
+        M = randmat(n, seed=21)
+        A0 = fm.plus(fm.times(M, fm.transpose(M)), fm.dot_times(fm.eye(n), float(n))); del M
+        A = fm.Flomat.alloc(n, n); info = fm.Pivots(0)
+        def f():
+            lib.fm_copy2d(A.a, n, A0.a, n, n, n)
+            lib.fm_potrf(b"L", n, A.a, n, info.info_ptr)
+        ms = timeit(f, reps=3) - timeit(lambda: lib.fm_copy2d(A.a, n, A0.a, n, n, n), reps=3)
+        print(f"potrf n={n}: {ms:.3f} ms  {n**3/3/ms/1e9:.2f} TFLOP/s on n^3/3 ({n**3/3/ms/1e9/PEAK*100:.1f}%), info {info.info()}", flush=True)
+        res[f"potrf_{n}"] = ms
+        del A0, A
 if "expm" in what:
     for n in [int(x) for x in os.environ.get("EXPM_N", "512,2048,8192").split(",")]:
         X = randmat(n, scale=1/math.sqrt(n), seed=5)
