@@ -1064,39 +1064,80 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
 // whole trailing square with W21^T formed by the transpose kernel: 2x the flops of a SYRK, no new kernel) -> ... ; finally only
 // the requested triangle is written back, so the other triangle of A stays untouched as LAPACK promises.
 // ---------------------------------------------------------------------------------------------
-// unblocked Cholesky of one nb x nb block (nb <= 128) in shared memory; info = global 1-based index of the first non-positive pivot
+// unblocked right-looking Cholesky of one nb x nb block (nb <= 128), the block distributed over the registers of one CTA:
+// thread (ti, tc) of a 16 x 16 grid holds the elements (ti + 16 a, tc + 16 b), a, b < 8.  Per column: the owners of the column
+// scale it by 1/sqrt(pivot) and publish it in shared memory, then every thread applies the rank-1 update to its 64 elements.
+// info = global 1-based index of the first non-positive pivot (DPOTF2 stops there).
 __global__ void __launch_bounds__(256) potf2_kernel(int nb, double *a, long long lda, int32_t *info, int j0) {
-    extern __shared__ double S[];  // S[j * (NB + 1) + i]
-    constexpr int LD = NB + 1;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < nb * nb; idx += 256) {
-        const int i = idx % nb, j = idx / nb;
-        S[j * LD + i] = a[j * lda + i];
-    }
-    __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        const double d = S[j * LD + j];
-        if (!(d > 0.0)) {  // not positive definite (or NaN): DPOTF2 stops here
-            if (tid == 0 && *info == 0) *info = j0 + j + 1;
-            break;
+    __shared__ double s_col[NB];
+    __shared__ double s_d;
+    const int tid = threadIdx.x, ti = tid & 15, tc = tid >> 4;
+    double e[8][8];
+#pragma unroll
+    for (int ba = 0; ba < 8; ++ba)
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) {
+            const int i = ti + 16 * ba, c = tc + 16 * bb;
+            e[ba][bb] = (i < nb && c < nb && i >= c) ? a[c * lda + i] : 0.0;
         }
-        const double rd = sqrt(d);
-        __syncthreads();
-        for (int i = j + tid; i < nb; i += 256) S[j * LD + i] = (i == j) ? rd : S[j * LD + i] / rd;
-        __syncthreads();
-        // trailing update of the lower triangle: S(i, c) -= S(i, j) S(c, j) for j < c <= i
-        const int rem = nb - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
-            if (i >= c) S[c * LD + i] -= S[j * LD + i] * S[j * LD + c];
-        }
-        __syncthreads();
-    }
+    if (tid == 0) s_d = e[0][0];
     __syncthreads();
-    for (int idx = tid; idx < nb * nb; idx += 256) {
-        const int i = idx % nb, j = idx / nb;
-        if (i >= j) a[j * lda + i] = S[j * LD + i];
+    bool stop = false;
+    // the column loop is split into an unrolled loop over the 16-column blocks (so that every register index below is a
+    // compile-time constant) and a rolled loop over the 16 columns of a block
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) {
+#pragma unroll 1
+        for (int jt = 0; jt < 16; ++jt) {
+            const int j = 16 * jb + jt;
+            if (stop || j >= nb) break;
+            const double d = s_d;
+            if (!(d > 0.0)) {  // not positive definite (or NaN)
+                if (tid == 0 && *info == 0) *info = j0 + j + 1;
+                stop = true;
+                break;
+            }
+            const double rd = sqrt(d);
+            if (tc == jt) {  // this thread owns rows ti + 16 a of column j
+#pragma unroll
+                for (int ba = 0; ba < 8; ++ba) {
+                    const int i = ti + 16 * ba;
+                    if (i == j) e[ba][jb] = rd;
+                    else if (i > j) e[ba][jb] = e[ba][jb] / rd;
+                    if (i >= j) s_col[i] = e[ba][jb];
+                }
+            }
+            __syncthreads();
+            double li[8], lc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                li[q] = s_col[ti + 16 * q];
+                lc[q] = s_col[tc + 16 * q];
+            }
+#pragma unroll
+            for (int ba = 0; ba < 8; ++ba)
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) {
+                    if (bb < jb || ba < bb) continue;  // finished columns / blocks above the diagonal (compile time)
+                    const int i = ti + 16 * ba, c = tc + 16 * bb;
+                    if (c > j && i >= c && i < nb) e[ba][bb] -= li[ba] * lc[bb];
+                }
+            // the next pivot, already updated, goes to everybody
+            if (jt < 15) {
+                if (ti == jt + 1 && tc == jt + 1) s_d = e[jb][jb];
+            } else if (jb < 7) {
+                if (ti == 0 && tc == 0) s_d = e[jb + 1 < 8 ? jb + 1 : 7][jb + 1 < 8 ? jb + 1 : 7];
+            }
+            __syncthreads();
+        }
     }
+#pragma unroll
+    for (int ba = 0; ba < 8; ++ba)
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) {
+            const int i = ti + 16 * ba, c = tc + 16 * bb;
+            if (i < nb && c < nb && i >= c) a[c * lda + i] = e[ba][bb];
+        }
 }
 // dst triangle := src triangle (lower: i >= j); with `flip` dst(j, i) := src(i, j) (the upper factor U = L^T)
 __global__ void __launch_bounds__(256) tri_copy_kernel(int n, const double *__restrict__ src, long long lds, double *dst, long long ldd, int flip) {
@@ -1185,16 +1226,10 @@ int k_potrf(char uplo, int n, double *a, int lda, int32_t *info) {
     if (!w) return FM_ERR_NOMEM;
     double *wt = w + (size_t)ldw * n;  // W21^T of the current step: NB x rows, leading dimension NB
     int rc = upper ? k_transpose(n, n, a, lda, w, ldw) : k_copy2d(w, ldw, a, lda, n, n);  // the lower triangle of W holds the data
-    static bool attr = false;
-    if (rc == FM_OK && !attr) {
-        cudaError_t e = cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB * (NB + 1) * (int)sizeof(double));
-        if (e != cudaSuccess) rc = set_error(FM_ERR_CUDA, "potrf: %s", cudaGetErrorString(e));
-        attr = true;
-    }
     for (int j0 = 0; rc == FM_OK && j0 < n; j0 += NB) {
         const int jb = std::min(NB, n - j0), j1 = j0 + jb, rest = n - j1;
         double *wkk = w + (size_t)j0 * ldw + j0;
-        potf2_kernel<<<1, 256, NB * (NB + 1) * sizeof(double), ctx().stream>>>(jb, wkk, ldw, info, j0);
+        potf2_kernel<<<1, 256, 0, ctx().stream>>>(jb, wkk, ldw, info, j0);
         rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "potf2 launch failed");
         count_launch();
         if (rest <= 0 || rc != FM_OK) break;
