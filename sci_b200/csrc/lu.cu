@@ -142,6 +142,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     cluster_arrive();
     cluster_wait();
     const uint32_t tx_bytes = csize * PAY * 8;
+    const bool solo = (csize == 1);
     // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP, ...: remote addresses of s_cand[0][crank][lane] and
     // s_bar[0] there
     constexpr int NDEST = (MAXC + NWARP - 1) / NWARP;
@@ -198,11 +199,14 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             }
             brcp = 1.0 / bval;  // issued early: its latency hides behind the reduction
         };
-        // the warp's winner publishes its row; the CTA's candidate goes to every CTA of the cluster
+        // the warp's winner publishes its row; the CTA's candidate goes to every CTA of the cluster.  A cluster of one CTA
+        // (`solo`: panels of <= 256 rows, the batched expm) skips the exchange: the CTA's candidate IS the pivot row and is
+        // read where the winning warp published it (solo_src = that warp).
+        int solo_src = 0;
         auto publish_and_push = [&](const int q, const bool iwin, const int bpos, const int kb, const double brcp) {
             const int buf = q % 3, wb = q & 1;
             PROF_T(tp0);
-            if (tid == 0)
+            if (tid == 0 && !solo)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsmem(&s_bar[buf])), "r"(tx_bytes) : "memory");
             if (iwin) {  // at most one lane per warp
                 double2 *wd = reinterpret_cast<double2 *>(s_wdata[wb][warp]);
@@ -224,6 +228,10 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             const int p2 = lane < NWARP ? s_wpos[wb][lane] : NOROW;
             const unsigned long long k2 = p2 != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_wdata[wb][lane < NWARP ? lane : 0][2])) : 0ull;
             const unsigned who = __ballot_sync(FULL, warp_argmax(k2, p2, p2 != NOROW));
+            if (solo) {
+                solo_src = who ? __ffs(who) - 1 : 0;
+                return;
+            }
             double payload;
             if (who) payload = s_wdata[wb][__ffs(who) - 1][lane < PAY ? lane : 0];
             else payload = __longlong_as_double((long long)NOROW << 32);
@@ -249,19 +257,21 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             const int buf = q % 3;
             if (lane == 0) s_wpos[(q + 1) & 1][warp] = NOROW;  // reset for the next publish (last read before the previous barrier)
             PROF_T(tc0);
-            bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
+            if (!solo) bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
             PROF_T(tc1);
             PROF_ADD(0, tc0, tc1);
             // global winner: same decision in every warp (lane d looks at CTA d's candidate)
-            int wr;
-            {
+            const double *prow;
+            if (!solo) {
                 const long long c0 = lane < (int)csize ? __double_as_longlong(s_cand[buf][lane][0]) : ((long long)NOROW << 32);
                 const int cp = (int)(c0 >> 32);
                 const unsigned long long ck = cp != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_cand[buf][lane < (int)csize ? lane : 0][2])) : 0ull;
                 const unsigned who = __ballot_sync(FULL, warp_argmax(ck, cp, cp != NOROW));
-                wr = who ? __ffs(who) - 1 : 0;
+                prow = &s_cand[buf][who ? __ffs(who) - 1 : 0][0];
+            } else {
+                prow = &s_wdata[q & 1][solo_src][0];
             }
-            const double2 *pr2 = reinterpret_cast<const double2 *>(&s_cand[buf][wr][0]);
+            const double2 *pr2 = reinterpret_cast<const double2 *>(prow);
             const double2 head = pr2[0];
             const long long hd = __double_as_longlong(head.x);
             const int p = (int)(hd >> 32);           // LAPACK position of the pivot row (ipiv)
@@ -276,7 +286,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             }
             const double pval = pm[0];
             if (warp == 0) {
-                if (lane < j) s_L[j][lane] = s_cand[buf][wr][2 + W - j + lane];  // multipliers of pivot row j for the leaf's earlier steps
+                if (lane < j) s_L[j][lane] = prow[2 + W - j + lane];  // multipliers of pivot row j for the leaf's earlier steps
                 if (lane == 0) {
                     s_pphys[q] = pphys;
                     if (crank == 0) {
@@ -913,6 +923,12 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
     if (csize_out) *csize_out = m <= 4096 ? pow2_ctas(m, 256) : 16;
     // many small independent panels (batched expm): a lean 128-thread variant, four CTAs per SM, one wave for 592 items
     if (A.batch >= 64 && m <= 256) return launch_panel<128, 2, 4>(A, j0, m, pw, ipiv, sp, info, maps, 1);
+    static const int solo_max = getenv("FLOMAT_LU_SOLO_MAX") ? atoi(getenv("FLOMAT_LU_SOLO_MAX")) : 256;  // developer switch
+    if (m <= solo_max && m > 256) {  // one CTA, no cluster exchange, more rows per thread
+        if (csize_out) *csize_out = 1;
+        if (m <= 512) return launch_panel<256, 2>(A, j0, m, pw, ipiv, sp, info, maps, 1);
+        if (m <= 1024) return launch_panel<256, 4>(A, j0, m, pw, ipiv, sp, info, maps, 1);
+    }
     if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
     if (m <= 8192) {
         static const char *variant = getenv("FLOMAT_LU_PANEL");  // developer switch for A/B timing: 512 | 128
