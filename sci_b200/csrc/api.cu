@@ -329,15 +329,7 @@ int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "fm_getri: bad dimensions");
     if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), g_ctx.stream));
     if (n == 0) return FM_OK;
-    // inv(A) = solution of (P L U) X = I, computed with the same blocked triangular solves as getrs.
-    const int ldx = n + (n & 1);
-    double *x = static_cast<double *>(fm_alloc_bytes((size_t)ldx * n * sizeof(double)));
-    if (!x) return FM_ERR_NOMEM;
-    int rc = k_eye(x, ldx, n, n, 0);
-    if (rc == FM_OK) rc = k_getrs(n, n, a, lda, 0, ipiv, 0, x, ldx, 0, 1);
-    if (rc == FM_OK) rc = k_copy2d(a, lda, x, ldx, n, n);
-    fm_free(x);
-    return rc;
+    return k_getri(n, a, lda, ipiv);
 }
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
     FM_TRY(ensure_init());

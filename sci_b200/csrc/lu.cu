@@ -1187,6 +1187,39 @@ __global__ void __launch_bounds__(256) tri_copy_kernel(int n, const double *__re
     }
 }
 
+// idx[i] = original row that LAPACK's interchange sequence leaves at position i (sequential: one thread)
+__global__ void perm_forward_kernel(int n, const int32_t *ipiv, int32_t *idx) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    for (int i = 0; i < n; ++i) {
+        const int p = ipiv[i] - 1;
+        if (p != i && p >= 0 && p < n) { const int t = idx[i]; idx[i] = idx[p]; idx[p] = t; }
+    }
+}
+// dst(:, idx[j]) := src(:, j)
+__global__ void __launch_bounds__(256) scatter_cols_kernel(int n, const double *__restrict__ src, long long lds, double *dst, long long ldd,
+                                                            const int32_t *idx) {
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        const long long dj = idx[j];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[dj * ldd + i] = src[(long long)j * lds + i];
+    }
+}
+
+// Z := L^-1 for the unit lower triangle T (w x w), Z initialised to the identity: Z11 = L11^-1, Z22 = L22^-1 recursively,
+// Z21 = -L22^-1 (L21 Z11); Z12 stays zero.  Half the work of a forward sweep over a dense identity.
+int rinv_unit_lower(int w, const double *T, int ldt, double *Z, int ldz) {
+    if (w <= 0) return FM_OK;
+    if (w <= NB) return trsm_leaf<false>(w, w, T, ldt, 0, Z, ldz, 0, 1);
+    const int w1 = split(w), w2 = w - w1;
+    FM_TRY(rinv_unit_lower(w1, T, ldt, Z, ldz));
+    FM_TRY(rinv_unit_lower(w2, T + (size_t)w1 * ldt + w1, ldt, Z + (size_t)w1 * ldz + w1, ldz));
+    GemmEpilogue ep;
+    ep.alpha = -1.0;
+    ep.beta = 0.0;
+    FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, w2, w1, w1, T + w1, ldt, 0, Z, ldz, 0, Z + w1, ldz, 0, 1, ep));  // Z21 = -L21 Z11
+    return rtrsm<false>(w2, w1, T + (size_t)w1 * ldt + w1, ldt, 0, Z + w1, ldz, 0, 1);                       // Z21 := L22^-1 Z21
+}
+
 }  // namespace
 
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch) {
@@ -1227,6 +1260,30 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     FM_TRY(permute_rows(B, 0, nrhs, maps, 0, n));                          // P B   (DLASWP)
     FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));          // L y = P B
     return rtrsm<true>(n, nrhs, lu, lda, sa, b, ldb, sb, batch);            // U x = y
+}
+
+// dgetri: a (its LU factors) := inverse.  A = P^T L U  =>  inv(A) = U^-1 L^-1 P: W = U^-1 (L^-1) with the structured inverse of
+// L (lower triangular, n^3/3 instead of n^3 flops for that half), then the columns of W go to their places: 4/3 n^3 flops on
+// top of the factorization, LAPACK's count, all of it in GEMMs and leaf solves.
+int k_getri(int n, double *a, int lda, const int32_t *ipiv) {
+    if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "getri: bad dimensions");
+    if (n == 0) return FM_OK;
+    const int ldx = n + (n & 1);
+    double *x = static_cast<double *>(fm_alloc_bytes((size_t)ldx * n * sizeof(double) + (size_t)n * sizeof(int32_t) + 16));
+    if (!x) return FM_ERR_NOMEM;
+    int32_t *idx = reinterpret_cast<int32_t *>(x + (size_t)ldx * n);
+    int rc = k_eye(x, ldx, n, n, 0);
+    if (rc == FM_OK) rc = rinv_unit_lower(n, a, lda, x, ldx);
+    if (rc == FM_OK) rc = rtrsm<true>(n, n, a, lda, 0, x, ldx, 0, 1);
+    if (rc == FM_OK) {
+        perm_forward_kernel<<<1, 32, 0, ctx().stream>>>(n, ipiv, idx);
+        dim3 grid(ceil_div(n, 256) < 32 ? ceil_div(n, 256) : 32, n < 4096 ? n : 4096);
+        scatter_cols_kernel<<<grid, 256, 0, ctx().stream>>>(n, x, ldx, a, lda, idx);
+        rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "getri: launch failed");
+        count_launch(2);
+    }
+    fm_free(x);
+    return rc;
 }
 
 // dpotrf: uplo 'L' (A = L L^T, lower triangle overwritten) or 'U' (A = U^T U, upper triangle overwritten)

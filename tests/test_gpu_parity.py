@@ -325,6 +325,19 @@ def test_solve_roundtrip_full_size_on_device(fm, n, nrhs):
     assert fm.norm(R2, 1) / fm.norm(A, 1) <= tol(n)
 
 
+@pytest.mark.parametrize("n", [130, 1500, 4096])
+def test_inverse_parity_and_property(fm, ref, n):
+    """`inv` = dgetrf + dgetri (flomat.rkt:1770-1781): structured L^-1, U sweep, column scatter.  Diagonally shifted random
+    matrices keep cond(A) small, so ||A inv(A) - I||_1 and the distance to the oracle's inverse stay inside 64 n eps."""
+    a = rnd(70 + n, n, n) + np.sqrt(n) * 2.0 * np.eye(n)
+    A = up(fm, a)
+    Ai = fm.inv(A)
+    R = fm.minus(fm.times(A, Ai), fm.eye(n))
+    assert fm.norm(R, 1) <= tol(n) * 8
+    if n <= 1500:
+        assert normwise_rel_err(Ai.to_numpy(), ref.inv(a)) <= tol(n) * 8
+
+
 # ---------------------------------------------------------------- expm
 @pytest.mark.parametrize("mode", [0, 1])
 def test_expm_closed_forms_and_quirks(fm, mode):

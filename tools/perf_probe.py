@@ -80,6 +80,13 @@ if "lu" in what:
         print(f"mldivide n={n} nrhs=64 (copies+gesv): {ms:.3f} ms  {w/ms/1e9:.2f} TFLOP/s ({w/ms/1e9/PEAK*100:.1f}%)", flush=True)
         res[f"mldivide_{n}"] = ms
         del A0, A, Bm, X
+if "inv" in what:
+    for n in [int(x) for x in os.environ.get("INV_N", "2048,8192").split(",")]:
+        A0 = randmat(n, seed=31)
+        ms = timeit(lambda: fm.inv(A0), reps=3)
+        print(f"inv n={n} (copy + getrf + getri): {ms:.3f} ms  {2*n**3/ms/1e9:.2f} TFLOP/s on 2n^3 ({2*n**3/ms/1e9/PEAK*100:.1f}%)", flush=True)
+        res[f"inv_{n}"] = ms
+        del A0
 if "chol" in what:
     for n in [int(x) for x in os.environ.get("CHOL_N", "4096,8192").split(",")]:
         M = randmat(n, seed=21)
