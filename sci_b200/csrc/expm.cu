@@ -161,12 +161,18 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
     // ---- repeated squaring (expm.rkt:209-210), per-item round counts ----
     double *cur = num, *nxt = spare;
-    if (batch == 1) {
-        if (max_rounds == 0) return k_copy2d(out, ldo, cur, ldw, n, n);
-        for (int r = 0; r < max_rounds; ++r) {
+    bool uniform = true;  // every item squares the same number of times (always true for one matrix, the common case for a batch)
+    for (int z = 1; z < batch; ++z) uniform = uniform && (h_rounds[z] == h_rounds[0]);
+    if (uniform) {
+        if (max_rounds == 0) {
+            if (batch == 1) return k_copy2d(out, ldo, cur, ldw, n, n);
+            for (int z = 0; z < batch; ++z) FM_TRY(k_copy2d(out + z * so, ldo, cur + z * sw, ldw, n, n));
+            return FM_OK;
+        }
+        for (int r = 0; r < max_rounds; ++r) {  // the last squaring writes straight into the output
             GemmEpilogue ep;
             const bool last = (r == max_rounds - 1);
-            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, cur, ldw, 0, cur, ldw, 0, last ? out : nxt, last ? ldo : ldw, 0, 1, ep));
+            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, cur, ldw, sw, cur, ldw, sw, last ? out : nxt, last ? ldo : ldw, last ? so : sw, batch, ep));
             double *t = cur; cur = nxt; nxt = t;
         }
         return FM_OK;
