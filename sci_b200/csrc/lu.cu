@@ -552,12 +552,13 @@ __global__ void __launch_bounds__(MAPN) permute_rows_kernel(double *a, long long
 // ipiv -> per-block net permutations (same format the panel kernel emits): one warp replays the <= 128 interchanges of
 // block blockIdx.x on a sparse model (the 128 block rows + the far rows they touch).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) ipiv_to_maps_kernel(int n, const int32_t *ipiv, long long sp, int2 *map, long long smap) {
+__global__ void __launch_bounds__(32) ipiv_to_maps_kernel(int n, const int32_t *ipiv, long long sp, int2 *map, long long smap, int block0,
+                                                          int npiv /* pivots in the block; 0 = up to NB */) {
     __shared__ int piv[NB], top[NB], fpos[NB], fval[NB];
     ipiv += blockIdx.y * sp;
-    map += blockIdx.y * smap + (long long)blockIdx.x * MAPN;
+    map += blockIdx.y * smap + (long long)(blockIdx.x + block0) * MAPN;
     const int lane = threadIdx.x;
-    const int k0 = blockIdx.x * NB, cnt = min(NB, n - k0);
+    const int k0 = (blockIdx.x + block0) * NB, cnt = min(npiv > 0 ? npiv : NB, n - k0);
     for (int i = lane; i < NB; i += 32) {
         piv[i] = i < cnt ? ipiv[k0 + i] - 1 : k0 + i;
         top[i] = k0 + i;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(32) ipiv_to_maps_kernel(int n, const int32_t *
         __syncwarp();
     }
     for (int i = lane; i < NB; i += 32) {
-        map[i] = (i < cnt && top[i] != k0 + i) ? make_int2(k0 + i, top[i]) : make_int2(-1, -1);
+        map[i] = (k0 + i < n && top[i] != k0 + i) ? make_int2(k0 + i, top[i]) : make_int2(-1, -1);  // rows of the block beyond the last pivot can be displaced too
         map[NB + i] = (i < nfar && fval[i] != fpos[i]) ? make_int2(fpos[i], fval[i]) : make_int2(-1, -1);
     }
 }
@@ -847,6 +848,46 @@ __global__ void zero_info_kernel(int32_t *info, int batch) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Panels taller than 16384 rows (more than the 16 x 1024 rows a cluster can hold in registers): plain DGETF2 with one IDAMAX
+// reduction and two small kernels per column, rows physically interchanged inside the panel.  Slow (launch bound, ~2.5 ms
+// per panel) but only the first (m - 16384)/128 panels of a very large factorization take this path.
+// ---------------------------------------------------------------------------------------------
+// one CTA: turn the IDAMAX result into ipiv / info, interchange rows j and p across the panel's columns, publish p and 1/pivot
+__global__ void __launch_bounds__(NB) tall_pivot_kernel(double *a, long long lda, int pw, int j, int grow0, const long long *amax_idx, int32_t *ipiv,
+                                                         int32_t *info, double *pivinfo /* [0] = pivot value */) {
+    const int p = j + (int)amax_idx[0];  // panel-local row of the pivot
+    const int c = threadIdx.x;
+    if (c < pw && p != j) {
+        const double t = a[c * lda + j];
+        a[c * lda + j] = a[c * lda + p];
+        a[c * lda + p] = t;
+    }
+    __syncthreads();
+    if (c == 0) {
+        const double pv = a[j * lda + j];
+        ipiv[grow0 + j] = grow0 + p + 1;
+        if (pv == 0.0 && *info == 0) *info = grow0 + j + 1;
+        pivinfo[0] = pv;
+    }
+}
+// rows below the pivot: multiplier (DGETF2's reciprocal rule) and the rank-1 update of the remaining panel columns
+__global__ void __launch_bounds__(256) tall_update_kernel(double *a, long long lda, int m, int pw, int j, const double *pivinfo) {
+    __shared__ double urow[NB];
+    const double pv = pivinfo[0];
+    for (int c = threadIdx.x; c < pw; c += 256) urow[c] = c > j ? a[c * lda + j] : 0.0;
+    __syncthreads();
+    if (pv == 0.0) return;
+    const bool use_rcp = fabs(pv) >= DBL_MIN;
+    const double rcp = 1.0 / pv;
+    for (int r = j + 1 + blockIdx.x * 256 + threadIdx.x; r < m; r += gridDim.x * 256) {
+        const double x = a[j * lda + r];
+        const double l = use_rcp ? x * rcp : x / pv;
+        a[j * lda + r] = l;
+        for (int c = j + 1; c < pw; ++c) a[c * lda + r] -= l * urow[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
 struct Mat {
@@ -912,9 +953,14 @@ int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
     return FM_OK;
 }
 
+int panel_tall(const Mat &A, int j0, int m, int pw, int32_t *ipiv, int32_t *info, const Maps &maps);
+int panel_tall_entry(const Mat &A, int j0, int m, int pw, int32_t *ipiv, int32_t *info, const Maps &maps, int *csize_out);
+
 // factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch.  One row per thread whenever the cluster
 // (<= 16 CTAs) can cover the panel: the column step is latency bound, so fewer rows per thread is faster.
 int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int *csize_out = nullptr) {
+    if (const char *tm = getenv("FLOMAT_LU_TALL_MIN"))  // test hook: send panels of more than this many rows to the tall fallback
+        if (m > atoi(tm) && A.batch == 1) return panel_tall_entry(A, j0, m, pw, ipiv, info, maps, csize_out);
     auto pow2_ctas = [](int rows, int per_cta) {
         int cs = 1;
         while (cs * per_cta < rows) cs *= 2;
@@ -937,7 +983,35 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
         return launch_panel<256, 2>(A, j0, m, pw, ipiv, sp, info, maps, 16);
     }
     if (m <= 16384) return launch_panel<256, 4>(A, j0, m, pw, ipiv, sp, info, maps, 16);
-    return set_error(FM_ERR_ARG, "getrf: panels taller than 16384 rows are not supported yet (m=%d)", m);
+    return panel_tall_entry(A, j0, m, pw, ipiv, info, maps, csize_out);
+}
+
+int panel_tall_entry(const Mat &A, int j0, int m, int pw, int32_t *ipiv, int32_t *info, const Maps &maps, int *csize_out) {
+    if (csize_out) *csize_out = 0;  // 0 = the tall fallback: no cluster, own columns already interchanged
+    return panel_tall(A, j0, m, pw, ipiv, info, maps);
+}
+
+// m > 16384: unblocked panel with explicit interchanges (see tall_pivot_kernel); the panel's own columns end up permuted,
+// its map (for the other columns) is rebuilt from ipiv
+int panel_tall(const Mat &A, int j0, int m, int pw, int32_t *ipiv, int32_t *info, const Maps &maps) {
+    if (A.batch != 1) return set_error(FM_ERR_ARG, "getrf: batched panels taller than 16384 rows are not supported (m=%d)", m);
+    double *a = A.at(j0, j0);
+    long long *d_idx = reinterpret_cast<long long *>(ctx().d_scalar + 8);
+    double *d_piv = ctx().d_scalar + 10;
+    for (int j = 0; j < pw; ++j) {
+        FM_TRY(k_iamax_device(m - j, a + (size_t)j * A.lda + j, 1, d_idx));
+        tall_pivot_kernel<<<1, NB, 0, ctx().stream>>>(a, A.lda, pw, j, j0, d_idx, ipiv, info, d_piv);
+        FM_LAUNCH_CHECK();
+        if (m - j - 1 > 0) {
+            tall_update_kernel<<<std::min(ceil_div(m - j - 1, 256), 4 * ctx().sm_count), 256, 0, ctx().stream>>>(a, A.lda, m, pw, j, d_piv);
+            FM_LAUNCH_CHECK();
+        }
+    }
+    // the net permutation of this block of pivots, in the format the cluster kernel emits (global row numbers)
+    // (`n` bounds the pivots replayed in the block: j0 + pw; every interchange target of this panel is a valid row)
+    ipiv_to_maps_kernel<<<dim3(1, 1), 32, 0, ctx().stream>>>(j0 + m, ipiv, 0, maps.base, maps.item_stride, j0 / NB, pw);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
 }
 
 // apply the row permutations of the panels covering pivots [p0, p1) to columns [c0, c0+ncols) of A
@@ -1052,8 +1126,10 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
     for (int j0 = 0; j0 < mn; j0 += NB) {
         const int jb = std::min(NB, mn - j0), j1 = j0 + jb;
         // panel j0 is complete: its interchanges go to its own and to the trailing columns now; the columns to its left (L)
-        // are off the critical chain and get all their interchanges in one pass at the end
-        FM_TRY(permute_rows(A, j0, n - j0, maps, j0, j1));
+        // are off the critical chain and get all their interchanges in one pass at the end.  (csize == 0: the tall fallback
+        // has already interchanged the panel's own columns.)
+        if (csize == 0) FM_TRY(permute_rows(A, j1, n - j1, maps, j0, j1));
+        else FM_TRY(permute_rows(A, j0, n - j0, maps, j0, j1));
         const int nr = n - j1;
         if (nr <= 0) break;
         FM_TRY(trsm_leaf<false>(jb, nr, A.at(j0, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.batch));
@@ -1068,7 +1144,7 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
         if (nb_cols > 0) {
             const bool dep = overlap && jb2 > 0;
             FM_TRY(gemm_minus(mrest, nb_cols, jb, A.at(j1, j0), A.lda, A.stride, A.at(j0, j1 + jb2), A.lda, A.stride, A.at(j1, j1 + jb2), A.lda,
-                              A.stride, A.batch, dep ? ctx().sm_count - csize : 0, dep));
+                              A.stride, A.batch, (dep && csize > 0) ? ctx().sm_count - csize : 0, dep && csize > 0));
         }
     }
     return permute_rows(A, 0, mn, maps, 0, mn, true);  // L part: column c receives the interchanges of every panel right of it
@@ -1255,7 +1331,7 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     maps.item_stride = (long long)nblocks * MAPN;
     maps.base = g_maps_getrs.get((size_t)maps.item_stride * batch);
     if (!maps.base) return FM_ERR_NOMEM;
-    ipiv_to_maps_kernel<<<dim3(nblocks, batch), 32, 0, ctx().stream>>>(n, ipiv, sp, maps.base, maps.item_stride);
+    ipiv_to_maps_kernel<<<dim3(nblocks, batch), 32, 0, ctx().stream>>>(n, ipiv, sp, maps.base, maps.item_stride, 0, 0);
     FM_LAUNCH_CHECK();
     FM_TRY(permute_rows(B, 0, nrhs, maps, 0, n));                          // P B   (DLASWP)
     FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));          // L y = P B

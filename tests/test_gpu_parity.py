@@ -325,6 +325,22 @@ def test_solve_roundtrip_full_size_on_device(fm, n, nrhs):
     assert fm.norm(R2, 1) / fm.norm(A, 1) <= tol(n)
 
 
+def test_lu_tall_panel_fallback(fm, ref, monkeypatch):
+    """Panels of more than 16384 rows take an unblocked fallback (explicit interchanges, one IDAMAX per column).  The test
+    hook FLOMAT_LU_TALL_MIN sends small panels down that path: same pivots and factors as the oracle, same solve."""
+    monkeypatch.setenv("FLOMAT_LU_TALL_MIN", "200")  # panels of > 200 rows use the fallback, the last ones the cluster kernel
+    for m, n in [(700, 700), (900, 300), (300, 900)]:
+        a = rnd(90 + m, m, n)
+        lu = up(fm, a)
+        piv, info = fm.flomat_lu_bang(lu)
+        want_lu, want_piv, _ = ref.lu(a)
+        assert info == 0 and np.array_equal(piv.to_numpy(), want_piv[: min(m, n)])
+        assert normwise_rel_err(lu.to_numpy(), want_lu) <= tol(max(m, n)) * 8
+    a, b = rnd(97, 600, 600), rnd(98, 600, 5)
+    x = fm.mldivide(up(fm, a), up(fm, b)).to_numpy()
+    assert np.abs(a @ x - b).sum(axis=0).max() / (np.abs(a).sum(axis=0).max() * np.abs(x).sum(axis=0).max()) <= tol(600)
+
+
 @pytest.mark.parametrize("n", [130, 1500, 4096])
 def test_inverse_parity_and_property(fm, ref, n):
     """`inv` = dgetrf + dgetri (flomat.rkt:1770-1781): structured L^-1, U sweep, column scatter.  Diagonally shifted random
