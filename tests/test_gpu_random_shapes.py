@@ -1,0 +1,75 @@
+"""GPU: randomized shapes (seeded) through the LU / solve / GEMM paths: non-multiples of the 128-column panels, of the
+16-column leaves and of the 8-column DMMA tiles, tall and wide matrices, views with odd offsets, many right-hand sides.
+Pivot sequences must equal the oracle's, factors and products stay inside 64 n eps."""
+import numpy as np
+import pytest
+
+from oracle.flomat_oracle import normwise_rel_err, tol
+
+pytestmark = pytest.mark.gpu
+
+
+def up(fm, x):
+    return fm.matrix(np.asfortranarray(x, dtype=np.float64))
+
+
+def plu_matrix(lu, ipiv, m, n):
+    k = min(m, n)
+    l = np.tril(lu[:, :k], -1) + np.eye(m, k)
+    u = np.triu(lu[:k, :])
+    perm = np.arange(m)
+    for i, p in enumerate(ipiv):
+        perm[[i, p - 1]] = perm[[p - 1, i]]
+    return l @ u, perm
+
+
+def test_lu_random_shapes(fm, ref):
+    rng = np.random.default_rng(2024)
+    shapes = [(int(rng.integers(1, 620)), int(rng.integers(1, 620))) for _ in range(36)]
+    shapes += [(129, 129), (257, 255), (144, 16), (16, 144), (136, 136), (1, 300), (300, 1), (513, 140), (140, 513)]
+    for m, n in shapes:
+        a = np.asfortranarray(rng.standard_normal((m, n)))
+        lu = up(fm, a)
+        piv, info = fm.flomat_lu_bang(lu)
+        _, want_piv, _ = ref.lu(a)
+        got, ip = lu.to_numpy(), piv.to_numpy()
+        assert info == 0, (m, n)
+        assert np.array_equal(ip, want_piv[: min(m, n)]), (m, n)
+        rec, perm = plu_matrix(got, ip, m, n)
+        assert normwise_rel_err(rec, a[perm, :]) <= tol(max(m, n)), (m, n)
+
+
+def test_lu_first_column_ties_pick_first_row(fm):
+    rng = np.random.default_rng(7)
+    for n in (5, 130, 300):
+        a = np.asfortranarray(rng.standard_normal((n, n)))
+        a[:, 0] = rng.choice([-1.0, 1.0], size=n)  # every entry of column 0 has the same magnitude: IDAMAX takes row 0
+        lu = up(fm, a)
+        piv, _ = fm.flomat_lu_bang(lu)
+        assert piv.to_numpy()[0] == 1
+
+
+def test_solve_random_shapes(fm, ref):
+    rng = np.random.default_rng(99)
+    for _ in range(14):
+        n, nrhs = int(rng.integers(1, 700)), int(rng.integers(1, 420))
+        a = np.asfortranarray(rng.standard_normal((n, n)) + np.sqrt(n) * np.eye(n))
+        b = np.asfortranarray(rng.standard_normal((n, nrhs)))
+        x = fm.mldivide(up(fm, a), up(fm, b)).to_numpy()
+        r = np.abs(a @ x - b).sum(axis=0).max() / (np.abs(a).sum(axis=0).max() * np.abs(x).sum(axis=0).max())
+        assert r <= tol(n), (n, nrhs)
+        assert normwise_rel_err(x, ref.mldivide(a, b)) <= tol(n) * 8, (n, nrhs)
+
+
+def test_gemm_random_shapes_and_views(fm, ref):
+    rng = np.random.default_rng(5)
+    for _ in range(24):
+        m, n, k = (int(rng.integers(1, 500)) for _ in range(3))
+        a, b = np.asfortranarray(rng.standard_normal((m, k))), np.asfortranarray(rng.standard_normal((k, n)))
+        assert normwise_rel_err(fm.times(up(fm, a), up(fm, b)).to_numpy(), a @ b) <= tol(max(m, n, k)), (m, n, k)
+    big_a, big_b = np.asfortranarray(rng.standard_normal((300, 280))), np.asfortranarray(rng.standard_normal((290, 310)))
+    A, B = up(fm, big_a), up(fm, big_b)
+    for (i, j, mm, kk, jj, nn) in [(1, 1, 150, 200, 3, 170), (2, 4, 128, 128, 2, 128), (7, 0, 33, 257, 1, 9)]:
+        va, vb = A.sub(i, j, mm, kk), B.sub(j, jj, kk, nn)  # odd offsets: 8-byte aligned views, lda > m
+        want = big_a[i:i + mm, j:j + kk] @ big_b[j:j + kk, jj:jj + nn]
+        assert normwise_rel_err(fm.times(va, vb).to_numpy(), want) <= tol(max(mm, nn, kk))
