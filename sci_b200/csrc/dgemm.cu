@@ -74,6 +74,7 @@ struct EpiParams {
     int pdl_wait;   // launched as a programmatic dependent of the previous kernel: wait for it before exiting
     int ksplit;     // > 1: the k range is cut into ksplit slices, slice s of tile t writes its raw partial product to C + s * kstride
     long long kstride;
+    int stagger_ns;  // two CTAs per SM: the second wave of CTAs starts this much later, so that one CTA's epilogue overlaps the other's main loop
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -168,6 +169,11 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     // ===================== DMMA consumers =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REG_CONSUMER));
+    if (Cfg::CTAS_PER_SM == 2 && ep.stagger_ns > 0 && blockIdx.x >= (gridDim.x + 1) / 2) {
+        // Equal tiles keep the two CTAs of an SM in lock step: both in their epilogue (C read-modify-write) at once, DMMA pipe idle.
+        // A fixed head start for the first wave of CTAs is kept for the whole launch, since every tile takes the same time.
+        for (int t = 0; t < ep.stagger_ns; t += 1000) __nanosleep(1000);
+    }
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp % Cfg::WGM, wn = warp / Cfg::WGM;
     const int wm0 = wm * Cfg::WTM, wn0 = wn * Cfg::WTN;
@@ -506,6 +512,8 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     int vec_all = vec_ok;
     for (int r = 0; r < ep.npeers; ++r)
         if (reinterpret_cast<uintptr_t>(ep.peer[r]) & 15u) vec_all = 0;
+    EpiParams epl = ep;
+    if (total < 4LL * grid) epl.stagger_ns = 0;  // the head start only pays when every CTA walks several tiles
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
@@ -516,13 +524,14 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = ep.pdl_wait ? 1 : 0;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, ep, vec_all));
+    FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, epl, vec_all));
     count_launch();
     return FM_OK;
 }
 
 bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer switches for A/B timing
 bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
+int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
 
 }  // namespace
 
@@ -550,6 +559,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
     ep.ksplit = 1;
     ep.kstride = 0;
+    ep.stagger_ns = (epi.beta != 0.0 && k <= 512) ? g_stagger_ns : 0;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
