@@ -815,6 +815,164 @@ __global__ void __launch_bounds__(TR_NT) trsm_leaf_kernel(int nb, int ncols, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// leaf triangular solve on the FP64 tensor pipe.  Same contract as trsm_leaf_kernel (and the same 16 x 16 blocking with
+// inverted diagonal blocks), but every 16 x 16 block product is 32 DMMAs on distributed fragments instead of 512 FMAs fed by
+// broadcast LDS.128 -- the FMA version is bound by the shared-memory pipe (one 16-byte broadcast per two FMAs).
+// One CTA = 8 warps = 32 columns; warp w owns block-row w (rows 16w..16w+15) as C fragments (16 doubles per lane).
+// Step bk: warp bk turns its block into B fragments through a small smem tile, multiplies by inv(T_kk) (A fragments straight
+// from the staged T, row stride 20 doubles: conflict free), publishes -x_bk in a double-buffered tile; one __syncthreads;
+// every warp still to be solved accumulates T(w, bk) (-x_bk).
+// ---------------------------------------------------------------------------------------------
+constexpr int TD_LP = 20;            // row stride of a staged T block
+constexpr int TD_BLK = 16 * TD_LP;   // doubles per block
+constexpr int TD_XLD = 36;           // row stride of the 16 x 32 exchange tiles
+constexpr int TD_SMEM = (36 * TD_BLK + 3 * 16 * TD_XLD) * (int)sizeof(double);
+template <bool UPPER, bool RSIDE>
+__global__ void __launch_bounds__(256) trsm_leaf_dmma_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
+                                                             long long ldb, long long sb) {
+    constexpr bool UNIT = !UPPER && !RSIDE;
+    extern __shared__ double sm[];
+    double *Ts = sm;                  // block (bi, bk): Ts[blk * TD_BLK + i * TD_LP + k] = T(16 bi + i, 16 bk + k)
+    double *XC = sm + 36 * TD_BLK;    // conversion tile of the solving warp
+    double *XB = XC + 16 * TD_XLD;    // two broadcast tiles
+    T += blockIdx.y * st;
+    B += blockIdx.y * sb;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int ngroups = (ncols + 31) / 32;
+    auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
+    // ---- stage the triangle of T (zeros beyond nb) ----
+    {
+        int big = 0, small = 0;
+        const int i = tid & 15, k = tid >> 4;  // one element per thread and block; consecutive threads walk a column of T
+        for (int blk = 0; blk < 36; ++blk) {
+            const int bi = UPPER ? small : big, bk = UPPER ? big : small;
+            const int gi = bi * 16 + i, gk = bk * 16 + k;
+            const bool ok = gi < nb && gk < nb;
+            cp_async8(lsmem(Ts + blk * TD_BLK + i * TD_LP + k), ok ? T + gk * ldt + gi : T, ok);
+            if (++small > big) { small = 0; ++big; }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int grp = blockIdx.x;
+    double yc[2][4][2];
+    auto elem = [&](int row, int col) -> double * { return RSIDE ? B + col + (long long)row * ldb : B + (long long)col * ldb + row; };
+    auto load_y = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = 16 * w + 8 * mt + g, col = grp * 32 + 8 * nt + 2 * t + e;
+                    yc[mt][nt][e] = (row < nb && col < ncols) ? *elem(row, col) : 0.0;
+                }
+    };
+    load_y();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
+    if (w < 4) {
+        const int d = w * 2 + (lane >> 4);
+        double *tb = Ts + blk_index(d, d) * TD_BLK;
+        auto el = [&](int i, int k) -> double & { return tb[i * TD_LP + k]; };
+        const int j = lane & 15;
+        double z[16];
+        if (!UPPER) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < i) acc -= el(i, k) * ((k >= j) ? z[k] : 0.0);
+                const double dg = (UNIT || 16 * d + i >= nb) ? 1.0 : el(i, i);
+                z[i] = (i >= j) ? (UNIT ? acc : acc / dg) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 15; i >= 0; --i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 15; k >= 0; --k)
+                    if (k > i) acc -= el(i, k) * ((k <= j) ? z[k] : 0.0);
+                const double dg = (16 * d + i < nb) ? el(i, i) : 1.0;
+                z[i] = (i <= j) ? acc / dg : 0.0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) el(i, j) = z[i];
+    }
+    __syncthreads();
+    auto frag_a = [&](const double *tb, double (&af)[2][4]) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) af[mt][ks] = tb[(8 * mt + g) * TD_LP + 4 * ks + t];
+    };
+    auto frag_b = [&](const double *xs, double (&bf)[4][4]) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) bf[ks][nt] = xs[(4 * ks + t) * TD_XLD + 8 * nt + g];
+    };
+    auto put_c = [&](double *xs, const double (&c)[2][4][2], double sign) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                *reinterpret_cast<double2 *>(xs + (8 * mt + g) * TD_XLD + 8 * nt + 2 * t) = make_double2(sign * c[mt][nt][0], sign * c[mt][nt][1]);
+    };
+    for (;;) {  // column groups of this CTA (T and the inverted diagonal blocks are staged once)
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {
+            const int bk = UPPER ? 7 - s : s;
+            double *xb = XB + (s & 1) * 16 * TD_XLD;
+            if (w == bk) {
+                double af[2][4], bf[4][4];
+                put_c(XC, yc, 1.0);
+                __syncwarp();
+                frag_b(XC, bf);
+                frag_a(Ts + blk_index(bk, bk) * TD_BLK, af);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        yc[mt][nt][0] = yc[mt][nt][1] = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) dmma884(yc[mt][nt][0], yc[mt][nt][1], af[mt][ks], bf[ks][nt]);
+                    }
+                put_c(xb, yc, -1.0);  // the others accumulate T (-x)
+            }
+            __syncthreads();
+            if (UPPER ? (w < bk) : (w > bk)) {
+                double af[2][4], bf[4][4];
+                frag_b(xb, bf);
+                frag_a(Ts + blk_index(w, bk) * TD_BLK, af);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) dmma884(yc[mt][nt][0], yc[mt][nt][1], af[mt][ks], bf[ks][nt]);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = 16 * w + 8 * mt + g, col = grp * 32 + 8 * nt + 2 * t + e;
+                    if (row < nb && col < ncols) *elem(row, col) = yc[mt][nt][e];
+                }
+        grp += gridDim.x;
+        if (grp >= ngroups) break;
+        __syncthreads();  // the last step's broadcast tile is still being read by slower warps
+        load_y();
+    }
+}
+
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
     // pivots-sign (flomat.rkt:1487) times the LEFT-TO-RIGHT product of the diagonal (:1837-1842): the product is taken
     // sequentially by one thread so the rounding sequence is the reference's; the loads are staged by the whole CTA.
@@ -1043,9 +1201,31 @@ int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, 
     return FM_OK;
 }
 
+template <bool UPPER, bool RSIDE>
+int trsm_leaf_dmma_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+    static bool attr = false;
+    if (!attr) {
+        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_dmma_kernel<UPPER, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM));
+        attr = true;
+    }
+    const int groups = ceil_div(ncols, 32);
+    int gx = ceil_div(2 * ctx().sm_count, batch);  // 2 CTAs per SM fill the machine; beyond that a CTA walks several groups
+    if (gx > groups) gx = groups;
+    if (gx < 1) gx = 1;
+    trsm_leaf_dmma_kernel<UPPER, RSIDE><<<dim3(gx, batch), 256, TD_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+bool trsm_use_fma() {
+    static const bool fma = getenv("FLOMAT_TRSM_FMA") != nullptr;  // developer switch: the FMA leaf kernel
+    return fma;
+}
+
 template <bool UPPER>
 int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     if (nb <= 0 || ncols <= 0) return FM_OK;
+    if (!trsm_use_fma()) return trsm_leaf_dmma_launch<UPPER, false>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
     // two columns per thread once 64-column CTAs already fill the machine (half the shared-memory traffic per column)
     const long long groups64 = (long long)ceil_div(ncols, 64) * batch;
     if (groups64 >= ctx().sm_count / 2) return trsm_leaf_launch<UPPER, 2>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
@@ -1383,7 +1563,8 @@ int k_potrf(char uplo, int n, double *a, int lda, int32_t *info) {
         count_launch();
         if (rest <= 0 || rc != FM_OK) break;
         double *w21 = wkk + jb;  // rest x jb
-        if (rest >= 64 * (ctx().sm_count / 2)) rc = trsm_leaf_launch<false, 2, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        if (!trsm_use_fma()) rc = trsm_leaf_dmma_launch<false, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        else if (rest >= 64 * (ctx().sm_count / 2)) rc = trsm_leaf_launch<false, 2, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
         else rc = trsm_leaf_launch<false, 1, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
         if (rc == FM_OK) rc = k_transpose(rest, jb, w21, ldw, wt, NB);
         if (rc == FM_OK) rc = gemm_minus(rest, rest, jb, w21, ldw, 0, wt, NB, 0, w + (size_t)j1 * ldw + j1, ldw, 0, 1);
