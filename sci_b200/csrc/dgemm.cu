@@ -592,6 +592,31 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
         return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
     }
 
+    // Operands the tensor maps cannot describe (transposed, 8-byte aligned views, odd leading dimensions): for products that are
+    // worth it, bring the offending operand into an aligned, untransposed workspace (16 B/element of extra traffic against
+    // 2k flops/element) and take the TMA path; small products stay on the generic kernel.
+    if (batch == 1 && k > 0 && encode_fn() != nullptr && (double)m * n * k >= 16777216.0 && epi.npeers == 0) {
+        const bool fix_a = ta || !al16(a) || (lda % 2 != 0), fix_b = tb || !al16(b) || (ldb % 2 != 0);
+        const int ldwa = m + (m & 1), ldwb = k + (k & 1);
+        double *wa = nullptr, *wb = nullptr;
+        int rc = FM_OK;
+        if (fix_a) {
+            wa = static_cast<double *>(fm_alloc_bytes((size_t)ldwa * k * sizeof(double)));
+            if (!wa) return FM_ERR_NOMEM;
+            rc = ta ? k_transpose(k, m, a, lda, wa, ldwa) : k_copy2d(wa, ldwa, a, lda, m, k);
+        }
+        if (rc == FM_OK && fix_b) {
+            wb = static_cast<double *>(fm_alloc_bytes((size_t)ldwb * n * sizeof(double)));
+            if (!wb) rc = FM_ERR_NOMEM;
+            else rc = tb ? k_transpose(n, k, b, ldb, wb, ldwb) : k_copy2d(wb, ldwb, b, ldb, k, n);
+        }
+        if (rc == FM_OK)
+            rc = k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, fix_a ? wa : a, fix_a ? ldwa : lda, 0, fix_b ? wb : b, fix_b ? ldwb : ldb, 0, c, ldc, sc, 1, epi);
+        if (wa) fm_free(wa);  // cached blocks are reused in stream order
+        if (wb) fm_free(wb);
+        return rc;
+    }
+
     dim3 grid(ceil_div(m, GB), ceil_div(n, GB), batch);
     if (grid.y > 65535 || grid.z > 65535) return set_error(FM_ERR_ARG, "dgemm(generic): grid too large");
     dgemm_generic_kernel<<<grid, 128, 0, ctx().stream>>>(ta ? 1 : 0, tb ? 1 : 0, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, ep);

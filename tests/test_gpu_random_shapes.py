@@ -73,3 +73,23 @@ def test_gemm_random_shapes_and_views(fm, ref):
         va, vb = A.sub(i, j, mm, kk), B.sub(j, jj, kk, nn)  # odd offsets: 8-byte aligned views, lda > m
         want = big_a[i:i + mm, j:j + kk] @ big_b[j:j + kk, jj:jj + nn]
         assert normwise_rel_err(fm.times(va, vb).to_numpy(), want) <= tol(max(mm, nn, kk))
+
+
+def test_gemm_large_transposed_and_unaligned_operands(fm, ref):
+    """Products big enough to be worth it re-lay transposed / 8-byte-aligned / odd-ld operands into aligned workspaces and run
+    the TMA kernel: same results as the generic path and the oracle."""
+    rng = np.random.default_rng(11)
+    m, n, k = 301, 283, 277
+    for ta, tb in [(True, False), (False, True), (True, True)]:
+        a = np.asfortranarray(rng.standard_normal((k, m) if ta else (m, k)))
+        b = np.asfortranarray(rng.standard_normal((n, k) if tb else (k, n)))
+        c = np.asfortranarray(rng.standard_normal((m, n)))
+        C = up(fm, c)
+        fm.flomat_times(up(fm, a), up(fm, b), C, alpha=1.5, beta=-0.25, transpose_a=ta, transpose_b=tb)
+        want = ref.gemm(a, b, c.copy(order="F"), alpha=1.5, beta=-0.25, ta=ta, tb=tb)
+        assert normwise_rel_err(C.to_numpy(), want) <= tol(max(m, n, k)), (ta, tb)
+    big_a, big_b = np.asfortranarray(rng.standard_normal((601, 580))), np.asfortranarray(rng.standard_normal((590, 611)))
+    A, B = up(fm, big_a), up(fm, big_b)  # odd leading dimensions and odd offsets
+    va, vb = A.sub(1, 3, 500, 400), B.sub(3, 1, 400, 450)
+    want = big_a[1:501, 3:403] @ big_b[3:403, 1:451]
+    assert normwise_rel_err(fm.times(va, vb).to_numpy(), want) <= tol(500)
