@@ -77,6 +77,9 @@ int k_copy_strided(int n, const double *x, long long incx, double *y, long long 
 int k_scal_strided(int n, double alpha, double *x, long long incx);
 int k_lincomb(int m, int n, double ci, double c1, const double *a1, int ld1, double c2, const double *a2, int ld2, double *out, int ldo,
               long long s1, long long s2, long long so, int batch);
+// out_k := ci_k*I + c1_k*a1 + c2_k*a2 over `batch` contiguous ld x n workspaces (ld even, item stride ld*n); a2, o1 may be null
+int k_pade_terms(int n, int ld, int batch, const double *a1, const double *a2, double ci0, double c10, double c20, double *o0, double ci1,
+                 double c11, double c21, double *o1);
 int k_div_pow2_batched(int n, const double *a, int lda, long long sa, double *x, int ldx, long long sx, const double *scale_dev, int batch);
 // norm.cu
 int k_norm_device(char type, int m, int n, const double *a, int lda, double *d_out);  // result stays on device

@@ -222,6 +222,71 @@ __global__ void __launch_bounds__(kThreads) div_scale_kernel(int n, const double
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[j * ldx + i] = a[j * lda + i] / d;
 }
 
+// The expm workspaces of a batch are one contiguous ld x (n*batch) array (item stride = ld*n, ld even), so the polynomial
+// terms are assembled over the flattened array with 16-byte accesses, four in flight per operand per thread, and up to two
+// results per pass over the inputs:  out_k := ci_k*I + c1_k*A1 + c2_k*A2  (k < NOUT; A2 may be null).
+// Rounding per element is that of lincomb_kernel (separate multiply and add, flomat.rkt:1020-1036 + 805-842).
+struct TermCoef { double ci, c1, c2; };
+template <int NOUT>
+__global__ void __launch_bounds__(kThreads) pade_terms_kernel(long long total2, int ld, int n, const double *__restrict__ a1,
+                                                               const double *__restrict__ a2, TermCoef k0, TermCoef k1,
+                                                               double *__restrict__ o0, double *__restrict__ o1) {
+    const long long stride = (long long)gridDim.x * kThreads * kUnroll;
+    for (long long i0 = (long long)blockIdx.x * kThreads * kUnroll + threadIdx.x; i0 < total2; i0 += stride) {
+        double2 x[kUnroll], y[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + (long long)u * kThreads;
+            if (i < total2) {
+                x[u] = reinterpret_cast<const double2 *>(a1)[i];
+                y[u] = a2 ? reinterpret_cast<const double2 *>(a2)[i] : make_double2(0.0, 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + (long long)u * kThreads;
+            if (i < total2) {
+                const long long col = (2 * i) / ld;
+                const int row = (int)(2 * i - col * ld), j = (int)(col % n);  // ld is even: both elements are in column j
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) {
+                    const TermCoef c = k ? k1 : k0;
+                    double v0 = __dmul_rn(c.c1, x[u].x), v1 = __dmul_rn(c.c1, x[u].y);
+                    if (a2) {
+                        v0 = __dadd_rn(v0, __dmul_rn(c.c2, y[u].x));
+                        v1 = __dadd_rn(v1, __dmul_rn(c.c2, y[u].y));
+                    }
+                    if (row == j) v0 = __dadd_rn(c.ci, v0);
+                    if (row + 1 == j) v1 = __dadd_rn(c.ci, v1);
+                    reinterpret_cast<double2 *>(k ? o1 : o0)[i] = make_double2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
+// flattened form of div_scale_kernel for contiguous even-sized items: x[e] = a[e] / scale[e / item]
+__global__ void __launch_bounds__(kThreads) div_scale_flat_kernel(long long total2, long long item2, const double *__restrict__ a,
+                                                                   double *__restrict__ x, const double *__restrict__ scale) {
+    const long long stride = (long long)gridDim.x * kThreads * kUnroll;
+    for (long long i0 = (long long)blockIdx.x * kThreads * kUnroll + threadIdx.x; i0 < total2; i0 += stride) {
+        double2 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + (long long)u * kThreads;
+            if (i < total2) v[u] = reinterpret_cast<const double2 *>(a)[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + (long long)u * kThreads;
+            if (i < total2) {
+                const double d = scale[i / item2];
+                reinterpret_cast<double2 *>(x)[i] = make_double2(v[u].x / d, v[u].y / d);
+            }
+        }
+    }
+}
+
 __global__ void axpy_strided_kernel(int n, double alpha, const double *x, long long incx, double *y, long long incy) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         y[i * incy] = __dadd_rn(y[i * incy], __dmul_rn(alpha, x[i * incx]));
@@ -391,8 +456,31 @@ int k_lincomb(int m, int n, double ci, double c1, const double *a1, int ld1, dou
     return FM_OK;
 }
 
+int k_pade_terms(int n, int ld, int batch, const double *a1, const double *a2, double ci0, double c10, double c20, double *o0, double ci1,
+                 double c11, double c21, double *o1) {
+    if (n <= 0 || batch <= 0) return FM_OK;
+    const long long total2 = (long long)ld * n * batch / 2;
+    long long blocks = (total2 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+    const long long cap = (long long)ctx().sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    const TermCoef k0 = {ci0, c10, c20}, k1 = {ci1, c11, c21};
+    if (o1) pade_terms_kernel<2><<<(int)blocks, kThreads, 0, ctx().stream>>>(total2, ld, n, a1, a2, k0, k1, o0, o1);
+    else pade_terms_kernel<1><<<(int)blocks, kThreads, 0, ctx().stream>>>(total2, ld, n, a1, a2, k0, k1, o0, o1);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
 int k_div_pow2_batched(int n, const double *a, int lda, long long sa, double *x, int ldx, long long sx, const double *scale_dev, int batch) {
     if (n <= 0 || batch <= 0) return FM_OK;
+    if (lda == ldx && (batch == 1 || sa == sx) && sx == (long long)ldx * n && (ldx % 2) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
+        const long long total2 = sx * batch / 2;
+        long long blocks = (total2 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+        const long long cap = (long long)ctx().sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        div_scale_flat_kernel<<<(int)blocks, kThreads, 0, ctx().stream>>>(total2, sx / 2, a, x, scale_dev);
+        FM_LAUNCH_CHECK();
+        return FM_OK;
+    }
     dim3 grid(ceil_div(n, kThreads), n > 1024 ? 1024 : n, batch);
     div_scale_kernel<<<grid, kThreads, 0, ctx().stream>>>(n, a, lda, sa, x, ldx, sx, scale_dev);
     FM_LAUNCH_CHECK();

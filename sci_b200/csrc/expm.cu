@@ -114,8 +114,12 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
         ep.diag = diag;
         return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, x, ldw, sw, y, ldw, sw, z, ldw, sw, batch, ep);
     };
+    // polynomial terms over the contiguous workspaces: o := ci I + c1 a1 + c2 a2, and optionally a second result of the same pass
     auto lin = [&](double ci, double c1, const double *a1, double c2, const double *a2, double *o) {
-        return k_lincomb(n, n, ci, c1, a1, ldw, c2, a2, ldw, o, ldw, sw, sw, sw, batch);
+        return k_pade_terms(n, ldw, batch, a1, a2, ci, c1, c2, o, 0.0, 0.0, 0.0, nullptr);
+    };
+    auto lin2 = [&](const double *a1, const double *a2, double ci0, double c10, double c20, double *o0, double ci1, double c11, double c21, double *o1) {
+        return k_pade_terms(n, ldw, batch, a1, a2, ci0, c10, c20, o0, ci1, c11, c21, o1);
     };
 
     double *X = B[0], *A2 = B[1];
@@ -141,12 +145,12 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     } else {
         double *A4 = B[2];
         FM_TRY(gemm(A2, A2, A4, 0.0, false, 0.0));
-        FM_TRY(lin(0.0, kC[6], A2, kC[8], A4, B[3]));               // c6 X^2 + c8 X^4
-        FM_TRY(lin(kC[0], kC[2], A2, kC[4], A4, B[4]));             // c0 I + c2 X^2 + c4 X^4
+        // one pass over X^2, X^4:  c6 X^2 + c8 X^4  and  c0 I + c2 X^2 + c4 X^4
+        FM_TRY(lin2(A2, A4, 0.0, kC[6], kC[8], B[3], kC[0], kC[2], kC[4], B[4]));
         FM_TRY(gemm(B[3], A4, B[4], 1.0, false, 0.0));              // even
         E = B[4];
-        FM_TRY(lin(kC[5], kC[7], A2, 0.0, nullptr, B[3]));          // c5 I + c7 X^2
-        FM_TRY(lin(kC[1], kC[3], A2, 0.0, nullptr, B[5]));          // c1 I + c3 X^2
+        // one pass over X^2:  c5 I + c7 X^2  and  c1 I + c3 X^2
+        FM_TRY(lin2(A2, nullptr, kC[5], kC[7], 0.0, B[3], kC[1], kC[3], 0.0, B[5]));
         FM_TRY(gemm(B[3], A4, B[5], 1.0, false, 0.0));
         FM_TRY(gemm(X, B[5], B[3], 0.0, false, 0.0));               // odd
         O = B[3];

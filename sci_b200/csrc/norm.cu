@@ -53,6 +53,35 @@ __global__ void __launch_bounds__(kT) colsum_kernel(int m, int n, const double *
     }
 }
 
+// One warp per column, 16-byte loads: for many columns (the batched 256x256 items of expm, or any n >= 2048) a CTA per column
+// spends its time in the block reduction and keeps one load per thread in flight; a warp streams its column with four
+// independent 16-byte loads per lane and reduces with shuffles only.
+__global__ void __launch_bounds__(kT) colsum_warp_kernel(int m, int n, long long total, const double *a, long long lda, long long stride,
+                                                         double *colsum) {
+    const long long w = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5);
+    if (w >= total) return;
+    const int lane = threadIdx.x & 31;
+    const long long z = w / n;
+    const double *col = a + z * stride + (w - z * n) * lda;
+    double s = 0.0;
+    if ((reinterpret_cast<uintptr_t>(col) & 15u) == 0) {
+        const int m2 = m >> 1;
+        const double2 *c2 = reinterpret_cast<const double2 *>(col);
+#pragma unroll 4
+        for (int i = lane; i < m2; i += 32) {
+            const double2 v = c2[i];
+            s += fabs(v.x) + fabs(v.y);
+        }
+        if ((m & 1) && lane == 0) s += fabs(col[m - 1]);
+    } else {
+#pragma unroll 4
+        for (int i = lane; i < m; i += 32) s += fabs(col[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) colsum[w] = s;
+}
+
 // out[z] = max_j v[z*n + j] with NaN propagation; one CTA per batch item
 __global__ void __launch_bounds__(kT) max_kernel(int n, const double *v, double *out) {
     v += (long long)blockIdx.x * n;
@@ -111,8 +140,13 @@ int k_norm1_batched(int n, const double *a, int lda, long long stride, int batch
     if (n <= 0 || batch <= 0) return FM_OK;
     double *colsum = static_cast<double *>(scratch((size_t)n * batch * sizeof(double)));
     if (!colsum) return FM_ERR_NOMEM;
-    dim3 grid(n < 2048 ? n : 2048, batch);
-    colsum_kernel<<<grid, kT, 0, ctx().stream>>>(n, n, a, lda, stride, colsum);
+    const long long total = (long long)n * batch;
+    if (total >= 2048) {
+        colsum_warp_kernel<<<(unsigned)((total + kT / 32 - 1) / (kT / 32)), kT, 0, ctx().stream>>>(n, n, total, a, lda, stride, colsum);
+    } else {
+        dim3 grid(n, batch);
+        colsum_kernel<<<grid, kT, 0, ctx().stream>>>(n, n, a, lda, stride, colsum);
+    }
     FM_LAUNCH_CHECK();
     max_kernel<<<batch, kT, 0, ctx().stream>>>(n, colsum, d_out);
     FM_LAUNCH_CHECK();
@@ -130,7 +164,8 @@ int k_norm_device(char type, int m, int n, const double *a, int lda, double *d_o
         case '1': case 'O': case 'o': {
             double *colsum = static_cast<double *>(scratch((size_t)n * sizeof(double)));
             if (!colsum) return FM_ERR_NOMEM;
-            colsum_kernel<<<dim3(n < 4096 ? n : 4096, 1), kT, 0, st>>>(m, n, a, lda, 0, colsum);
+            if (n >= 2048) colsum_warp_kernel<<<(unsigned)((n + kT / 32 - 1) / (kT / 32)), kT, 0, st>>>(m, n, n, a, lda, 0, colsum);
+            else colsum_kernel<<<dim3(n, 1), kT, 0, st>>>(m, n, a, lda, 0, colsum);
             FM_LAUNCH_CHECK();
             max_kernel<<<1, kT, 0, st>>>(n, colsum, d_out);
             FM_LAUNCH_CHECK();
