@@ -973,6 +973,160 @@ __global__ void __launch_bounds__(256) trsm_leaf_dmma_kernel(int nb, int ncols, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// leaf triangular solve, right-hand sides owned by warps (the default).  The columns of B are independent, so a warp that owns
+// 8 of them never has to talk to another warp: the solve is done on the transposed system  X^T = Y^T T^-T  with the 8 columns
+// as the M dimension of the m8n8k4 DMMA and the 128 unknowns as N (16 accumulator tiles, 32 doubles per lane).  The C fragment
+// of a solved 16-row block (lane (g,t): column g, rows 2t, 2t+1, 8+2t, 8+2t+1) is, as it stands, a valid A fragment for the
+// next product if the k index of slice s is read as {2t, 2t+1, 8+2t, 8+2t+1}[s] -- the B fragments (rows of the staged T block)
+// are simply loaded with the same k order, one conflict-free LDS.128 per two slices (row stride 24 doubles).  No shared-memory
+// exchange, no __syncthreads after the staging, perfectly balanced DMMA work (the block-row version above serialises on the
+// solving warp and loads the four sub-partitions unevenly: 217 us against 65 us of DMMA time for 512 x (128 x 128, 256 rhs)).
+// Same 16 x 16 blocking and inverted diagonal blocks as the other two leaf kernels, so the same rounding behaviour.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_LP = 24;            // row stride of a staged T block: 16-byte loads of a quarter warp (2 rows x 64 B) hit all banks once
+constexpr int TC_BLK = 16 * TC_LP;
+constexpr int TC_SMEM = 36 * TC_BLK * (int)sizeof(double);
+template <bool UPPER, bool RSIDE>
+__global__ void __launch_bounds__(256, 2) trsm_leaf_cols_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
+                                                                long long ldb, long long sb, int vec_ok) {
+    constexpr bool UNIT = !UPPER && !RSIDE;
+    extern __shared__ double sm[];
+    double *Ts = sm;  // block (bi, bk): Ts[blk * TC_BLK + i * TC_LP + k] = T(16 bi + i, 16 bk + k); diagonal blocks hold their inverse
+    T += blockIdx.y * st;
+    B += blockIdx.y * sb;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    auto blk_index = [](int bi, int bk) { return UPPER ? bk * (bk + 1) / 2 + bi : bi * (bi + 1) / 2 + bk; };
+    const int nblk = (nb + 15) >> 4;
+    {
+        int big = 0, small = 0;
+        const int i = tid & 15, k = tid >> 4;  // consecutive threads walk a column of T
+        for (int blk = 0; blk < 36; ++blk) {
+            const int bi = UPPER ? small : big, bk = UPPER ? big : small;
+            const int gi = bi * 16 + i, gk = bk * 16 + k;
+            const bool ok = gi < nb && gk < nb;
+            if (big < nblk) cp_async8(lsmem(Ts + blk * TC_BLK + i * TC_LP + k), ok ? T + gk * ldt + gi : T, ok);
+            if (++small > big) { small = 0; ++big; }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- invert the diagonal blocks in place: 16 lanes per block, lane j owns column j of the inverse ----
+    if (w < 4) {
+        const int d = w * 2 + (lane >> 4);
+        double *tb = Ts + blk_index(d, d) * TC_BLK;
+        auto el = [&](int i, int k) -> double & { return tb[i * TC_LP + k]; };
+        const int j = lane & 15;
+        double z[16];
+        if (d < nblk) {
+            if (!UPPER) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (k < i) acc -= el(i, k) * ((k >= j) ? z[k] : 0.0);
+                    const double dg = (UNIT || 16 * d + i >= nb) ? 1.0 : el(i, i);
+                    z[i] = (i >= j) ? (UNIT ? acc : acc / dg) : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int i = 15; i >= 0; --i) {
+                    double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 15; k >= 0; --k)
+                        if (k > i) acc -= el(i, k) * ((k <= j) ? z[k] : 0.0);
+                    const double dg = (16 * d + i < nb) ? el(i, i) : 1.0;
+                    z[i] = (i <= j) ? acc / dg : 0.0;
+                }
+            }
+        }
+        __syncwarp();
+        if (d < nblk) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) el(i, j) = z[i];
+        }
+    }
+    __syncthreads();
+    // B fragments of one 16 x 16 block for both 8-wide n-tiles: bf[nt2][s] = Tb[8 nt2 + g][k_s(t)]
+    auto frag_b = [&](const double *tb, double (&bf)[2][4]) {
+#pragma unroll
+        for (int nt2 = 0; nt2 < 2; ++nt2) {
+            const double2 lo = *reinterpret_cast<const double2 *>(tb + (8 * nt2 + g) * TC_LP + 2 * t);
+            const double2 hi = *reinterpret_cast<const double2 *>(tb + (8 * nt2 + g) * TC_LP + 8 + 2 * t);
+            bf[nt2][0] = lo.x; bf[nt2][1] = lo.y; bf[nt2][2] = hi.x; bf[nt2][3] = hi.y;
+        }
+    };
+    const int chunks = (ncols + 63) / 64;
+    for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+        const int col = chunk * 64 + 8 * w + g;  // this lane's right-hand side
+        if (chunk * 64 + 8 * w >= ncols) continue;  // warp-uniform
+        double wc[16][2];  // wc[nt][e] = Y(8 nt + 2 t + e, col)
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            const int row = 8 * nt + 2 * t;
+            wc[nt][0] = wc[nt][1] = 0.0;
+            if (col < ncols && nt < 2 * nblk) {
+                if (!RSIDE && vec_ok && row + 1 < nb) {
+                    const double2 v = *reinterpret_cast<const double2 *>(B + (long long)col * ldb + row);
+                    wc[nt][0] = v.x; wc[nt][1] = v.y;
+                } else {
+                    if (row < nb) wc[nt][0] = RSIDE ? B[col + (long long)row * ldb] : B[(long long)col * ldb + row];
+                    if (row + 1 < nb) wc[nt][1] = RSIDE ? B[col + (long long)(row + 1) * ldb] : B[(long long)col * ldb + row + 1];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int bk = UPPER ? 7 - s : s;
+            if (bk >= nblk) continue;  // block rows beyond nb (short leaves): warp-uniform
+            double bf[2][4];
+            // x_bk^T = y_bk^T inv(T_kk)^T
+            frag_b(Ts + blk_index(bk, bk) * TC_BLK, bf);
+            const double a0 = wc[2 * bk][0], a1 = wc[2 * bk][1], a2 = wc[2 * bk + 1][0], a3 = wc[2 * bk + 1][1];
+#pragma unroll
+            for (int nt2 = 0; nt2 < 2; ++nt2) {
+                double c0 = 0.0, c1 = 0.0;
+                dmma884(c0, c1, a0, bf[nt2][0]);
+                dmma884(c0, c1, a1, bf[nt2][1]);
+                dmma884(c0, c1, a2, bf[nt2][2]);
+                dmma884(c0, c1, a3, bf[nt2][3]);
+                wc[2 * bk + nt2][0] = c0; wc[2 * bk + nt2][1] = c1;
+            }
+            const double n0 = -wc[2 * bk][0], n1 = -wc[2 * bk][1], n2 = -wc[2 * bk + 1][0], n3 = -wc[2 * bk + 1][1];
+            // y_bi^T -= x_bk^T T(bi, bk)^T for the block rows still to be solved (the next one to be solved first)
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const int bi = UPPER ? bk - q : bk + q;
+                if (bi < 0 || bi > 7) continue;  // compile time after unrolling
+                if (bi >= nblk) continue;
+                frag_b(Ts + blk_index(bi, bk) * TC_BLK, bf);
+#pragma unroll
+                for (int nt2 = 0; nt2 < 2; ++nt2) {
+                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n0, bf[nt2][0]);
+                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n1, bf[nt2][1]);
+                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n2, bf[nt2][2]);
+                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n3, bf[nt2][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            const int row = 8 * nt + 2 * t;
+            if (col < ncols && nt < 2 * nblk) {
+                if (!RSIDE && vec_ok && row + 1 < nb) {
+                    *reinterpret_cast<double2 *>(B + (long long)col * ldb + row) = make_double2(wc[nt][0], wc[nt][1]);
+                } else {
+                    if (row < nb) (RSIDE ? B[col + (long long)row * ldb] : B[(long long)col * ldb + row]) = wc[nt][0];
+                    if (row + 1 < nb) (RSIDE ? B[col + (long long)(row + 1) * ldb] : B[(long long)col * ldb + row + 1]) = wc[nt][1];
+                }
+            }
+        }
+    }
+}
+
+
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
     // pivots-sign (flomat.rkt:1487) times the LEFT-TO-RIGHT product of the diagonal (:1837-1842): the product is taken
     // sequentially by one thread so the rounding sequence is the reference's; the loads are staged by the whole CTA.
@@ -1217,6 +1371,27 @@ int trsm_leaf_dmma_launch(int nb, int ncols, const double *T, int ldt, long long
     return FM_OK;
 }
 
+template <bool UPPER, bool RSIDE>
+int trsm_leaf_cols_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+    static bool attr = false;
+    if (!attr) {
+        FM_CUDA(cudaFuncSetAttribute(trsm_leaf_cols_kernel<UPPER, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr = true;
+    }
+    const int chunks = ceil_div(ncols, 64);
+    int gx = ceil_div(2 * ctx().sm_count, batch);  // 2 CTAs per SM fill the machine; beyond that a CTA walks several 64-column chunks
+    if (gx > chunks) gx = chunks;
+    if (gx < 1) gx = 1;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15u) == 0 && (ldb % 2) == 0 && (sb % 2) == 0) ? 1 : 0;
+    trsm_leaf_cols_kernel<UPPER, RSIDE><<<dim3(gx, batch), 256, TC_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb, vec_ok);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
+int trsm_variant() {  // developer switch: 0 = right-hand sides per warp (default), 1 = block rows per warp (DMMA), 2 = FMA leaf
+    static const int v = getenv("FLOMAT_TRSM_FMA") ? 2 : getenv("FLOMAT_TRSM_ROWS") ? 1 : 0;
+    return v;
+}
 bool trsm_use_fma() {
     static const bool fma = getenv("FLOMAT_TRSM_FMA") != nullptr;  // developer switch: the FMA leaf kernel
     return fma;
@@ -1225,6 +1400,7 @@ bool trsm_use_fma() {
 template <bool UPPER>
 int trsm_leaf(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     if (nb <= 0 || ncols <= 0) return FM_OK;
+    if (trsm_variant() == 0) return trsm_leaf_cols_launch<UPPER, false>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
     if (!trsm_use_fma()) return trsm_leaf_dmma_launch<UPPER, false>(nb, ncols, T, ldt, st, B, ldb, sb, batch);
     // two columns per thread once 64-column CTAs already fill the machine (half the shared-memory traffic per column)
     const long long groups64 = (long long)ceil_div(ncols, 64) * batch;
@@ -1563,7 +1739,8 @@ int k_potrf(char uplo, int n, double *a, int lda, int32_t *info) {
         count_launch();
         if (rest <= 0 || rc != FM_OK) break;
         double *w21 = wkk + jb;  // rest x jb
-        if (!trsm_use_fma()) rc = trsm_leaf_dmma_launch<false, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        if (trsm_variant() == 0) rc = trsm_leaf_cols_launch<false, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
+        else if (!trsm_use_fma()) rc = trsm_leaf_dmma_launch<false, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
         else if (rest >= 64 * (ctx().sm_count / 2)) rc = trsm_leaf_launch<false, 2, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
         else rc = trsm_leaf_launch<false, 1, true>(jb, rest, wkk, ldw, 0, w21, ldw, 0, 1);
         if (rc == FM_OK) rc = k_transpose(rest, jb, w21, ldw, wt, NB);
