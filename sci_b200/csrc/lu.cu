@@ -1127,6 +1127,196 @@ __global__ void __launch_bounds__(256, 2) trsm_leaf_cols_kernel(int nb, int ncol
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Whole-triangle solve for FEW right-hand sides (dgetrs with nrhs <= 256: `solve`/`mldivide` with a handful of columns,
+// BASELINE config 3).  With 64 columns a blocked sweep is one leaf solve + one thin GEMM per 128 rows, 2 x 64 dependent
+// launches of ~18 us each for n = 8192; the flops are nothing, the chain of launches is everything.  Here the whole sweep is
+// ONE launch: CTA r owns block row r (128 rows x 64 columns, kept in registers as in trsm_leaf_cols_kernel: 8 columns per
+// warp, C fragments), streams the tiles T(r, k) of its block row through a 3-deep cp.async ring (the tiles do not depend on
+// the solution, so they are prefetched ahead of the wavefront), and for every k waits for CTA k to publish x_k
+// (release/acquire flag in global memory), subtracts T(r,k) x_k on the DMMA pipe, finally solves with its own diagonal tile
+// (16 x 16 diagonal blocks inverted up front, off the critical path) and publishes x_r.  All CTAs are co-resident
+// (grid <= SM count, checked by the host), so the spin waits cannot deadlock; they are bounded anyway.
+// Same blocking and inverted 16 x 16 diagonal blocks as the leaf kernels: same rounding behaviour.
+// ---------------------------------------------------------------------------------------------
+constexpr int TW_LD = 132;                 // column stride of a staged 128 x 64 half tile: LDS.64 fragment loads hit every bank once per wavefront
+constexpr int TW_HALF = 64 * TW_LD;
+constexpr int TW_DLP = 24;                 // row stride of the inverted diagonal blocks (LDS.128, as TC_LP)
+constexpr int TW_SMEM = (3 * TW_HALF + 8 * 16 * TW_DLP) * (int)sizeof(double);
+template <bool UPPER>
+__global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, const double *__restrict__ T, long long ldt, double *B, long long ldb,
+                                                           int *flags, int epoch, int vec_ok) {
+    constexpr bool UNIT = !UPPER;
+    extern __shared__ double sm[];
+    double *ring = sm;
+    double *Dinv = sm + 3 * TW_HALF;  // Dinv[d * 16 * TW_DLP + i * TW_DLP + k] = inv(T_rr block d)(i, k)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nblk = gridDim.x, cchunks = gridDim.y, chunk = blockIdx.y;
+    const int r = UPPER ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;  // low block index = early in the wavefront
+    const int rbase = r * 128;
+    const int nk = UPPER ? nblk - 1 - r : r;  // off-diagonal tiles of this block row, in the order their x_k become available
+    const int njobs = 2 * (nk + 1);           // half tiles, the diagonal tile last
+    auto issue = [&](int q) {
+        if (q < njobs) {
+            const int i = q >> 1, k = i < nk ? (UPPER ? nblk - 1 - i : i) : r, h = UPPER ? 1 - (q & 1) : (q & 1);
+            double *dst = ring + (q % 3) * TW_HALF;
+            const int cbase = k * 128 + 64 * h, row = tid & 127, gr = rbase + row;
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const int col = (tid >> 7) + 2 * jj, gc = cbase + col;
+                const bool ok = gr < n && gc < n;
+                cp_async8(lsmem(dst + col * TW_LD + row), ok ? T + (long long)gc * ldt + gr : T, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    issue(1);
+    // ---- the diagonal 16 x 16 blocks of T_rr, inverted (identity beyond n) ----
+    for (int e = tid; e < 8 * 256; e += 256) {
+        const int d = e >> 8, i = e & 15, k = (e >> 4) & 15, gi = rbase + 16 * d + i, gk = rbase + 16 * d + k;
+        Dinv[d * 16 * TW_DLP + i * TW_DLP + k] = (gi < n && gk < n) ? T[(long long)gk * ldt + gi] : 0.0;
+    }
+    __syncthreads();
+    if (w < 4) {
+        const int d = w * 2 + (lane >> 4), j = lane & 15;
+        double *tb = Dinv + d * 16 * TW_DLP;
+        auto el = [&](int i, int k) -> double & { return tb[i * TW_DLP + k]; };
+        double z[16];
+        if (!UPPER) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < i) acc -= el(i, k) * ((k >= j) ? z[k] : 0.0);
+                const double dg = (UNIT || rbase + 16 * d + i >= n) ? 1.0 : el(i, i);
+                z[i] = (i >= j) ? (UNIT ? acc : acc / dg) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 15; i >= 0; --i) {
+                double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 15; k >= 0; --k)
+                    if (k > i) acc -= el(i, k) * ((k <= j) ? z[k] : 0.0);
+                const double dg = (rbase + 16 * d + i < n) ? el(i, i) : 1.0;
+                z[i] = (i <= j) ? acc / dg : 0.0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) el(i, j) = z[i];
+    }
+    // ---- this warp's 8 right-hand sides of block row r ----
+    const int col = chunk * 64 + 8 * w + g;
+    const bool have = chunk * 64 + 8 * w < ncols;  // warp-uniform; idle warps still stage tiles and meet the barriers
+    auto ld2 = [&](int row, double &v0, double &v1) {  // rows row, row+1 of this lane's column, bypassing L1 (x_k comes from another SM)
+        v0 = v1 = 0.0;
+        if (col < ncols) {
+            const double *p = B + (long long)col * ldb + row;
+            if (vec_ok && row + 1 < n) {
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+                v0 = v.x; v1 = v.y;
+            } else {
+                if (row < n) v0 = __ldcg(p);
+                if (row + 1 < n) v1 = __ldcg(p + 1);
+            }
+        }
+    };
+    double wc[16][2];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+        wc[nt][0] = wc[nt][1] = 0.0;
+        if (have) ld2(rbase + 8 * nt + 2 * t, wc[nt][0], wc[nt][1]);
+    }
+    for (int q = 0; q < njobs; ++q) {
+        const int i = q >> 1, h = UPPER ? 1 - (q & 1) : (q & 1);
+        const bool diag = i >= nk;
+        const int k = diag ? r : (UPPER ? nblk - 1 - i : i);
+        if (!diag && (q & 1) == 0 && tid == 0) {  // x_k published?
+            const int *f = flags + k * cchunks + chunk;
+            int v, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            } while (v != epoch && ++spins < (1 << 21));
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();   // half tile q has landed for every thread; everyone is done with half tile q-1; x_k is visible
+        issue(q + 2);      // into the buffer of half tile q-1
+        const double *buf = ring + (q % 3) * TW_HALF;
+        if (!have) continue;
+        if (!diag) {
+            double xf[8][2];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) ld2(k * 128 + 64 * h + 8 * nt + 2 * t, xf[nt][0], xf[nt][1]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const double n0 = -xf[2 * kk][0], n1 = -xf[2 * kk][1], n2 = -xf[2 * kk + 1][0], n3 = -xf[2 * kk + 1][1];
+                const double *cb = buf + (16 * kk + 2 * t) * TW_LD + g;
+#pragma unroll
+                for (int nt = 0; nt < 16; ++nt) {
+                    const double b0 = cb[8 * nt], b1 = cb[TW_LD + 8 * nt], b2 = cb[8 * TW_LD + 8 * nt], b3 = cb[9 * TW_LD + 8 * nt];
+                    dmma884(wc[nt][0], wc[nt][1], n0, b0);
+                    dmma884(wc[nt][0], wc[nt][1], n1, b1);
+                    dmma884(wc[nt][0], wc[nt][1], n2, b2);
+                    dmma884(wc[nt][0], wc[nt][1], n3, b3);
+                }
+            }
+            continue;
+        }
+        // ---- diagonal tile: the four block steps whose columns are in this half ----
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+            const int bk = UPPER ? 7 - s8 : s8;
+            if ((bk >> 2) != h) continue;  // warp-uniform
+            {
+                const double *db = Dinv + bk * 16 * TW_DLP;
+                const double a0 = wc[2 * bk][0], a1 = wc[2 * bk][1], a2 = wc[2 * bk + 1][0], a3 = wc[2 * bk + 1][1];
+#pragma unroll
+                for (int nt2 = 0; nt2 < 2; ++nt2) {
+                    const double2 lo = *reinterpret_cast<const double2 *>(db + (8 * nt2 + g) * TW_DLP + 2 * t);
+                    const double2 hi = *reinterpret_cast<const double2 *>(db + (8 * nt2 + g) * TW_DLP + 8 + 2 * t);
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma884(c0, c1, a0, lo.x);
+                    dmma884(c0, c1, a1, lo.y);
+                    dmma884(c0, c1, a2, hi.x);
+                    dmma884(c0, c1, a3, hi.y);
+                    wc[2 * bk + nt2][0] = c0; wc[2 * bk + nt2][1] = c1;
+                }
+            }
+            const double n0 = -wc[2 * bk][0], n1 = -wc[2 * bk][1], n2 = -wc[2 * bk + 1][0], n3 = -wc[2 * bk + 1][1];
+            const double *cb = buf + (16 * (bk & 3) + 2 * t) * TW_LD + g;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                if (UPPER ? (nt >= 2 * bk) : (nt < 2 * bk + 2)) continue;  // compile time: only the block rows still to be solved
+                const double b0 = cb[8 * nt], b1 = cb[TW_LD + 8 * nt], b2 = cb[8 * TW_LD + 8 * nt], b3 = cb[9 * TW_LD + 8 * nt];
+                dmma884(wc[nt][0], wc[nt][1], n0, b0);
+                dmma884(wc[nt][0], wc[nt][1], n1, b1);
+                dmma884(wc[nt][0], wc[nt][1], n2, b2);
+                dmma884(wc[nt][0], wc[nt][1], n3, b3);
+            }
+        }
+    }
+    // ---- publish x_r ----
+    if (have && col < ncols) {
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            const int row = rbase + 8 * nt + 2 * t;
+            double *p = B + (long long)col * ldb + row;
+            if (vec_ok && row + 1 < n) *reinterpret_cast<double2 *>(p) = make_double2(wc[nt][0], wc[nt][1]);
+            else {
+                if (row < n) p[0] = wc[nt][0];
+                if (row + 1 < n) p[1] = wc[nt][1];
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + r * cchunks + chunk), "r"(epoch) : "memory");
+}
+
+
 __global__ void __launch_bounds__(256) det_kernel(int n, const double *lu, long long lda, const int32_t *ipiv, double *out) {
     // pivots-sign (flomat.rkt:1487) times the LEFT-TO-RIGHT product of the diagonal (:1837-1842): the product is taken
     // sequentially by one thread so the rounding sequence is the reference's; the loads are staged by the whole CTA.
@@ -1419,6 +1609,37 @@ int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, cons
     return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
 }
 
+// the single-launch wavefront solve: one CTA per (128-row block, 64-column chunk), all co-resident
+template <bool UPPER>
+int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bool *done) {
+    *done = false;
+    static const bool off = getenv("FLOMAT_TRSM_NO_WAVE") != nullptr;  // developer switch
+    const int nblk = ceil_div(w, 128), cchunks = ceil_div(ncols, 64);
+    if (off || nblk < 2 || (long long)nblk * cchunks > ctx().sm_count || ctx().max_smem_optin < TW_SMEM) return FM_OK;
+    static int *d_flags = nullptr;
+    static int epoch = 0;
+    const int nflags = 4096;
+    if (nblk * cchunks > nflags) return FM_OK;
+    if (!d_flags) {
+        FM_CUDA(cudaMalloc(&d_flags, nflags * sizeof(int)));
+        FM_CUDA(cudaMemsetAsync(d_flags, 0, nflags * sizeof(int), ctx().stream));
+    }
+    static bool attr = false;
+    if (!attr) {
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        attr = true;
+    }
+    if (++epoch == 0x7fffffff) {  // keep the published values distinct from anything an earlier launch left behind
+        FM_CUDA(cudaMemsetAsync(d_flags, 0, nflags * sizeof(int), ctx().stream));
+        epoch = 1;
+    }
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15u) == 0 && (ldb % 2) == 0) ? 1 : 0;
+    trsm_wave_kernel<UPPER><<<dim3(nblk, cchunks), 256, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok);
+    FM_LAUNCH_CHECK();
+    *done = true;
+    return FM_OK;
+}
+
 int split(int w) { return ((w / 2 + NB - 1) / NB) * NB; }  // first half of a recursive split, a multiple of the panel width
 
 // B := T^-1 B with T the w x w triangle at `T` (unit lower or upper), B w x ncols; recursive: GEMMs with a large inner
@@ -1428,6 +1649,11 @@ int rtrsm(int w, int ncols, const double *T, int ldt, long long st, double *B, i
     if (w <= 0 || ncols <= 0) return FM_OK;
     if (w <= NB) return trsm_leaf<UPPER>(w, ncols, T, ldt, st, B, ldb, sb, batch);
     if (ncols <= 2 * NB) {
+        if (batch == 1) {  // one launch for the whole triangle when every block row fits on the machine at once
+            bool done = false;
+            FM_TRY(trsm_wave<UPPER>(w, ncols, T, ldt, B, ldb, &done));
+            if (done) return FM_OK;
+        }
         // few right-hand sides: a recursive split would leave GEMMs with a handful of tiles and a long inner dimension;
         // the right-looking sweep (rank-128 updates of everything still to be solved) exposes rows/128 tiles per update
         const int nblk = ceil_div(w, NB);

@@ -93,3 +93,41 @@ def test_gemm_large_transposed_and_unaligned_operands(fm, ref):
     va, vb = A.sub(1, 3, 500, 400), B.sub(3, 1, 400, 450)
     want = big_a[1:501, 3:403] @ big_b[3:403, 1:451]
     assert normwise_rel_err(fm.times(va, vb).to_numpy(), want) <= tol(500)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nrhs", [(129, 1), (257, 65), (640, 8), (1000, 200), (2050, 64), (3001, 130), (4100, 17)])
+def test_solve_few_right_hand_sides_wavefront(fm, ref, n, nrhs):
+    """dgetrs with nrhs <= 256 and n > 128 runs the single-launch wavefront triangular solves (one CTA per 128-row block,
+    x_k handed from CTA to CTA through release/acquire flags): partial last blocks, partial column chunks, idle warps."""
+    rng = np.random.default_rng(n + nrhs)
+    a = np.asfortranarray(rng.standard_normal((n, n)))
+    b = np.asfortranarray(rng.standard_normal((n, nrhs)))
+    x = fm.mldivide(up(fm, a), up(fm, b)).to_numpy()
+    r = np.abs(a @ x - b).sum(axis=0).max() / (np.abs(a).sum(axis=0).max() * np.abs(x).sum(axis=0).max())
+    assert r <= tol(n), (n, nrhs)
+    assert normwise_rel_err(x, ref.mldivide(a, b)) <= tol(n) * 50, (n, nrhs)
+
+
+@pytest.mark.gpu
+def test_getrs_wavefront_unaligned_view_and_repeat(fm, ref):
+    """B as an 8-byte-aligned view with an odd leading dimension (scalar load/store path), solved twice with the same factors
+    (the flag epoch must separate the launches)."""
+    lib = fm.load()
+    n, nrhs = 700, 50
+    rng = np.random.default_rng(4)
+    a = np.asfortranarray(rng.standard_normal((n, n)))
+    lu = up(fm, a)
+    piv, info = fm.flomat_lu_bang(lu)
+    assert info == 0
+    for rep in range(3):
+        b = np.asfortranarray(rng.standard_normal((n + 3, nrhs + 2)))
+        big = up(fm, b)
+        view = big.sub(1, 1, n, nrhs)  # odd row offset: 8-byte aligned, ld = n + 3 (odd)
+        assert lib.fm_getrs(n, nrhs, lu.a, lu.lda, piv.ptr, view.a, view.lda) == 0
+        got = big.to_numpy()
+        want = np.linalg.solve(a, b[1:n + 1, 1:nrhs + 1])
+        assert normwise_rel_err(got[1:n + 1, 1:nrhs + 1], want) <= tol(n) * 50
+        untouched = np.ones_like(b, dtype=bool)
+        untouched[1:n + 1, 1:nrhs + 1] = False
+        assert np.array_equal(got[untouched], b[untouched])  # nothing outside the view was written
