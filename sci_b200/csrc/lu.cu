@@ -47,6 +47,15 @@ __device__ long long g_prof[32];
 #define PROF_T(var) do {} while (0)
 #define PROF_ADD(slot, t0, t1) do {} while (0)
 #endif
+#ifdef FM_LU_PROF  // wavefront solve: thread 0 of the chunk-0 CTAs, critical section only (last off-diagonal tile + diagonal tile)
+#define PROFW_DECL long long pw_last = 0; bool pw_on = false
+#define PROFW(slot) do { if (tid == 0 && chunk == 0) { const long long now_ = clock64(); if (pw_on) atomicAdd((unsigned long long *)&g_prof[slot], (unsigned long long)(now_ - pw_last)); pw_last = now_; } } while (0)
+#define PROFW_ON(c) do { pw_on = (c); } while (0)
+#else
+#define PROFW_DECL do {} while (0)
+#define PROFW(slot) do {} while (0)
+#define PROFW_ON(c) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t lsmem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
@@ -1085,30 +1094,37 @@ __global__ void __launch_bounds__(256, 2) trsm_leaf_cols_kernel(int nb, int ncol
             // x_bk^T = y_bk^T inv(T_kk)^T
             frag_b(Ts + blk_index(bk, bk) * TC_BLK, bf);
             const double a0 = wc[2 * bk][0], a1 = wc[2 * bk][1], a2 = wc[2 * bk + 1][0], a3 = wc[2 * bk + 1][1];
-#pragma unroll
-            for (int nt2 = 0; nt2 < 2; ++nt2) {
-                double c0 = 0.0, c1 = 0.0;
-                dmma884(c0, c1, a0, bf[nt2][0]);
-                dmma884(c0, c1, a1, bf[nt2][1]);
-                dmma884(c0, c1, a2, bf[nt2][2]);
-                dmma884(c0, c1, a3, bf[nt2][3]);
-                wc[2 * bk + nt2][0] = c0; wc[2 * bk + nt2][1] = c1;
+            {
+                double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // the two n-tiles interleaved
+                dmma884(c0, c1, a0, bf[0][0]); dmma884(d0, d1, a0, bf[1][0]);
+                dmma884(c0, c1, a1, bf[0][1]); dmma884(d0, d1, a1, bf[1][1]);
+                dmma884(c0, c1, a2, bf[0][2]); dmma884(d0, d1, a2, bf[1][2]);
+                dmma884(c0, c1, a3, bf[0][3]); dmma884(d0, d1, a3, bf[1][3]);
+                wc[2 * bk][0] = c0; wc[2 * bk][1] = c1; wc[2 * bk + 1][0] = d0; wc[2 * bk + 1][1] = d1;
             }
             const double n0 = -wc[2 * bk][0], n1 = -wc[2 * bk][1], n2 = -wc[2 * bk + 1][0], n3 = -wc[2 * bk + 1][1];
-            // y_bi^T -= x_bk^T T(bi, bk)^T for the block rows still to be solved (the next one to be solved first)
+            // y_bi^T -= x_bk^T T(bi, bk)^T for the block rows still to be solved (the next one to be solved first), two block
+            // rows = four accumulators at a time, slice-major, so that consecutive DMMAs never depend on each other
+            const double ng[4] = {n0, n1, n2, n3};
 #pragma unroll
-            for (int q = 1; q < 8; ++q) {
-                const int bi = UPPER ? bk - q : bk + q;
-                if (bi < 0 || bi > 7) continue;  // compile time after unrolling
-                if (bi >= nblk) continue;
-                frag_b(Ts + blk_index(bi, bk) * TC_BLK, bf);
+            for (int q = 1; q < 8; q += 2) {
+                double bf2[2][2][4];
 #pragma unroll
-                for (int nt2 = 0; nt2 < 2; ++nt2) {
-                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n0, bf[nt2][0]);
-                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n1, bf[nt2][1]);
-                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n2, bf[nt2][2]);
-                    dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], n3, bf[nt2][3]);
+                for (int j = 0; j < 2; ++j) {
+                    const int bi = UPPER ? bk - (q + j) : bk + (q + j);
+                    if (bi < 0 || bi > 7) continue;  // compile time after unrolling
+                    if (bi < nblk) frag_b(Ts + blk_index(bi, bk) * TC_BLK, bf2[j]);
                 }
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int bi = UPPER ? bk - (q + j) : bk + (q + j);
+                        if (bi < 0 || bi > 7) continue;
+                        if (bi >= nblk) continue;  // warp-uniform
+#pragma unroll
+                        for (int nt2 = 0; nt2 < 2; ++nt2) dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], ng[sl], bf2[j][nt2][sl]);
+                    }
             }
         }
 #pragma unroll
@@ -1143,10 +1159,11 @@ constexpr int TW_LD = 132;                 // column stride of a staged 128 x 64
 constexpr int TW_HALF = 64 * TW_LD;
 constexpr int TW_DLP = 24;                 // row stride of the inverted diagonal blocks (LDS.128, as TC_LP)
 constexpr int TW_SMEM = (3 * TW_HALF + 8 * 16 * TW_DLP) * (int)sizeof(double);
-template <bool UPPER>
-__global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, const double *__restrict__ T, long long ldt, double *B, long long ldb,
-                                                           int *flags, int epoch, int vec_ok) {
+template <bool UPPER, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols, const double *__restrict__ T, long long ldt, double *B, long long ldb,
+                                                           int *flags, int epoch, int vec_ok, int tvec_ok) {
     constexpr bool UNIT = !UPPER;
+    constexpr int THREADS = 32 * WPC, CW = 8 * WPC;  // CW right-hand sides per CTA: 8 per warp
     extern __shared__ double sm[];
     double *ring = sm;
     double *Dinv = sm + 3 * TW_HALF;  // Dinv[d * 16 * TW_DLP + i * TW_DLP + k] = inv(T_rr block d)(i, k)
@@ -1160,20 +1177,32 @@ __global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, con
         if (q < njobs) {
             const int i = q >> 1, k = i < nk ? (UPPER ? nblk - 1 - i : i) : r, h = UPPER ? 1 - (q & 1) : (q & 1);
             double *dst = ring + (q % 3) * TW_HALF;
-            const int cbase = k * 128 + 64 * h, row = tid & 127, gr = rbase + row;
+            const int cbase = k * 128 + 64 * h;
+            if (tvec_ok && rbase + 128 <= n && cbase + 64 <= n) {  // full, 16-byte aligned half tile: 16-byte copies
+                const int rp = tid & 63;
 #pragma unroll 8
-            for (int jj = 0; jj < 32; ++jj) {
-                const int col = (tid >> 7) + 2 * jj, gc = cbase + col;
-                const bool ok = gr < n && gc < n;
-                cp_async8(lsmem(dst + col * TW_LD + row), ok ? T + (long long)gc * ldt + gr : T, ok);
+                for (int jj = 0; jj < 64 * 64 / THREADS; ++jj) {
+                    const int col = (tid >> 6) + (THREADS / 64) * jj;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lsmem(dst + col * TW_LD + 2 * rp)),
+                                 "l"(T + (long long)(cbase + col) * ldt + rbase + 2 * rp) : "memory");
+                }
+            } else {  // edge tiles of a ragged n (zero fill) and unaligned triangles
+                const int row = tid & 127, gr = rbase + row;
+#pragma unroll 8
+                for (int jj = 0; jj < 64 * 128 / THREADS; ++jj) {
+                    const int col = (tid >> 7) + (THREADS / 128) * jj, gc = cbase + col;
+                    const bool ok = gr < n && gc < n;
+                    cp_async8(lsmem(dst + col * TW_LD + row), ok ? T + (long long)gc * ldt + gr : T, ok);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto landed = [&](int) { asm volatile("cp.async.wait_group 1;" ::: "memory"); };  // this thread's part of half tile q is in shared memory
     issue(0);
     issue(1);
     // ---- the diagonal 16 x 16 blocks of T_rr, inverted (identity beyond n) ----
-    for (int e = tid; e < 8 * 256; e += 256) {
+    for (int e = tid; e < 8 * 256; e += THREADS) {
         const int d = e >> 8, i = e & 15, k = (e >> 4) & 15, gi = rbase + 16 * d + i, gk = rbase + 16 * d + k;
         Dinv[d * 16 * TW_DLP + i * TW_DLP + k] = (gi < n && gk < n) ? T[(long long)gk * ldt + gi] : 0.0;
     }
@@ -1209,8 +1238,8 @@ __global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, con
         for (int i = 0; i < 16; ++i) el(i, j) = z[i];
     }
     // ---- this warp's 8 right-hand sides of block row r ----
-    const int col = chunk * 64 + 8 * w + g;
-    const bool have = chunk * 64 + 8 * w < ncols;  // warp-uniform; idle warps still stage tiles and meet the barriers
+    const int col = chunk * CW + 8 * w + g;
+    const bool have = chunk * CW + 8 * w < ncols;  // warp-uniform; idle warps still stage tiles and meet the barriers
     auto ld2 = [&](int row, double &v0, double &v1) {  // rows row, row+1 of this lane's column, bypassing L1 (x_k comes from another SM)
         v0 = v1 = 0.0;
         if (col < ncols) {
@@ -1230,72 +1259,102 @@ __global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, con
         wc[nt][0] = wc[nt][1] = 0.0;
         if (have) ld2(rbase + 8 * nt + 2 * t, wc[nt][0], wc[nt][1]);
     }
-    for (int q = 0; q < njobs; ++q) {
-        const int i = q >> 1, h = UPPER ? 1 - (q & 1) : (q & 1);
-        const bool diag = i >= nk;
+    PROFW_DECL;
+    for (int i = 0; i <= nk; ++i) {
+        const bool diag = i == nk;
         const int k = diag ? r : (UPPER ? nblk - 1 - i : i);
-        if (!diag && (q & 1) == 0 && tid == 0) {  // x_k published?
-            const int *f = flags + k * cchunks + chunk;
-            int v, spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            } while (v != epoch && ++spins < (1 << 21));
-        }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();   // half tile q has landed for every thread; everyone is done with half tile q-1; x_k is visible
-        issue(q + 2);      // into the buffer of half tile q-1
-        const double *buf = ring + (q % 3) * TW_HALF;
-        if (!have) continue;
-        if (!diag) {
-            double xf[8][2];
+        double xf[16][2];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) ld2(k * 128 + 64 * h + 8 * nt + 2 * t, xf[nt][0], xf[nt][1]);
+        for (int hh = 0; hh < 2; ++hh) {
+            const int q = 2 * i + hh, h = UPPER ? 1 - hh : hh;
+            landed(q);
+            __syncthreads();  // half tile q has landed for every thread; everyone is done with half tile q-1; x_k is visible
+            PROFW(diag ? 21 : 17);
+            issue(q + 2);  // into the buffer of half tile q-1; ahead of the flag wait: the tiles do not depend on the solution
+            PROFW(diag ? 22 : 18);
+            if (hh == 0 && !diag) {
+                if (tid == 0) {  // x_k published?
+                    const int *f = flags + k * cchunks + chunk;
+                    int v, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    } while (v != epoch && ++spins < (1 << 21));
+                }
+                PROFW_ON(false); PROFW(16); PROFW_ON(nk > 0 && i >= nk - 1);
+                __syncthreads();  // x_k is visible to every thread
+                if (have) {       // one L2 round trip for the whole x_k
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const double n0 = -xf[2 * kk][0], n1 = -xf[2 * kk][1], n2 = -xf[2 * kk + 1][0], n3 = -xf[2 * kk + 1][1];
-                const double *cb = buf + (16 * kk + 2 * t) * TW_LD + g;
+                    for (int nt = 0; nt < 16; ++nt) ld2(k * 128 + 8 * nt + 2 * t, xf[nt][0], xf[nt][1]);
+                }
+                PROFW(20);
+            }
+            const double *buf = ring + (q % 3) * TW_HALF;
+            if (!have) continue;
+            if (!diag) {
 #pragma unroll
-                for (int nt = 0; nt < 16; ++nt) {
-                    const double b0 = cb[8 * nt], b1 = cb[TW_LD + 8 * nt], b2 = cb[8 * TW_LD + 8 * nt], b3 = cb[9 * TW_LD + 8 * nt];
-                    dmma884(wc[nt][0], wc[nt][1], n0, b0);
-                    dmma884(wc[nt][0], wc[nt][1], n1, b1);
-                    dmma884(wc[nt][0], wc[nt][1], n2, b2);
-                    dmma884(wc[nt][0], wc[nt][1], n3, b3);
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int xn = 8 * h + 2 * kk;
+                    const double ng[4] = {-xf[xn][0], -xf[xn][1], -xf[xn + 1][0], -xf[xn + 1][1]};
+                    const double *cb = buf + (16 * kk + 2 * t) * TW_LD + g;
+                    // four accumulators at a time, slice-major: consecutive DMMAs never depend on each other
+#pragma unroll
+                    for (int nt0 = 0; nt0 < 16; nt0 += 4) {
+                        double bv[4][4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            bv[j][0] = cb[8 * (nt0 + j)]; bv[j][1] = cb[TW_LD + 8 * (nt0 + j)];
+                            bv[j][2] = cb[8 * TW_LD + 8 * (nt0 + j)]; bv[j][3] = cb[9 * TW_LD + 8 * (nt0 + j)];
+                        }
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dmma884(wc[nt0 + j][0], wc[nt0 + j][1], ng[sl], bv[j][sl]);
+                    }
+                }
+                PROFW(19);
+                continue;
+            }
+            // ---- diagonal tile: the four block steps whose columns are in this half ----
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int bk = 4 * h + (UPPER ? 3 - s4 : s4);
+                {
+                    const double *db = Dinv + bk * 16 * TW_DLP;
+                    const double a0 = wc[2 * bk][0], a1 = wc[2 * bk][1], a2 = wc[2 * bk + 1][0], a3 = wc[2 * bk + 1][1];
+                    const double2 lo0 = *reinterpret_cast<const double2 *>(db + g * TW_DLP + 2 * t);
+                    const double2 hi0 = *reinterpret_cast<const double2 *>(db + g * TW_DLP + 8 + 2 * t);
+                    const double2 lo1 = *reinterpret_cast<const double2 *>(db + (8 + g) * TW_DLP + 2 * t);
+                    const double2 hi1 = *reinterpret_cast<const double2 *>(db + (8 + g) * TW_DLP + 8 + 2 * t);
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                    dmma884(c0, c1, a0, lo0.x); dmma884(d0, d1, a0, lo1.x);
+                    dmma884(c0, c1, a1, lo0.y); dmma884(d0, d1, a1, lo1.y);
+                    dmma884(c0, c1, a2, hi0.x); dmma884(d0, d1, a2, hi1.x);
+                    dmma884(c0, c1, a3, hi0.y); dmma884(d0, d1, a3, hi1.y);
+                    wc[2 * bk][0] = c0; wc[2 * bk][1] = c1; wc[2 * bk + 1][0] = d0; wc[2 * bk + 1][1] = d1;
+                }
+                const double ng[4] = {-wc[2 * bk][0], -wc[2 * bk][1], -wc[2 * bk + 1][0], -wc[2 * bk + 1][1]};
+                const double *cb = buf + (16 * (bk & 3) + 2 * t) * TW_LD + g;
+                // the block rows still to be solved, nearest first, four accumulators at a time
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    double bv[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int nt = UPPER ? 2 * bk - 1 - (4 * q4 + j) : 2 * bk + 2 + 4 * q4 + j;
+                        if (nt < 0 || nt > 15) continue;  // compile time
+                        bv[j][0] = cb[8 * nt]; bv[j][1] = cb[TW_LD + 8 * nt]; bv[j][2] = cb[8 * TW_LD + 8 * nt]; bv[j][3] = cb[9 * TW_LD + 8 * nt];
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int nt = UPPER ? 2 * bk - 1 - (4 * q4 + j) : 2 * bk + 2 + 4 * q4 + j;
+                            if (nt < 0 || nt > 15) continue;
+                            dmma884(wc[nt][0], wc[nt][1], ng[sl], bv[j][sl]);
+                        }
                 }
             }
-            continue;
-        }
-        // ---- diagonal tile: the four block steps whose columns are in this half ----
-#pragma unroll
-        for (int s8 = 0; s8 < 8; ++s8) {
-            const int bk = UPPER ? 7 - s8 : s8;
-            if ((bk >> 2) != h) continue;  // warp-uniform
-            {
-                const double *db = Dinv + bk * 16 * TW_DLP;
-                const double a0 = wc[2 * bk][0], a1 = wc[2 * bk][1], a2 = wc[2 * bk + 1][0], a3 = wc[2 * bk + 1][1];
-#pragma unroll
-                for (int nt2 = 0; nt2 < 2; ++nt2) {
-                    const double2 lo = *reinterpret_cast<const double2 *>(db + (8 * nt2 + g) * TW_DLP + 2 * t);
-                    const double2 hi = *reinterpret_cast<const double2 *>(db + (8 * nt2 + g) * TW_DLP + 8 + 2 * t);
-                    double c0 = 0.0, c1 = 0.0;
-                    dmma884(c0, c1, a0, lo.x);
-                    dmma884(c0, c1, a1, lo.y);
-                    dmma884(c0, c1, a2, hi.x);
-                    dmma884(c0, c1, a3, hi.y);
-                    wc[2 * bk + nt2][0] = c0; wc[2 * bk + nt2][1] = c1;
-                }
-            }
-            const double n0 = -wc[2 * bk][0], n1 = -wc[2 * bk][1], n2 = -wc[2 * bk + 1][0], n3 = -wc[2 * bk + 1][1];
-            const double *cb = buf + (16 * (bk & 3) + 2 * t) * TW_LD + g;
-#pragma unroll
-            for (int nt = 0; nt < 16; ++nt) {
-                if (UPPER ? (nt >= 2 * bk) : (nt < 2 * bk + 2)) continue;  // compile time: only the block rows still to be solved
-                const double b0 = cb[8 * nt], b1 = cb[TW_LD + 8 * nt], b2 = cb[8 * TW_LD + 8 * nt], b3 = cb[9 * TW_LD + 8 * nt];
-                dmma884(wc[nt][0], wc[nt][1], n0, b0);
-                dmma884(wc[nt][0], wc[nt][1], n1, b1);
-                dmma884(wc[nt][0], wc[nt][1], n2, b2);
-                dmma884(wc[nt][0], wc[nt][1], n3, b3);
-            }
+            PROFW(23);
         }
     }
     // ---- publish x_r ----
@@ -1311,9 +1370,17 @@ __global__ void __launch_bounds__(256, 1) trsm_wave_kernel(int n, int ncols, con
             }
         }
     }
-    __threadfence();
+    PROFW(24);
     __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + r * cchunks + chunk), "r"(epoch) : "memory");
+    PROFW(25);
+    if (tid == 0) {  // the barrier orders every thread's stores before this thread's fence; the fence is cumulative
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + r * cchunks + chunk), "r"(epoch) : "memory");
+    }
+    PROFW(26);
+#ifdef FM_LU_PROF
+    if (tid == 0 && chunk == 0 && nk > 0) atomicAdd((unsigned long long *)&g_prof[27], 1ull);
+#endif
 }
 
 
@@ -1613,20 +1680,26 @@ int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, cons
 template <bool UPPER>
 int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bool *done) {
     *done = false;
-    static const bool off = getenv("FLOMAT_TRSM_NO_WAVE") != nullptr;  // developer switch
-    const int nblk = ceil_div(w, 128), cchunks = ceil_div(ncols, 64);
-    if (off || nblk < 2 || (long long)nblk * cchunks > ctx().sm_count || ctx().max_smem_optin < TW_SMEM) return FM_OK;
+    static const bool off = getenv("FLOMAT_TRSM_NO_WAVE") != nullptr;  // developer switches
+    static const bool wide_only = getenv("FLOMAT_TRSM_WAVE_WIDE") != nullptr;
+    const int nblk = ceil_div(w, 128);
+    if (off || nblk < 2 || ctx().max_smem_optin < TW_SMEM) return FM_OK;
+    // the step of the wavefront is bound by the DMMA issue rate of ONE warp per SM sub-partition: 4-warp CTAs (32 columns each)
+    // when that many CTAs still fit on the machine at once, 8-warp CTAs (64 columns) otherwise
+    const bool narrow = !wide_only && (long long)nblk * ceil_div(ncols, 32) <= ctx().sm_count;
+    const int cchunks = ceil_div(ncols, narrow ? 32 : 64);
     static int *d_flags = nullptr;
     static int epoch = 0;
     const int nflags = 4096;
-    if (nblk * cchunks > nflags) return FM_OK;
+    if ((long long)nblk * cchunks > ctx().sm_count || nblk * cchunks > nflags) return FM_OK;
     if (!d_flags) {
         FM_CUDA(cudaMalloc(&d_flags, nflags * sizeof(int)));
         FM_CUDA(cudaMemsetAsync(d_flags, 0, nflags * sizeof(int), ctx().stream));
     }
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
         attr = true;
     }
     if (++epoch == 0x7fffffff) {  // keep the published values distinct from anything an earlier launch left behind
@@ -1634,7 +1707,9 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
         epoch = 1;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15u) == 0 && (ldb % 2) == 0) ? 1 : 0;
-    trsm_wave_kernel<UPPER><<<dim3(nblk, cchunks), 256, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok);
+    const int tvec_ok = ((reinterpret_cast<uintptr_t>(T) & 15u) == 0 && (ldt % 2) == 0) ? 1 : 0;
+    if (narrow) trsm_wave_kernel<UPPER, 4><<<dim3(nblk, cchunks), 128, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok, tvec_ok);
+    else trsm_wave_kernel<UPPER, 8><<<dim3(nblk, cchunks), 256, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok, tvec_ok);
     FM_LAUNCH_CHECK();
     *done = true;
     return FM_OK;
