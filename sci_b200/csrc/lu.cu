@@ -1929,6 +1929,22 @@ __global__ void perm_forward_kernel(int n, const int32_t *ipiv, int32_t *idx) {
         if (p != i && p >= 0 && p < n) { const int t = idx[i]; idx[i] = idx[p]; idx[p] = t; }
     }
 }
+// same, with ipiv and idx staged in shared memory (8n bytes): the sequential replay runs at shared-memory instead of global-memory
+// latency (n = 8192: 0.78 ms -> < 0.1 ms)
+__global__ void __launch_bounds__(1024) perm_forward_smem_kernel(int n, const int32_t *ipiv, int32_t *idx) {
+    extern __shared__ int32_t pf[];
+    int32_t *sp = pf, *si = pf + n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { sp[i] = ipiv[i] - 1; si[i] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i) {
+            const int p = sp[i];
+            if (p != i && p >= 0 && p < n) { const int t = si[i]; si[i] = si[p]; si[p] = t; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = si[i];
+}
 // dst(:, idx[j]) := src(:, j)
 __global__ void __launch_bounds__(256) scatter_cols_kernel(int n, const double *__restrict__ src, long long lds, double *dst, long long ldd,
                                                             const int32_t *idx) {
@@ -1940,17 +1956,34 @@ __global__ void __launch_bounds__(256) scatter_cols_kernel(int n, const double *
 
 // Z := L^-1 for the unit lower triangle T (w x w), Z initialised to the identity: Z11 = L11^-1, Z22 = L22^-1 recursively,
 // Z21 = -L22^-1 (L21 Z11); Z12 stays zero.  Half the work of a forward sweep over a dense identity.
-int rinv_unit_lower(int w, const double *T, int ldt, double *Z, int ldz) {
-    if (w <= 0) return FM_OK;
-    if (w <= NB) return trsm_leaf<false>(w, w, T, ldt, 0, Z, ldz, 0, 1);
-    const int w1 = split(w), w2 = w - w1;
-    FM_TRY(rinv_unit_lower(w1, T, ldt, Z, ldz));
-    FM_TRY(rinv_unit_lower(w2, T + (size_t)w1 * ldt + w1, ldt, Z + (size_t)w1 * ldz + w1, ldz));
+// Z := inverse of the unit lower triangle at T (Z holds the identity on entry), bottom-up and level by level so that the many
+// small independent pieces of a level are ONE batched launch each: all 128 x 128 diagonal blocks first, then pairs of inverted
+// w x w blocks are merged ([Z11 0; Z21 Z22] with Z21 = -L22^-1 (L21 Z11)) for w = 128, 256, ... with batch = number of pairs and
+// item stride 2w (ld + 1).  A ragged last pair (n not a multiple of 2w) is one extra unbatched merge per level.
+// (The recursive top-down form ran the same pieces one after the other: 230 small GEMMs and 290 leaves for n = 8192.)
+int rinv_merge(int w1, int w2, const double *T, int ldt, double *Z, int ldz, long long stT, long long stZ, int batch) {
     GemmEpilogue ep;
     ep.alpha = -1.0;
     ep.beta = 0.0;
-    FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, w2, w1, w1, T + w1, ldt, 0, Z, ldz, 0, Z + w1, ldz, 0, 1, ep));  // Z21 = -L21 Z11
-    return rtrsm<false>(w2, w1, T + (size_t)w1 * ldt + w1, ldt, 0, Z + w1, ldz, 0, 1);                       // Z21 := L22^-1 Z21
+    FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, w2, w1, w1, T + w1, ldt, stT, Z, ldz, stZ, Z + w1, ldz, stZ, batch, ep));  // Z21 = -L21 Z11
+    return rtrsm<false>(w2, w1, T + (size_t)w1 * ldt + w1, ldt, stT, Z + w1, ldz, stZ, batch);                        // Z21 := L22^-1 Z21
+}
+int rinv_unit_lower(int n, const double *T, int ldt, double *Z, int ldz) {
+    if (n <= 0) return FM_OK;
+    const int nfull0 = n / NB, rem0 = n % NB;
+    if (nfull0 > 0) FM_TRY(trsm_leaf<false>(NB, NB, T, ldt, (long long)NB * (ldt + 1), Z, ldz, (long long)NB * (ldz + 1), nfull0));
+    if (rem0 > 0)
+        FM_TRY(trsm_leaf<false>(rem0, rem0, T + (size_t)nfull0 * NB * (ldt + 1), ldt, 0, Z + (size_t)nfull0 * NB * (ldz + 1), ldz, 0, 1));
+    for (long long w = NB; w < n; w *= 2) {
+        const int nblocks = (int)((n + w - 1) / w), npairs = nblocks / 2;  // pairs of level-w blocks whose second block exists
+        if (npairs == 0) break;
+        const long long last_second = std::min<long long>(w, n - (2LL * npairs - 1) * w);
+        const int nfull = last_second == w ? npairs : npairs - 1;
+        const long long stT = 2 * w * ((long long)ldt + 1), stZ = 2 * w * ((long long)ldz + 1);
+        if (nfull > 0) FM_TRY(rinv_merge((int)w, (int)w, T, ldt, Z, ldz, stT, stZ, nfull));
+        if (nfull < npairs) FM_TRY(rinv_merge((int)w, (int)last_second, T + (size_t)nfull * stT, ldt, Z + (size_t)nfull * stZ, ldz, 0, 0, 1));
+    }
+    return FM_OK;
 }
 
 }  // namespace
@@ -2009,7 +2042,16 @@ int k_getri(int n, double *a, int lda, const int32_t *ipiv) {
     if (rc == FM_OK) rc = rinv_unit_lower(n, a, lda, x, ldx);
     if (rc == FM_OK) rc = rtrsm<true>(n, n, a, lda, 0, x, ldx, 0, 1);
     if (rc == FM_OK) {
-        perm_forward_kernel<<<1, 32, 0, ctx().stream>>>(n, ipiv, idx);
+        if ((size_t)n * 8 <= (size_t)ctx().max_smem_optin) {
+            static bool attr = false;
+            if (!attr) {
+                cudaFuncSetAttribute(perm_forward_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx().max_smem_optin);
+                attr = true;
+            }
+            perm_forward_smem_kernel<<<1, 1024, (size_t)n * 8, ctx().stream>>>(n, ipiv, idx);
+        } else {
+            perm_forward_kernel<<<1, 32, 0, ctx().stream>>>(n, ipiv, idx);
+        }
         dim3 grid(ceil_div(n, 256) < 32 ? ceil_div(n, 256) : 32, n < 4096 ? n : 4096);
         scatter_cols_kernel<<<grid, 256, 0, ctx().stream>>>(n, x, ldx, a, lda, idx);
         rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "getri: launch failed");

@@ -341,7 +341,7 @@ def test_lu_tall_panel_fallback(fm, ref, monkeypatch):
     assert np.abs(a @ x - b).sum(axis=0).max() / (np.abs(a).sum(axis=0).max() * np.abs(x).sum(axis=0).max()) <= tol(600)
 
 
-@pytest.mark.parametrize("n", [130, 1500, 4096])
+@pytest.mark.parametrize("n", [130, 257, 384, 700, 1153, 1500, 4096])
 def test_inverse_parity_and_property(fm, ref, n):
     """`inv` = dgetrf + dgetri (flomat.rkt:1770-1781): structured L^-1, U sweep, column scatter.  Diagonally shifted random
     matrices keep cond(A) small, so ||A inv(A) - I||_1 and the distance to the oracle's inverse stay inside 64 n eps."""
@@ -352,6 +352,20 @@ def test_inverse_parity_and_property(fm, ref, n):
     assert fm.norm(R, 1) <= tol(n) * 8
     if n <= 1500:
         assert normwise_rel_err(Ai.to_numpy(), ref.inv(a)) <= tol(n) * 8
+
+
+@pytest.mark.parametrize("n", [200, 640, 1000, 2304])
+def test_inverse_general_matrix_with_interchanges(fm, ref, n):
+    """Unshifted random matrices: every panel interchanges rows, so the column scatter of dgetri and the ragged levels of the
+    batched structured inverse of L are exercised.  Residual ||A inv(A) - I||_1 <= 64 n eps ||A||_1 ||inv(A)||_1 (backward-stable bound)."""
+    a = rnd(300 + n, n, n)
+    A = up(fm, a)
+    Ai = fm.inv(A)
+    R = fm.minus(fm.times(A, Ai), fm.eye(n))
+    assert fm.norm(R, 1) <= tol(n) * fm.norm(A, 1) * fm.norm(Ai, 1)
+    if n <= 1000:
+        want = ref.inv(a)
+        assert normwise_rel_err(Ai.to_numpy(), want) <= tol(n) * np.linalg.cond(a, 1)
 
 
 # ---------------------------------------------------------------- expm
