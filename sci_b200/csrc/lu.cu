@@ -1278,7 +1278,8 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
                     int v, spins = 0;
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                    } while (v != epoch && ++spins < (1 << 21));
+                    } while (v != epoch && ++spins < (1 << 22));
+                    if (v != epoch) asm volatile("trap;");  // seconds without progress under a cooperative launch: fail loudly, never continue on stale data
                 }
                 PROFW_ON(false); PROFW(16); PROFW_ON(nk > 0 && i >= nk - 1);
                 __syncthreads();  // x_k is visible to every thread
@@ -1708,9 +1709,27 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15u) == 0 && (ldb % 2) == 0) ? 1 : 0;
     const int tvec_ok = ((reinterpret_cast<uintptr_t>(T) & 15u) == 0 && (ldt % 2) == 0) ? 1 : 0;
-    if (narrow) trsm_wave_kernel<UPPER, 4><<<dim3(nblk, cchunks), 128, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok, tvec_ok);
-    else trsm_wave_kernel<UPPER, 8><<<dim3(nblk, cchunks), 256, TW_SMEM, ctx().stream>>>(w, ncols, T, ldt, B, ldb, d_flags, epoch, vec_ok, tvec_ok);
-    FM_LAUNCH_CHECK();
+    // cooperative launch: the runtime guarantees that all CTAs are resident at once (the flag waits depend on it) or refuses the
+    // launch, in which case the caller falls back to the blocked sweep
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk, cchunks, 1);
+    cfg.blockDim = dim3(narrow ? 128 : 256, 1, 1);
+    cfg.dynamicSmemBytes = TW_SMEM;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const long long ldt_ll = ldt, ldb_ll = ldb;
+    cudaError_t e = narrow ? cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 4>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok)
+                           : cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 8>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();
+        return FM_OK;  // not done: blocked sweep
+    }
+    if (e != cudaSuccess) return set_error(FM_ERR_CUDA, "trsm_wave: launch failed: %s", cudaGetErrorString(e));
+    count_launch();
     *done = true;
     return FM_OK;
 }
