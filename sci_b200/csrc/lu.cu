@@ -1545,6 +1545,14 @@ int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
         if (m <= 512) return launch_panel<256, 2>(A, j0, m, pw, ipiv, sp, info, maps, 1);
         if (m <= 1024) return launch_panel<256, 4>(A, j0, m, pw, ipiv, sp, info, maps, 1);
     }
+    // 257..2048 rows: 128-row CTAs, i.e. twice the SMs of the 256-row shape.  The in-panel rank-16 update streams each CTA's rows of
+    // the remaining panel columns through L2 at the per-SM rate (~24 B/clk), so more SMs is more bandwidth: getrf n = 2048 3.54 -> 3.18 ms,
+    // n = 1024 1.69 -> 1.54 ms (64-row CTAs lose again: 1.59 ms).  FLOMAT_LU_NO_SMALL_WIDE restores the 256-row shape for A/B timing.
+    static const bool wide_small = getenv("FLOMAT_LU_NO_SMALL_WIDE") == nullptr;
+    if (wide_small && m <= 2048 && m > 256) {
+        if (csize_out) *csize_out = pow2_ctas(m, 128);
+        return launch_panel<128, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 128));
+    }
     if (m <= 4096) return launch_panel<256, 1>(A, j0, m, pw, ipiv, sp, info, maps, pow2_ctas(m, 256));
     if (m <= 8192) {
         static const char *variant = getenv("FLOMAT_LU_PANEL");  // developer switch for A/B timing: 512 | 128
