@@ -427,6 +427,25 @@ def test_expm_batched(fm, ref):
         assert normwise_rel_err(Ez, ref.expm(items[z])) <= tol(n), z
 
 
+@pytest.mark.parametrize("n,batch", [(33, 5), (129, 3), (256, 6)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_expm_batched_odd_sizes_and_modes(fm, ref, n, batch, mode):
+    """Odd n: the workspaces carry a padding row (ld = n + 1) that the flattened polynomial-term and scaling kernels walk over;
+    n = 256 is the item size of BASELINE config 5.  Both product orders, uniform and mixed squaring counts."""
+    rng = np.random.default_rng(7000 + n)
+    items = [np.asfortranarray(rng.standard_normal((n, n)) / math.sqrt(n) * (1.0 if z % 2 == 0 or n == 256 else 3.0)) for z in range(batch)]
+    stacked = np.concatenate([x.ravel(order="F") for x in items])
+    src = fm.Flomat.from_numpy(stacked.reshape(-1, 1))
+    dst = fm.Flomat.alloc(n * n * batch, 1)
+    s_out = np.zeros(batch)
+    fm.expm_batched(src.a, n, batch, dst.a, mode, s_out)
+    got = dst.to_numpy().ravel()
+    for z in range(batch):
+        assert s_out[z] == ref.scaling_exponent(items[z])
+        Ez = got[z * n * n:(z + 1) * n * n].reshape(n, n, order="F")
+        assert normwise_rel_err(Ez, ref.expm(items[z])) <= tol(n), z
+
+
 def test_expm_semigroup_property_large(fm):
     """exp(A)^2 == exp(2A) at n=1024 (size-independent property; no CPU expm needed)."""
     n = 1024
