@@ -112,6 +112,12 @@ int fm_free(void *dev);                   /* returns the block to the library's 
 int fm_trim_cache(void);                  /* cudaFree every cached block */
 int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n);   /* H2D, strided */
 int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n); /* D2H, strided */
+/* asynchronous variants on the library's transfer stream (no reference counterpart: the reference has no device).  An upload may
+ * overlap kernels queued before it and is visible to everything queued after it; a download waits for the work queued before it and
+ * overlaps what is queued after it -- the host buffer is valid after fm_transfer_sync() / fm_sync().  Use pinned host memory. */
+int fm_upload_async(double *dev, int ldd, const double *host, int ldh, int m, int n);
+int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, int n);
+int fm_transfer_sync(void);
 int fm_get(const double *dev, size_t index, double *out);  /* unsafe-ref on a device buffer (syncs) */
 int fm_set(double *dev, size_t index, double value);       /* unsafe-set! */
 int fm_upload_i32(int32_t *dev, const int32_t *host, size_t n);

@@ -54,6 +54,9 @@ SIGNATURES = {
     "fm_trim_cache": (c_int, []),
     "fm_upload": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
     "fm_download": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
+    "fm_upload_async": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
+    "fm_download_async": (c_int, [_DP, c_int, _DP, c_int, c_int, c_int]),
+    "fm_transfer_sync": (c_int, []),
     "fm_get": (c_int, [_DP, c_size_t, POINTER(c_double)]),
     "fm_set": (c_int, [_DP, c_size_t, c_double]),
     "fm_upload_i32": (c_int, [_IP, _IP, c_size_t]),

@@ -131,7 +131,12 @@ int fm_set_stream(void *s) {
     g_ctx.stream = static_cast<cudaStream_t>(s);
     return FM_OK;
 }
-int fm_sync(void) { FM_TRY(ensure_init()); FM_CUDA(cudaStreamSynchronize(g_ctx.stream)); return FM_OK; }
+int fm_transfer_sync(void);
+int fm_sync(void) {
+    FM_TRY(ensure_init());
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return fm_transfer_sync();
+}
 const char *fm_last_error(void) { return g_err; }
 const char *fm_version(void) { return "libflomat_cuda 0.1 (sm_100a)"; }
 uint64_t fm_kernel_launches(void) { return g_ctx.launches; }
@@ -142,9 +147,22 @@ uint64_t fm_kernel_launches(void) { return g_ctx.launches; }
 // are kept in an exact-size cache and handed out again; reuse is safe without a sync because all work of the library is
 // ordered on one stream.  FLOMAT_CUDA_CACHE_MB bounds the cache (default 64 GiB); fm_trim_cache() empties it.
 namespace {
+// Asynchronous host<->device transfers run on their own stream so that an upload can overlap the kernels queued before it and a
+// download the kernels queued after it (fm_upload_async / fm_download_async / fm_transfer_sync).
+struct Xfer {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t last = nullptr, tmp = nullptr;
+    bool dirty = false;  // transfers issued since the last fm_transfer_sync
+};
+Xfer g_xfer;
+struct Block {
+    size_t bytes = 0;
+    cudaEvent_t freed = nullptr;  // recorded on the compute stream when the block was last given back (only once transfers are in use)
+    bool fresh = true;            // straight from cudaMalloc: no queued work can refer to it
+};
 struct BlockCache {
-    std::multimap<size_t, void *> free_blocks;
-    std::unordered_map<void *, size_t> live;
+    std::multimap<size_t, std::pair<void *, Block>> free_blocks;
+    std::unordered_map<void *, Block> live;
     size_t cached_bytes = 0;
     size_t limit() {
         static size_t lim = [] {
@@ -156,12 +174,30 @@ struct BlockCache {
     void trim() {
         if (free_blocks.empty()) return;
         cudaStreamSynchronize(g_ctx.stream);
-        for (auto &kv : free_blocks) cudaFree(kv.second);
+        if (g_xfer.stream) cudaStreamSynchronize(g_xfer.stream);
+        for (auto &kv : free_blocks) {
+            if (kv.second.second.freed) cudaEventDestroy(kv.second.second.freed);
+            cudaFree(kv.second.first);
+        }
         free_blocks.clear();
         cached_bytes = 0;
     }
+    Block *find(const void *p) {  // the live block containing p (views point into the middle of a block)
+        auto it = live.find(const_cast<void *>(p));
+        if (it != live.end()) return &it->second;
+        for (auto &kv : live)
+            if (p >= kv.first && p < static_cast<const char *>(kv.first) + kv.second.bytes) return &kv.second;
+        return nullptr;
+    }
 };
 BlockCache g_cache;
+int xfer_init() {
+    if (g_xfer.stream) return FM_OK;
+    FM_CUDA(cudaStreamCreateWithFlags(&g_xfer.stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaEventCreateWithFlags(&g_xfer.last, cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&g_xfer.tmp, cudaEventDisableTiming));
+    return FM_OK;
+}
 }  // namespace
 
 void *fm_alloc_bytes(size_t bytes) {
@@ -170,10 +206,12 @@ void *fm_alloc_bytes(size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;
     auto it = g_cache.free_blocks.find(bytes);
     if (it != g_cache.free_blocks.end()) {
-        void *p = it->second;
+        void *p = it->second.first;
+        Block blk = it->second.second;
         g_cache.free_blocks.erase(it);
         g_cache.cached_bytes -= bytes;
-        g_cache.live[p] = bytes;
+        blk.fresh = false;
+        g_cache.live[p] = blk;
         return p;
     }
     void *p = nullptr;
@@ -186,7 +224,9 @@ void *fm_alloc_bytes(size_t bytes) {
             return nullptr;
         }
     }
-    g_cache.live[p] = bytes;
+    Block blk;
+    blk.bytes = bytes;
+    g_cache.live[p] = blk;
     return p;
 }
 double *fm_alloc(int m, int n) {
@@ -200,14 +240,22 @@ int fm_free(void *dev) {
         FM_CUDA(cudaFree(dev));
         return FM_OK;
     }
-    const size_t bytes = it->second;
+    Block blk = it->second;
     g_cache.live.erase(it);
-    if (g_cache.cached_bytes + bytes > g_cache.limit()) {
+    if (g_xfer.stream) {
+        // a transfer may still be reading or writing the block: whatever reuses it on the compute stream comes after the transfers
+        if (g_xfer.dirty) FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.last, 0));
+        // and a later asynchronous upload into the recycled block must wait for the kernels queued up to now
+        if (!blk.freed) FM_CUDA(cudaEventCreateWithFlags(&blk.freed, cudaEventDisableTiming));
+        FM_CUDA(cudaEventRecord(blk.freed, g_ctx.stream));
+    }
+    if (g_cache.cached_bytes + blk.bytes > g_cache.limit()) {
+        if (blk.freed) cudaEventDestroy(blk.freed);
         FM_CUDA(cudaFree(dev));
         return FM_OK;
     }
-    g_cache.free_blocks.emplace(bytes, dev);
-    g_cache.cached_bytes += bytes;
+    g_cache.free_blocks.emplace(blk.bytes, std::make_pair(dev, blk));
+    g_cache.cached_bytes += blk.bytes;
     return FM_OK;
 }
 int fm_trim_cache(void) {
@@ -228,6 +276,47 @@ int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n)
     if (m == 0 || n == 0) return FM_OK;
     FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
     FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return FM_OK;
+}
+// Asynchronous transfers on the library's transfer stream.  Upload: the copy may run while kernels queued BEFORE the call are still
+// executing (the destination must not be in use by them, other than through the allocator's recycling, which is tracked); everything
+// queued on the compute stream AFTER the call sees the data.  Download: waits for the work queued before the call, then runs beside
+// whatever is queued after it; the host buffer is valid after fm_transfer_sync (or fm_sync).  Pinned host memory is needed for a
+// real overlap; pageable memory works but serialises inside the driver.
+int fm_upload_async(double *dev, int ldd, const double *host, int ldh, int m, int n) {
+    FM_TRY(ensure_init());
+    if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_upload_async: bad dimensions");
+    if (m == 0 || n == 0) return FM_OK;
+    FM_TRY(xfer_init());
+    Block *blk = g_cache.find(dev);
+    if (blk && blk->freed) {
+        FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, blk->freed, 0));
+    } else if (!blk || !blk->fresh) {  // unknown history: behind everything queued so far
+        FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
+        FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
+    }
+    FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ldd * 8, host, (size_t)ldh * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, g_xfer.stream));
+    FM_CUDA(cudaEventRecord(g_xfer.last, g_xfer.stream));
+    FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.last, 0));
+    g_xfer.dirty = true;
+    return FM_OK;
+}
+int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, int n) {
+    FM_TRY(ensure_init());
+    if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download_async: bad dimensions");
+    if (m == 0 || n == 0) return FM_OK;
+    FM_TRY(xfer_init());
+    FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
+    FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
+    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_xfer.stream));
+    FM_CUDA(cudaEventRecord(g_xfer.last, g_xfer.stream));
+    g_xfer.dirty = true;
+    return FM_OK;
+}
+int fm_transfer_sync(void) {
+    FM_TRY(ensure_init());
+    if (g_xfer.stream) FM_CUDA(cudaStreamSynchronize(g_xfer.stream));
+    g_xfer.dirty = false;
     return FM_OK;
 }
 int fm_get(const double *dev, size_t index, double *out) {

@@ -53,6 +53,16 @@ class _Buffer:
             pass
 
 
+def _host_layout_ok(h, m: int, n: int) -> bool:
+    """A host array the async transfers can use in place: float64, either column-major with the matrix's shape or a flat
+    contiguous buffer of m*n elements holding the column-major bytes."""
+    if not isinstance(h, np.ndarray) or h.dtype != np.float64:
+        return False
+    if h.ndim == 2 and h.shape == (m, n) and h.flags.f_contiguous:
+        return True
+    return h.ndim == 1 and h.size == m * n and h.flags.c_contiguous
+
+
 class Flomat:
     """`(struct flomat (m n a lda))`: m rows, n columns, device address `a`, leading dimension lda (column-major)."""
 
@@ -89,6 +99,25 @@ class Flomat:
         if h.size:
             check(_L().fm_download(h.ctypes.data, max(self.m, 1), self.a, self.lda, self.m, self.n), "fm_download")
         return h
+
+    # ---- asynchronous transfers (library transfer stream): for pinned host arrays that outlive the transfer ----------
+    def upload_async(self, h: np.ndarray) -> "Flomat":
+        """Start copying the column-major host array `h` (m x n float64, pinned for a real overlap) into this matrix.  The copy
+        may overlap kernels queued before the call; everything queued after it sees the data.  `h` must stay alive and
+        unchanged until transfer_sync() / sync()."""
+        if not _host_layout_ok(h, self.m, self.n):
+            raise ValueError("upload_async: expected a column-major float64 array of the matrix's shape (or its flat column-major bytes)")
+        if h.size:
+            check(_L().fm_upload_async(self.a, self.lda, h.ctypes.data, max(self.m, 1), self.m, self.n), "fm_upload_async")
+        return self
+
+    def download_async(self, h: np.ndarray) -> None:
+        """Start copying this matrix into the column-major host array `h` once the work queued so far is done; runs beside
+        whatever is queued afterwards.  `h` is valid after transfer_sync() / sync(); keep this matrix alive until then."""
+        if not _host_layout_ok(h, self.m, self.n) or not h.flags.writeable:
+            raise ValueError("download_async: expected a writable column-major float64 array of the matrix's shape (or a flat buffer of m*n)")
+        if h.size:
+            check(_L().fm_download_async(h.ctypes.data, max(self.m, 1), self.a, self.lda, self.m, self.n), "fm_download_async")
 
     # ---- views (shared-submatrix!, flomat.rkt:295-300): pointer arithmetic only -----------------------
     def sub(self, i: int, j: int, m: int, n: int) -> "Flomat":
@@ -668,3 +697,8 @@ def expm_batched(a_ptr: int, n: int, batch: int, out_ptr: int, mode: int = EXPM_
 
 def sync() -> None:
     check(_L().fm_sync(), "fm_sync")
+
+
+def transfer_sync() -> None:
+    """Wait for the asynchronous uploads / downloads issued so far (Flomat.upload_async / download_async)."""
+    check(_L().fm_transfer_sync(), "fm_transfer_sync")
