@@ -1701,9 +1701,12 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     static int epoch = 0;
     const int nflags = 4096;
     if ((long long)nblk * cchunks > ctx().sm_count || nblk * cchunks > nflags) return FM_OK;
-    if (!d_flags) {
+    static int flags_device = -1;
+    if (!d_flags || flags_device != ctx().device) {  // (the flags of a previously used device are left to that context)
         FM_CUDA(cudaMalloc(&d_flags, nflags * sizeof(int)));
         FM_CUDA(cudaMemsetAsync(d_flags, 0, nflags * sizeof(int), ctx().stream));
+        flags_device = ctx().device;
+        epoch = 0;
     }
     static bool attr = false;
     if (!attr) {
