@@ -1159,11 +1159,14 @@ constexpr int TW_LD = 132;                 // column stride of a staged 128 x 64
 constexpr int TW_HALF = 64 * TW_LD;
 constexpr int TW_DLP = 24;                 // row stride of the inverted diagonal blocks (LDS.128, as TC_LP)
 constexpr int TW_SMEM = (3 * TW_HALF + 8 * 16 * TW_DLP) * (int)sizeof(double);
-template <bool UPPER, int WPC>
-__global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols, const double *__restrict__ T, long long ldt, double *B, long long ldb,
+template <bool UPPER, int WPC, bool PAIR>
+__global__ void __launch_bounds__(32 * WPC * (PAIR ? 2 : 1), 1) trsm_wave_kernel(int n, int ncols, const double *__restrict__ T, long long ldt, double *B, long long ldb,
                                                            int *flags, int epoch, int vec_ok, int tvec_ok) {
     constexpr bool UNIT = !UPPER;
-    constexpr int THREADS = 32 * WPC, CW = 8 * WPC;  // CW right-hand sides per CTA: 8 per warp
+    // CW right-hand sides per CTA: 8 per owner warp.  PAIR: every owner warp w has a helper warp w + WPC on the same sub-partition that
+    // takes rows 64..127 of the off-diagonal updates (its own running sum, handed over once before the diagonal tile): one warp per
+    // sub-partition issues a DMMA every ~26 cycles (4-deep dependent chains), two interleave to the 16-cycle rate of the pipe.
+    constexpr int THREADS = 32 * WPC * (PAIR ? 2 : 1), CW = 8 * WPC;
     extern __shared__ double sm[];
     double *ring = sm;
     double *Dinv = sm + 3 * TW_HALF;  // Dinv[d * 16 * TW_DLP + i * TW_DLP + k] = inv(T_rr block d)(i, k)
@@ -1238,8 +1241,10 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
         for (int i = 0; i < 16; ++i) el(i, j) = z[i];
     }
     // ---- this warp's 8 right-hand sides of block row r ----
-    const int col = chunk * CW + 8 * w + g;
-    const bool have = chunk * CW + 8 * w < ncols;  // warp-uniform; idle warps still stage tiles and meet the barriers
+    const bool helper = PAIR && w >= WPC;
+    const int cw = helper ? w - WPC : w;
+    const int col = chunk * CW + 8 * cw + g;
+    const bool have = chunk * CW + 8 * cw < ncols;  // warp-uniform; idle warps still stage tiles and meet the barriers
     auto ld2 = [&](int row, double &v0, double &v1) {  // rows row, row+1 of this lane's column, bypassing L1 (x_k comes from another SM)
         v0 = v1 = 0.0;
         if (col < ncols) {
@@ -1257,7 +1262,7 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) {
         wc[nt][0] = wc[nt][1] = 0.0;
-        if (have) ld2(rbase + 8 * nt + 2 * t, wc[nt][0], wc[nt][1]);
+        if (have && !helper) ld2(rbase + 8 * nt + 2 * t, wc[nt][0], wc[nt][1]);  // a helper starts from zero: wc[8..15] is its running sum
     }
     PROFW_DECL;
     for (int i = 0; i <= nk; ++i) {
@@ -1290,7 +1295,23 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
                 PROFW(20);
             }
             const double *buf = ring + (q % 3) * TW_HALF;
-            if (!have) continue;
+            if (PAIR && diag && hh == 0 && nk > 0) {
+                // hand-over of the helpers' sums through the ring slot of half tile q-1 (free: nothing is staged after the diagonal tile)
+                double *xch = ring + ((q + 2) % 3) * TW_HALF + (cw * 32 + lane) * 16;
+                if (helper && have) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2 *>(xch + 2 * nt) = make_double2(wc[8 + nt][0], wc[8 + nt][1]);
+                }
+                __syncthreads();
+                if (!helper && have) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const double2 hv = *reinterpret_cast<const double2 *>(xch + 2 * nt);
+                        wc[8 + nt][0] += hv.x; wc[8 + nt][1] += hv.y;
+                    }
+                }
+            }
+            if (!have || (helper && diag)) continue;
             if (!diag) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
@@ -1300,6 +1321,7 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
                     // four accumulators at a time, slice-major: consecutive DMMAs never depend on each other
 #pragma unroll
                     for (int nt0 = 0; nt0 < 16; nt0 += 4) {
+                        if (PAIR && (helper ? nt0 < 8 : nt0 >= 8)) continue;  // warp-uniform: owner rows 0..63, helper rows 64..127
                         double bv[4][4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -1359,7 +1381,7 @@ __global__ void __launch_bounds__(32 * WPC, 1) trsm_wave_kernel(int n, int ncols
         }
     }
     // ---- publish x_r ----
-    if (have && col < ncols) {
+    if (have && !helper && col < ncols) {
 #pragma unroll
         for (int nt = 0; nt < 16; ++nt) {
             const int row = rbase + 8 * nt + 2 * t;
@@ -1693,8 +1715,9 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     static const bool wide_only = getenv("FLOMAT_TRSM_WAVE_WIDE") != nullptr;
     const int nblk = ceil_div(w, 128);
     if (off || nblk < 2 || ctx().max_smem_optin < TW_SMEM) return FM_OK;
-    // the step of the wavefront is bound by the DMMA issue rate of ONE warp per SM sub-partition: 4-warp CTAs (32 columns each)
-    // when that many CTAs still fit on the machine at once, 8-warp CTAs (64 columns) otherwise
+    // 32-column CTAs (four owner warps + four helper warps) when that many CTAs still fit on the machine at once, 64-column CTAs
+    // (eight unpaired warps) otherwise
+    static const bool no_pair = getenv("FLOMAT_TRSM_WAVE_NO_PAIR") != nullptr;  // developer switch: four unpaired warps
     const bool narrow = !wide_only && (long long)nblk * ceil_div(ncols, 32) <= ctx().sm_count;
     const int cchunks = ceil_div(ncols, narrow ? 32 : 64);
     static int *d_flags = nullptr;
@@ -1710,8 +1733,9 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     }
     static bool attr = false;
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
-        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+        FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
         attr = true;
     }
     if (++epoch == 0x7fffffff) {  // keep the published values distinct from anything an earlier launch left behind
@@ -1724,7 +1748,7 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     // launch, in which case the caller falls back to the blocked sweep
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nblk, cchunks, 1);
-    cfg.blockDim = dim3(narrow ? 128 : 256, 1, 1);
+    cfg.blockDim = dim3(narrow && no_pair ? 128 : 256, 1, 1);
     cfg.dynamicSmemBytes = TW_SMEM;
     cfg.stream = ctx().stream;
     cudaLaunchAttribute at[1];
@@ -1733,8 +1757,10 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     cfg.attrs = at;
     cfg.numAttrs = 1;
     const long long ldt_ll = ldt, ldb_ll = ldb;
-    cudaError_t e = narrow ? cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 4>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok)
-                           : cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 8>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok);
+    cudaError_t e;
+    if (narrow && !no_pair) e = cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 4, true>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok);
+    else if (narrow) e = cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 4, false>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok);
+    else e = cudaLaunchKernelEx(&cfg, trsm_wave_kernel<UPPER, 8, false>, w, ncols, T, ldt_ll, B, ldb_ll, d_flags, epoch, vec_ok, tvec_ok);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
         (void)cudaGetLastError();
         return FM_OK;  // not done: blocked sweep
