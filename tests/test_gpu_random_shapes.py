@@ -131,3 +131,34 @@ def test_getrs_wavefront_unaligned_view_and_repeat(fm, ref):
         untouched = np.ones_like(b, dtype=bool)
         untouched[1:n + 1, 1:nrhs + 1] = False
         assert np.array_equal(got[untouched], b[untouched])  # nothing outside the view was written
+
+
+@pytest.mark.gpu
+def test_wavefront_solve_is_repeatable(fm):
+    """The wavefront hands x_k from CTA to CTA through flags in global memory: 40 solves with the same factors must give the
+    same bits every time and a backward error inside the bound (a rare ordering bug would show up as a sporadic difference)."""
+    import torch
+
+    lib = fm.load()
+    n, nrhs = 1500, 130
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    a = torch.randn(n * n, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(n * nrhs, dtype=torch.float64, device="cuda", generator=g)
+    A, LU = fm.Flomat.alloc(n, n), fm.Flomat.alloc(n, n)
+    lib.fm_copy2d(A.a, n, a.data_ptr(), n, n, n)
+    lib.fm_copy2d(LU.a, n, a.data_ptr(), n, n, n)
+    piv = fm.Pivots(n)
+    assert lib.fm_getrf(n, n, LU.a, n, piv.ptr, piv.info_ptr) == 0
+    B, X = fm.Flomat.alloc(n, nrhs), fm.Flomat.alloc(n, nrhs)
+    lib.fm_copy2d(B.a, n, b.data_ptr(), n, n, nrhs)
+    first = None
+    for _ in range(40):
+        lib.fm_copy2d(X.a, n, b.data_ptr(), n, n, nrhs)
+        assert lib.fm_getrs(n, nrhs, LU.a, n, piv.ptr, X.a, n) == 0
+        x = X.to_numpy()
+        if first is None:
+            first = x
+            res = fm.norm(fm.minus(fm.times(A, X), B), 1) / (fm.norm(A, 1) * fm.norm(X, 1))
+            assert res <= tol(n)
+        else:
+            assert np.array_equal(first, x)
