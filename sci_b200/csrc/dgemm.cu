@@ -204,6 +204,17 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < MT; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        if (ep.beta != 0.0) {
+            // rank-k updates (short k): the epilogue's C loads would pay the full DRAM latency twice per tile (two batches of loads),
+            // a quarter of a k = 128 tile's time.  Pull this warp's WTM x WTN block of C into L2 now, one 128-byte line per lane and pass.
+            const double *cw = C + z * sc + ks * ep.kstride + (long long)(tn * BN + wn0) * ldc + tm * BM + wm0;
+#pragma unroll
+            for (int i = 0; i < Cfg::WTN * (Cfg::WTM / 16) / 32; ++i) {
+                const int line = lane + 32 * i, colw = line / (Cfg::WTM / 16), seg = line % (Cfg::WTM / 16);
+                if (tn * BN + wn0 + colw < N && tm * BM + wm0 + 16 * seg < M)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cw + (long long)colw * ldc + 16 * seg));
+            }
+        }
 
         for (int kt = kt_begin; kt < kt_end; ++kt) {
             mbar_wait(full_bar(stage), phase);
@@ -274,26 +285,32 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (ep.beta != 0.0) {
                 double *q = p0;
 #pragma unroll
-                for (int ni = 0; ni < NT; ++ni, q += 8 * ldc) {
-                    // the C loads of one n-tile are all in flight before the first dependent store; with load/use/store interleaved
+                for (int ni = 0; ni < NT; ni += 2, q += 16 * ldc) {
+                    // the C loads of two n-tiles are all in flight before the first dependent store; with load/use/store interleaved
                     // per element the stores fence the next load (possible aliasing) and every load pays a full memory latency
-                    double2 old[2][R];
+                    double2 old[2][2][R];
 #pragma unroll
-                    for (int x = 0; x < 2; ++x)
+                    for (int d = 0; d < 2; ++d)
 #pragma unroll
-                        for (int c = 0; c < R; ++c) old[x][c] = *reinterpret_cast<const double2 *>(q + (long long)(4 * x) * ldc + 2 * c * GPB);
+                        for (int x = 0; x < 2; ++x)
 #pragma unroll
-                    for (int x = 0; x < 2; ++x)
+                            for (int c = 0; c < R; ++c)
+                                if (ni + d < NT) old[d][x][c] = *reinterpret_cast<const double2 *>(q + (long long)(8 * d + 4 * x) * ldc + 2 * c * GPB);
 #pragma unroll
-                        for (int c = 0; c < R; ++c) {
-                            // the products depend on the loaded value, so ptxas cannot hoist all 64 of them above the loads (spills)
-                            double v0 = fma(ep.alpha, acc[2 * c][ni][x], ep.beta * old[x][c].x);
-                            double v1 = fma(ep.alpha, acc[2 * c + 1][ni][x], ep.beta * old[x][c].y);
-                            const int off = 8 * ni + 4 * x - 2 * c * GPB;
-                            if (dm == off) v0 += dgv;
-                            if (dm + 1 == off) v1 += dgv;
-                            *reinterpret_cast<double2 *>(q + (long long)(4 * x) * ldc + 2 * c * GPB) = make_double2(v0, v1);
-                        }
+                    for (int d = 0; d < 2; ++d)
+#pragma unroll
+                        for (int x = 0; x < 2; ++x)
+#pragma unroll
+                            for (int c = 0; c < R; ++c) {
+                                if (ni + d >= NT) continue;
+                                // the products depend on the loaded value, so ptxas cannot hoist all 64 of them above the loads (spills)
+                                double v0 = fma(ep.alpha, acc[2 * c][ni + d][x], ep.beta * old[d][x][c].x);
+                                double v1 = fma(ep.alpha, acc[2 * c + 1][ni + d][x], ep.beta * old[d][x][c].y);
+                                const int off = 8 * (ni + d) + 4 * x - 2 * c * GPB;
+                                if (dm == off) v0 += dgv;
+                                if (dm + 1 == off) v1 += dgv;
+                                *reinterpret_cast<double2 *>(q + (long long)(8 * d + 4 * x) * ldc + 2 * c * GPB) = make_double2(v0, v1);
+                            }
                 }
                 continue;
             }
