@@ -94,6 +94,7 @@ struct GemmEpilogue {
     const int32_t *active_until = nullptr;  // batched: item z is skipped when round >= active_until[z]
     int round = 0;
     int max_sms = 0;             // > 0: use at most this many SMs (look-ahead LU leaves room for the concurrent panel)
+    bool dynamic_tiles = false;  // hand tiles out through an atomic counter (full grid even with max_sms: CTAs that become resident late join in)
     bool pdl_dependent = false;  // launch as a programmatic dependent of the previous kernel in the stream (TMA path only)
 };
 int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,

@@ -74,6 +74,8 @@ struct EpiParams {
     int pdl_wait;   // launched as a programmatic dependent of the previous kernel: wait for it before exiting
     int ksplit;     // > 1: the k range is cut into ksplit slices, slice s of tile t writes its raw partial product to C + s * kstride
     long long kstride;
+    int *tile_counter;  // non-null: tiles are handed out dynamically (atomic counter) instead of round-robin; see the producer loop
+    int *counter_to_clear;  // a counter slot no kernel in flight uses: zeroed for a later launch
     int stagger_ns;  // two CTAs per SM: the second wave of CTAs starts this much later, so that one CTA's epilogue overlaps the other's main loop
 };
 
@@ -110,7 +112,7 @@ struct GemmCfg {
     static constexpr int B_BOX_BYTES = BN * 128;      // one box: BN rows (n) x 16 doubles (k)
     static constexpr int B_STAGE = (BK / 16) * B_BOX_BYTES;
     static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ids*/;
     static_assert(BK % 16 == 0 && WTM % 16 == 0 && WTN % 8 == 0 && R >= 1 && R <= 4, "tile shape");
 };
 
@@ -126,6 +128,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // full[s] then empty[s]
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tile_slot = bar_base + 16u * STAGES;  // dynamic scheduling: the tile whose FIRST k-step sits in stage s
+    const bool dynamic = ep.tile_counter != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -143,15 +147,31 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            // Dynamic scheduling (look-ahead LU: the trailing update shares the machine with the panel kernel, whose 16 SMs become
+            // free half-way): the producer draws the next tile from a global counter and tells the consumers through a per-stage
+            // slot written before the first k-step of the tile is armed; a negative id ends the consumers.  CTAs that only become
+            // resident when the panel exits simply join in.
+            if (dynamic && blockIdx.x == 0) *ep.counter_to_clear = 0;
+            int tile = dynamic ? atomicAdd(ep.tile_counter, 1) : (int)blockIdx.x;
+            for (;;) {
+                if (tile >= total_tiles) {
+                    if (dynamic) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        asm volatile("st.shared.s32 [%0], %1;" ::"r"(tile_slot + 4u * stage), "r"(-1) : "memory");
+                        mbar_arrive(full_bar(stage));
+                    }
+                    break;
+                }
+                const int next = dynamic ? 0 : tile + (int)gridDim.x;
                 int tm, tn, z;
                 const int ks = tile % ep.ksplit;
                 decode_tile(tile / ep.ksplit, tiles_m, tiles_n, tm, tn, z);
-                if (ep.active_until && ep.round >= ep.active_until[z]) continue;
+                if (ep.active_until && ep.round >= ep.active_until[z]) { tile = next; continue; }  // (never combined with dynamic)
                 const int m0 = tm * BM, n0 = tn * BN;
                 const int kt_per = (KT + ep.ksplit - 1) / ep.ksplit, kt_end = min(KT, (ks + 1) * kt_per);
                 for (int kt = ks * kt_per; kt < kt_end; ++kt) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (dynamic && kt == ks * kt_per) asm volatile("st.shared.s32 [%0], %1;" ::"r"(tile_slot + 4u * stage), "r"(tile) : "memory");
                     const uint32_t fb = full_bar(stage);
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -162,6 +182,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int kb = 0; kb < BK / 16; ++kb) tma_load_3d(sb + kb * Cfg::B_BOX_BYTES, &tmB, kt * BK + 16 * kb, n0, z, fb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                tile = dynamic ? atomicAdd(ep.tile_counter, 1) : next;
             }
         }
         return;
@@ -193,7 +214,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x;; tile += gridDim.x) {
+        if (dynamic) {  // the id of the tile whose first k-step is (or will be) in this stage
+            mbar_wait(full_bar(stage), phase);
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(tile_slot + 4u * stage) : "memory");
+            if (tile < 0) break;
+        } else if (tile >= total_tiles) break;
         int tm, tn, z;
         const int ks = tile % ep.ksplit;
         decode_tile(tile / ep.ksplit, tiles_m, tiles_n, tm, tn, z);
@@ -582,7 +608,7 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     const long long total = (long long)tiles_m * tiles_n * batch * ep.ksplit;
     if (total > 0x7fffffffLL) return set_error(FM_ERR_ARG, "dgemm: too many tiles");
     int sms = ctx().sm_count;
-    if (max_sms > 0 && max_sms < sms) sms = max_sms;
+    if (max_sms > 0 && max_sms < sms && !ep.tile_counter) sms = max_sms;  // dynamic tiles: full grid, late CTAs join when SMs free up
     const long long slots = (long long)sms * Cfg::CTAS_PER_SM;
     const int grid = (int)(total < slots ? total : slots);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(c) & 15u) == 0 && (ldc % 2) == 0 && (sc % 2) == 0) ? 1 : 0;
@@ -609,6 +635,7 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
 bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer switches for A/B timing
 bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
 bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
+bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
 int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
 
 }  // namespace
@@ -635,6 +662,8 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.round = epi.round;
     ep.zero = 0u;
     ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
+    ep.tile_counter = nullptr;
+    ep.counter_to_clear = nullptr;
     ep.ksplit = 1;
     ep.kstride = 0;
     ep.stagger_ns = ((epi.beta != 0.0 || g_stagger_all) && k <= 512) ? g_stagger_ns : 0;
@@ -665,6 +694,19 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
                 FM_LAUNCH_CHECK();
                 return FM_OK;
             }
+        }
+        if (epi.dynamic_tiles && g_dynamic_enabled && !epi.active_until) {
+            // a ring of counters: this launch draws from slot i and clears slot i + 32 for a launch far in the future (at most a
+            // couple of GEMMs are ever in flight at once)
+            static int *d_counters = nullptr;
+            static unsigned seq = 0;
+            if (!d_counters) {
+                FM_CUDA(cudaMalloc(&d_counters, 64 * sizeof(int)));
+                FM_CUDA(cudaMemsetAsync(d_counters, 0, 64 * sizeof(int), ctx().stream));
+            }
+            ep.tile_counter = d_counters + (seq % 64);
+            ep.counter_to_clear = d_counters + ((seq + 32) % 64);
+            ++seq;
         }
         if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
         return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);

@@ -1704,6 +1704,7 @@ int gemm_minus(int m, int n, int k, const double *a, int lda, long long sa, cons
     ep.beta = 1.0;
     ep.max_sms = max_sms;
     ep.pdl_dependent = pdl_dependent;
+    ep.dynamic_tiles = pdl_dependent;  // the trailing update that runs beside the panel kernel
     return k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep);
 }
 
