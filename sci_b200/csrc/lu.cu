@@ -151,7 +151,8 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     cluster_arrive();
     cluster_wait();
     const uint32_t tx_bytes = csize * PAY * 8;
-    const bool solo = (csize == 1);
+    // the lean batched configuration (MINB > 1) is only ever launched as a single CTA: the exchange code is compiled out
+    const bool solo = (MINB > 1) || (csize == 1);
     // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP, ...: remote addresses of s_cand[0][crank][lane] and
     // s_bar[0] there
     constexpr int NDEST = (MAXC + NWARP - 1) / NWARP;
