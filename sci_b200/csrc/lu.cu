@@ -1781,12 +1781,15 @@ template <bool UPPER>
 int rtrsm(int w, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
     if (w <= 0 || ncols <= 0) return FM_OK;
     if (w <= NB) return trsm_leaf<UPPER>(w, ncols, T, ldt, st, B, ldb, sb, batch);
+    if (batch == 1) {
+        // one launch for the whole triangle whenever one CTA per (128-row block, 32- or 64-column chunk) fits on the machine at once:
+        // few right-hand sides at any n (dgetrs with nrhs <= 256 up to n = 18944), or as many columns as rows for n <= 1024 (the solve
+        // inside expm n = 512: 4 leaves + 3 GEMMs per triangle, ~110 us, become one ~50 us launch)
+        bool done = false;
+        FM_TRY(trsm_wave<UPPER>(w, ncols, T, ldt, B, ldb, &done));
+        if (done) return FM_OK;
+    }
     if (ncols <= 2 * NB) {
-        if (batch == 1) {  // one launch for the whole triangle when every block row fits on the machine at once
-            bool done = false;
-            FM_TRY(trsm_wave<UPPER>(w, ncols, T, ldt, B, ldb, &done));
-            if (done) return FM_OK;
-        }
         // few right-hand sides: a recursive split would leave GEMMs with a handful of tiles and a long inner dimension;
         // the right-looking sweep (rank-128 updates of everything still to be solved) exposes rows/128 tiles per update
         const int nblk = ceil_div(w, NB);
