@@ -237,13 +237,12 @@ def run_gpu(args):
 
     # ---- e2e: host buffers in, host buffers out, through the public API, every step ----
     def e2e_step():
-        # the copies a user of the API would overlap are overlapped: X goes up while `times` runs, C comes down while `expm` runs
-        # (library transfer stream); the inputs of `times` and the result of `expm` are on the critical path either way
-        a_, b_ = upload(hA), upload(hB)
+        # `times` on HOST operands through fm_dgemm_host (what cblas_dgemm does with the reference's host matrices): A goes up, then
+        # B and C move in column blocks beside the product.  X goes up behind B's blocks while `times` runs; the result of `expm`
+        # is on the critical path either way.
         x_ = fm.Flomat.alloc(n, n)
-        c_ = fm.flomat_times(a_, b_)
+        fm.times_host(hA.T, hB.T, hC.T, 1.0, 0.0, wait=False)
         x_.upload_async(hX.reshape(-1))
-        c_.download_async(hC.reshape(-1))
         e_ = fm.expm(x_, mode)
         fm._lib.check(lib.fm_download(hE.ctypes.data, n, e_.a, n, n, n), "fm_download")
         fm.transfer_sync()
@@ -265,7 +264,7 @@ def run_gpu(args):
     e2e_ms = float(te.item())
     e2e = {"value": world * flops_step / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 3 * n * n * 8,
            "d2h_bytes_per_step": 2 * n * n * 8, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "api": "Flomat upload (pinned host) -> flomat_times / expm -> download, per step; X upload and C download overlap the kernels (fm_upload_async / fm_download_async)"}
+           "api": "per step, pinned host buffers: times_host (fm_dgemm_host: A up, B/C in column blocks beside the product) -> X upload_async beside it -> expm -> download"}
 
     # ---- column-sharded times (BASELINE config 4): fused P2P all-gather epilogue when N > 1 ----
     colshard = None

@@ -146,6 +146,12 @@ int fm_norm(char type, int m, int n, const double *a, int lda, double *out);
 /* C := alpha*op(A)*op(B) + beta*C, all pointers device (flomat.rkt:877-896).  beta == 0 never reads C. */
 int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double *a, int lda, const double *b,
              int ldb, double beta, double *c, int ldc);
+/* C := alpha*A*B + beta*C (NN) with all three operands in HOST memory -- what the unmodified reference hands to cblas_dgemm
+ * (flomat.rkt:888).  A goes up once; B and C travel in column blocks so that the upload of block j+1, the product of block j and
+ * the download of block j-1 overlap.  cblas_dgemm takes this path for host operands with N >= 1024 and M*N*K >= 2^30.
+ * async != 0: returns without waiting, C is valid after fm_transfer_sync() / fm_sync(); use pinned host memory for a real overlap. */
+int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
+                  double *c, int ldc, int async);
 /* as fm_dgemm (NN only) and then adds diag to C[i,i]: the `(plus (.* c I) (times A P))` step of mpoly, expm.rkt:176 */
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
                   double *c, int ldc, double diag);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "fm_larnv": (c_int, [c_int, _IP, c_longlong, _DP]),
     "fm_potrf": (c_int, [c_char, c_int, _DP, c_int, _IP]),
     "fm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
+    "fm_dgemm_host": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_int]),
     "fm_dgemm_diag": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_double]),
     "fm_dgemm_batched": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_double, _DP, c_int,
                                  c_longlong, c_double, c_int]),

@@ -101,12 +101,12 @@ struct Staged {
         }
         owned = true;
         if (copy_in)
-            FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ld * 8, host, (size_t)ldh * 8, (size_t)rows * 8, cols, cudaMemcpyHostToDevice, g_ctx.stream));
+            FM_TRY(copy_h2d(dev, ld, host, ldh, rows, cols, g_ctx.stream));
         return FM_OK;
     }
     int out() {
         if (!owned) return FM_OK;
-        FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ld * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+        FM_TRY(copy_d2h(host, ldh, dev, ld, m, n, g_ctx.stream));
         return FM_OK;
     }
     ~Staged() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); fm_free(dev); } }
@@ -151,6 +151,7 @@ namespace {
 // download the kernels queued after it (fm_upload_async / fm_download_async / fm_transfer_sync).
 struct Xfer {
     cudaStream_t stream = nullptr;
+    cudaStream_t down = nullptr;  // device->host chunks of fm_dgemm_host: a second copy engine beside the uploads on `stream`
     cudaEvent_t last = nullptr, tmp = nullptr;
     bool dirty = false;  // transfers issued since the last fm_transfer_sync
 };
@@ -175,6 +176,7 @@ struct BlockCache {
         if (free_blocks.empty()) return;
         cudaStreamSynchronize(g_ctx.stream);
         if (g_xfer.stream) cudaStreamSynchronize(g_xfer.stream);
+        if (g_xfer.down) cudaStreamSynchronize(g_xfer.down);
         for (auto &kv : free_blocks) {
             if (kv.second.second.freed) cudaEventDestroy(kv.second.second.freed);
             cudaFree(kv.second.first);
@@ -194,6 +196,7 @@ BlockCache g_cache;
 int xfer_init() {
     if (g_xfer.stream) return FM_OK;
     FM_CUDA(cudaStreamCreateWithFlags(&g_xfer.stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamCreateWithFlags(&g_xfer.down, cudaStreamNonBlocking));
     FM_CUDA(cudaEventCreateWithFlags(&g_xfer.last, cudaEventDisableTiming));
     FM_CUDA(cudaEventCreateWithFlags(&g_xfer.tmp, cudaEventDisableTiming));
     return FM_OK;
@@ -267,14 +270,13 @@ int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n) {
     FM_TRY(ensure_init());
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_upload: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
-    FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ldd * 8, host, (size_t)ldh * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, g_ctx.stream));
-    return FM_OK;
+    return copy_h2d(dev, ldd, host, ldh, m, n, g_ctx.stream);  // pageable host memory is staged by the library's own copy threads
 }
 int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n) {
     FM_TRY(ensure_init());
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
-    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, g_ctx.stream));
     FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return FM_OK;
 }
@@ -316,6 +318,7 @@ int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, 
 int fm_transfer_sync(void) {
     FM_TRY(ensure_init());
     if (g_xfer.stream) FM_CUDA(cudaStreamSynchronize(g_xfer.stream));
+    if (g_xfer.down) FM_CUDA(cudaStreamSynchronize(g_xfer.down));
     g_xfer.dirty = false;
     return FM_OK;
 }
@@ -375,6 +378,88 @@ int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const do
     ep.alpha = alpha;
     ep.beta = beta;
     return k_dgemm(transA, transB, m, n, k, a, lda, 0, b, ldb, 0, c, ldc, 0, 1, ep);
+}
+// C := alpha*A*B + beta*C with all three operands in HOST memory (what the unmodified reference passes to cblas_dgemm,
+// flomat.rkt:888): instead of upload / compute / download one after the other, B and C travel in column blocks -- A goes up once,
+// then block j of B is uploaded while the product of block j-1 runs and block j-2 of C comes down (uploads on the transfer stream,
+// downloads on a second one: both copy engines and the SMs are busy at once).  Block widths are whole numbers of 128-column tile
+// columns chosen so that a block's tiles fill complete waves of the persistent GEMM.  n = 8192 from pinned memory: upload + compute +
+// download 60 ms one after the other, ~44 ms pipelined.  async != 0: return without waiting; C is valid after fm_transfer_sync().
+int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta, double *c, int ldc,
+                  int async) {
+    FM_TRY(ensure_init());
+    if (m < 0 || n < 0 || k < 0) return set_error(FM_ERR_ARG, "fm_dgemm_host: negative dimension");
+    if (lda < (m > 1 ? m : 1) || ldb < (k > 1 ? k : 1) || ldc < (m > 1 ? m : 1)) return set_error(FM_ERR_ARG, "fm_dgemm_host: leading dimension too small");
+    if (m == 0 || n == 0) return FM_OK;
+    if (is_device_ptr(a) || is_device_ptr(b) || is_device_ptr(c)) return set_error(FM_ERR_ARG, "fm_dgemm_host: operands must be host memory (use fm_dgemm)");
+    FM_TRY(xfer_init());
+    const int ldda = m + (m & 1) < 2 ? 2 : m + (m & 1), lddb = k + (k & 1) < 2 ? 2 : k + (k & 1), lddc = ldda;
+    double *da = k > 0 ? static_cast<double *>(fm_alloc_bytes((size_t)ldda * k * 8)) : nullptr;
+    double *db = k > 0 ? static_cast<double *>(fm_alloc_bytes((size_t)lddb * n * 8)) : nullptr;
+    double *dc = static_cast<double *>(fm_alloc_bytes((size_t)lddc * n * 8));
+    int rc = FM_OK;
+    if ((k > 0 && (!da || !db)) || !dc) rc = FM_ERR_NOMEM;
+    // column blocks: about eight, each a whole number of tile columns whose tiles come close to complete waves
+    const int tile_rows = (m + 127) / 128, nblk = (n + 127) / 128, sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+    int per = 1;
+    {
+        const int lo = nblk / 8 > 1 ? nblk / 8 : 1, hi = nblk / 3 > lo ? nblk / 3 : lo;
+        double best = -1.0;
+        for (int cnd = lo; cnd <= hi; ++cnd) {
+            const long long tiles = (long long)cnd * tile_rows, waves = (tiles + sms - 1) / sms;
+            const double eff = (double)tiles / (double)(waves * sms);
+            if (eff > best + 1e-9) { best = eff; per = cnd; }
+        }
+    }
+    const int cw = per * 128, nchunks = (n + cw - 1) / cw;
+    static std::vector<cudaEvent_t> ev;  // [2j] block j uploaded, [2j+1] block j computed
+    while (rc == FM_OK && (int)ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: event creation failed");
+        else ev.push_back(e);
+    }
+    auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == FM_OK) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: %s", cudaGetErrorString(e)); };
+    if (rc == FM_OK) {
+        // the staging blocks may be recycled ones that kernels queued so far still use
+        chk(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
+        chk(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
+        if (k > 0 && rc == FM_OK) rc = copy_h2d(da, ldda, a, lda, m, k, g_xfer.stream);
+        for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
+            const int c0 = j * cw, w = n - c0 < cw ? n - c0 : cw;
+            if (k > 0) rc = copy_h2d(db + (size_t)c0 * lddb, lddb, b + (size_t)c0 * ldb, ldb, k, w, g_xfer.stream);
+            if (beta != 0.0 && rc == FM_OK) rc = copy_h2d(dc + (size_t)c0 * lddc, lddc, c + (size_t)c0 * ldc, ldc, m, w, g_xfer.stream);
+            chk(cudaEventRecord(ev[2 * j], g_xfer.stream));
+            chk(cudaStreamWaitEvent(g_ctx.stream, ev[2 * j], 0));
+            if (rc != FM_OK) break;
+            GemmEpilogue ep;
+            ep.alpha = alpha;
+            ep.beta = beta;
+            if (k > 0) rc = k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, w, k, da, ldda, 0, db + (size_t)c0 * lddb, lddb, 0, dc + (size_t)c0 * lddc, lddc, 0, 1, ep);
+            else if (beta == 0.0) rc = k_fill(dc + (size_t)c0 * lddc, lddc, m, w, 0.0);  // BLAS: k = 0 leaves C := beta*C (beta = 0: no read of C)
+            else rc = k_scal2d(m, w, beta, dc + (size_t)c0 * lddc, lddc);
+            if (rc == FM_OK) chk(cudaEventRecord(ev[2 * j + 1], g_ctx.stream));
+        }
+        // downloads are queued after every upload: a copy to pageable memory blocks the host until it has run
+        for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
+            const int c0 = j * cw, w = n - c0 < cw ? n - c0 : cw;
+            chk(cudaStreamWaitEvent(g_xfer.down, ev[2 * j + 1], 0));
+            if (rc == FM_OK) rc = copy_d2h(c + (size_t)c0 * ldc, ldc, dc + (size_t)c0 * lddc, lddc, m, w, g_xfer.down);
+        }
+        // whatever reuses the staging blocks (compute stream) comes after the last download
+        chk(cudaEventRecord(g_xfer.tmp, g_xfer.down));
+        chk(cudaStreamWaitEvent(g_ctx.stream, g_xfer.tmp, 0));
+        chk(cudaEventRecord(g_xfer.last, g_xfer.stream));
+        g_xfer.dirty = true;
+    }
+    if (rc != FM_OK || !async) {
+        cudaStreamSynchronize(g_xfer.stream);
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaStreamSynchronize(g_xfer.down);
+    }
+    if (da) fm_free(da);
+    if (db) fm_free(db);
+    if (dc) fm_free(dc);
+    return rc;
 }
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta, double *c, int ldc,
                   double diag) {
@@ -585,6 +670,13 @@ void cblas_dgemm(int order, int transA, int transB, int M, int N, int K, double 
     if (rc == FM_OK && order != FM_COL_MAJOR) rc = set_error(FM_ERR_ARG, "cblas_dgemm: only CblasColMajor (102) is supported, as flomat.rkt:888 passes");
     if (rc == FM_OK) {
         const bool ta = transA == FM_TRANS, tb = transB == FM_TRANS;
+        // all operands on the host and a product large enough for the transfers to matter: column-block pipeline
+        if (!ta && !tb && transA == FM_NO_TRANS && transB == FM_NO_TRANS && M > 0 && N >= 1024 && K > 0 && (double)M * N * K >= 1073741824.0 &&
+            !is_device_ptr(A) && !is_device_ptr(B) && !is_device_ptr(C)) {
+            rc = fm_dgemm_host(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+            report("cblas_dgemm", rc);
+            return;
+        }
         Staged a, b, c;
         rc = a.in(A, lda, ta ? K : M, ta ? M : K, true);
         if (rc == FM_OK) rc = b.in(B, ldb, tb ? N : K, tb ? K : N, true);

@@ -65,6 +65,9 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ---- kernels' host entry points (device pointers, library stream) ------------------------------
 namespace fm {
 // ewise.cu
+// host <-> HBM copies that stage pageable host memory through pinned bounce buffers with several host threads (xfer.cu)
+int copy_h2d(double *dev, size_t ldd, const double *host, size_t ldh, size_t m, size_t n, cudaStream_t st);
+int copy_d2h(double *host, size_t ldh, const double *dev, size_t ldd, size_t m, size_t n, cudaStream_t st);
 int k_fill(double *a, int lda, int m, int n, double x);
 int k_eye(double *a, int lda, int m, int n, int k);
 int k_copy2d(double *dst, int ldd, const double *src, int lds, int m, int n);

@@ -104,7 +104,7 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     }
     FM_CUDA(cudaMemcpyAsync(d_scale, h_scale.data(), batch * sizeof(double), cudaMemcpyHostToDevice, st));
     FM_CUDA(cudaMemcpyAsync(d_rounds, h_rounds.data(), batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    FM_CUDA(cudaStreamSynchronize(st));  // h_* go out of scope at return; the copies must have read them
+    // no second sync: a copy FROM pageable host memory returns once the source has been staged, so h_* may go out of scope
 
     auto gemm = [&](const double *x, const double *y, double *z, double beta, bool has_diag, double diag) {
         GemmEpilogue ep;

@@ -344,6 +344,28 @@ def flomat_times(a: Flomat, b: Flomat, c: Flomat | None = None, alpha: float = 1
     return c
 
 
+def times_host(a: np.ndarray, b: np.ndarray, c: np.ndarray | None = None, alpha: float = 1.0, beta: float = 1.0,
+               wait: bool = True) -> np.ndarray:
+    """flomat* (flomat.rkt:905) on HOST matrices, the call the unmodified reference makes (cblas_dgemm with GC'd host memory,
+    :888): C := alpha*A*B + beta*C through fm_dgemm_host, which moves B and C in column blocks so that upload, product and
+    download overlap.  a, b, c are column-major float64 arrays (pinned memory for a real overlap).  Without c a new array is
+    returned and beta is 0 (the reference's zero matrix with beta = 1).  wait=False returns at once; c is valid after
+    transfer_sync()."""
+    for x in (a, b) + ((c,) if c is not None else ()):
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 2 and x.flags.f_contiguous):
+            raise ValueError("times_host: expected column-major float64 matrices")
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"flomat*: expected two matrices with compatible dimensions, got {a.shape[0]}x{a.shape[1]} and {b.shape[0]}x{b.shape[1]}")
+    m, k, n = a.shape[0], a.shape[1], b.shape[1]
+    if c is None:
+        c, beta = np.empty((m, n), order="F"), 0.0
+    elif c.shape != (m, n):
+        raise ValueError("flomat*!: result matrix has the wrong dimensions")
+    check(_L().fm_dgemm_host(m, n, k, float(alpha), a.ctypes.data, max(1, m), b.ctypes.data, max(1, k), float(beta), c.ctypes.data,
+                             max(1, m), 0 if wait else 1), "fm_dgemm_host")
+    return c
+
+
 def times(a, *bs):
     """`times` (flomat.rkt:3202): left fold; matrix*matrix -> flomat*, anything with a number -> `.*`."""
     for b in bs:

@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from oracle.flomat_oracle import normwise_rel_err, tol
+
 pytestmark = pytest.mark.gpu
 
 
@@ -70,3 +72,79 @@ def test_flat_buffers_and_argument_checks(fm):
         A.upload_async(np.zeros((n, m), order="F"))
     with pytest.raises(ValueError):
         A.download_async(np.zeros((m, n), dtype=np.float32, order="F"))
+
+
+# ---------------------------------------------------------------- host-operand product: column-block pipeline (fm_dgemm_host)
+@pytest.mark.parametrize("m,n,k,alpha,beta", [(1024, 1024, 1024, 1.0, 1.0), (700, 1300, 515, -0.5, 0.75), (129, 2055, 64, 2.0, 0.0),
+                                              (256, 1024, 0, 1.0, 0.5), (5, 3, 4, 1.0, 1.0)])
+def test_dgemm_host_pipeline_matches_oracle(fm, ref, m, n, k, alpha, beta):
+    rng = np.random.default_rng(m + 3 * n + 7 * k)
+    A, B = np.asfortranarray(rng.standard_normal((m, k))), np.asfortranarray(rng.standard_normal((k, n)))
+    C0 = np.asfortranarray(rng.standard_normal((m, n)))
+    got = fm.times_host(A, B, C0.copy(order="F"), alpha, beta)
+    if k == 0:  # BLAS: C := beta*C
+        assert np.array_equal(got, beta * C0)
+        return
+    want = ref.gemm(A, B, C0.copy(order="F"), alpha, beta)
+    assert normwise_rel_err(got, want) <= tol(max(m, n, k))
+    # the resident path on uploaded operands, same kernels: agreement to rounding of a different tile schedule at most
+    Cd = fm.matrix(C0)
+    fm.flomat_times(fm.matrix(A), fm.matrix(B), Cd, alpha, beta)
+    assert normwise_rel_err(got, Cd.to_numpy()) <= tol(max(m, n, k))
+
+
+def test_dgemm_host_async_and_views(fm, ref):
+    """wait=False leaves C to fm_transfer_sync; leading dimensions larger than the row count (views, flomat.rkt:288-300)."""
+    lib = fm.load()
+    rng = np.random.default_rng(77)
+    m, n, k, lda, ldb, ldc = 300, 1500, 200, 333, 256, 301
+    A, B, C = (np.asfortranarray(rng.standard_normal(s)) for s in ((lda, k), (ldb, n), (ldc, n)))
+    keep = C.copy(order="F")
+    rc = lib.fm_dgemm_host(m, n, k, 1.0, A.ctypes.data, lda, B.ctypes.data, ldb, 0.0, C.ctypes.data, ldc, 1)
+    assert rc == 0, lib.fm_last_error()
+    fm.transfer_sync()
+    want = ref.gemm(np.asfortranarray(A[:m]), np.asfortranarray(B[:k]))
+    assert normwise_rel_err(C[:m], want) <= tol(max(m, n, k))
+    assert np.array_equal(C[m:], keep[m:])  # rows outside the view untouched
+    # a device pointer is refused, not misread
+    d = fm.matrix(A)
+    assert lib.fm_dgemm_host(m, n, k, 1.0, d.a, lda, B.ctypes.data, ldb, 0.0, C.ctypes.data, ldc, 0) != 0
+
+
+def test_compat_cblas_dgemm_host_large_takes_pipeline(fm, ref):
+    """cblas_dgemm with host pointers at a size past the pipeline threshold (N >= 1024, MNK >= 2^30), alpha = beta = 1 into zeros
+    exactly as flomat.rkt:888 calls it."""
+    lib = fm.load()
+    n = 1024
+    rng = np.random.default_rng(5)
+    A, B = np.asfortranarray(rng.standard_normal((n, n))), np.asfortranarray(rng.standard_normal((n, n)))
+    C = np.zeros((n, n), order="F")
+    lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, A.ctypes.data, n, B.ctypes.data, n, 1.0, C.ctypes.data, n)
+    assert normwise_rel_err(C, ref.gemm(A, B)) <= tol(n)
+
+
+# ---------------------------------------------------------------- pageable host memory: the library's own staging (xfer.cu)
+@pytest.mark.parametrize("m,n,ldh", [(1500, 1500, 1500), (4096, 5200, 4096), (1000, 3000, 1111), (2049, 1025, 2050)])
+def test_pageable_upload_download_round_trip_is_exact(fm, m, n, ldh):
+    """Unpinned host matrices (what the reference's GC malloc gives, flomat.rkt:437) go through pinned bounce buffers filled by
+    several host threads; contiguous and strided (lda > m views) layouts, more chunks than bounce buffers."""
+    lib = fm.load()
+    rng = np.random.default_rng(m * 31 + n)
+    H = np.asfortranarray(rng.standard_normal((ldh, n)))
+    D = fm.Flomat.alloc(m, n)
+    assert lib.fm_upload(D.a, m, H.ctypes.data, ldh, m, n) == 0, lib.fm_last_error()
+    H2 = np.full((ldh, n), -7.0, order="F")
+    assert lib.fm_download(H2.ctypes.data, ldh, D.a, m, m, n) == 0, lib.fm_last_error()
+    assert np.array_equal(H2[:m], H[:m])
+    assert np.all(H2[m:] == -7.0)  # rows between the view's end and the leading dimension are not written
+    # and the device really holds the matrix: a kernel result computed from it
+    assert np.array_equal(fm.dot_plus(D, D).to_numpy(), 2.0 * H[:m])
+
+
+def test_pageable_staging_repeated_calls_do_not_mix_buffers(fm):
+    """Back-to-back staged uploads and downloads of different matrices share the bounce ring; each result must be its own."""
+    rng = np.random.default_rng(9)
+    mats = [np.asfortranarray(rng.standard_normal((1200 + 64 * i, 1300))) for i in range(6)]
+    dev = [fm.matrix(x) for x in mats]
+    for x, d in zip(mats, dev):
+        assert np.array_equal(d.to_numpy(), x)
