@@ -351,6 +351,21 @@ def run_gpu(args):
                                          "h2d_bytes": 2 * nh * nh * 8, "d2h_bytes": nh * nh * 8,
                                          "path": "fm_dgemm_host: column-block pipeline, pageable memory staged by the library's copy threads"}
             del pa, pb, pc
+            # config 3 the same way: dgesv_ on pageable host operands (flomat.rkt:2140 after its two copies); A comes back as L\U
+            from ctypes import byref, c_int
+            rs = np.random.default_rng(3001)
+            a0, b0 = np.asfortranarray(rs.standard_normal((ns, ns))), np.asfortranarray(rs.standard_normal((ns, nrhs)))
+            ipv, inf = np.zeros(ns, dtype=np.int32), c_int(0)
+            best = 1e30
+            for _ in range(3):
+                a1, b1 = a0.copy(order="F"), b0.copy(order="F")
+                t0 = time.perf_counter()
+                lib.dgesv_(byref(c_int(ns)), byref(c_int(nrhs)), a1.ctypes.data, byref(c_int(ns)), ipv.ctypes.data, b1.ctypes.data, byref(c_int(ns)), byref(inf))
+                best = min(best, (time.perf_counter() - t0) * 1e3)
+            resid = float(np.abs(a0[:256] @ b1 - b0[:256]).max())
+            extra["dgesv_host"] = {"n": ns, "nrhs": nrhs, "ms": best, "tflops_end_to_end": w / best / 1e9, "host_memory": "pageable", "info": inf.value,
+                                   "h2d_bytes": (ns * ns + ns * nrhs) * 8, "d2h_bytes": (ns * ns + ns * nrhs) * 8, "max_residual_rows_0_255": resid}
+            del a0, b0, a1, b1
         fm.load().fm_trim_cache()
 
     cpu = None

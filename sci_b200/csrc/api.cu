@@ -413,6 +413,12 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
     }
     const int cw = per * 128, nchunks = (n + cw - 1) / cw;
     static std::vector<cudaEvent_t> ev;  // [2j] block j uploaded, [2j+1] block j computed
+    static int ev_device = -1;
+    if (ev_device != g_ctx.device) {  // events belong to the device that was current when they were created
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+        ev_device = g_ctx.device;
+    }
     while (rc == FM_OK && (int)ev.size() < 2 * nchunks) {
         cudaEvent_t e;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: event creation failed");

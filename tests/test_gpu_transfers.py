@@ -148,3 +148,23 @@ def test_pageable_staging_repeated_calls_do_not_mix_buffers(fm):
     dev = [fm.matrix(x) for x in mats]
     for x, d in zip(mats, dev):
         assert np.array_equal(d.to_numpy(), x)
+
+
+def test_compat_dgesv_pageable_operands_through_staging(fm, ref):
+    """dgesv_ as flomat.rkt:2140 calls it, at a size where the pageable operands take the library's staged copies (> 4 MB):
+    X in B, L\\U in A, 1-based ipiv on the host -- against the oracle's dgesv on the same inputs."""
+    from ctypes import byref, c_int
+
+    lib = fm.load()
+    n, nrhs = 1100, 600
+    rng = np.random.default_rng(2024)
+    a, b = np.asfortranarray(rng.standard_normal((n, n))), np.asfortranarray(rng.standard_normal((n, nrhs)))
+    A, B = a.copy(order="F"), b.copy(order="F")
+    ipiv, info = np.zeros(n, dtype=np.int32), c_int(-1)
+    lib.dgesv_(byref(c_int(n)), byref(c_int(nrhs)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, B.ctypes.data, byref(c_int(n)), byref(info))
+    assert info.value == 0
+    want_lu, want_piv, _ = ref.lu(a)
+    assert np.array_equal(ipiv, want_piv)
+    assert normwise_rel_err(A, want_lu) <= tol(n)
+    assert normwise_rel_err(B, ref.mldivide(a, b)) <= tol(n) * 50  # cond(A) slack as in test_compat_lapack_symbols_host_pointers
+    assert np.abs(a @ B - b).max() <= 1e-9 * np.abs(b).max() * n
