@@ -403,15 +403,19 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
     const int tile_rows = (m + 127) / 128, nblk = (n + 127) / 128, sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
     int per = 1;
     {
+        // the narrowest block (shortest head and tail of the pipeline) whose tiles fill >= 97 % of their waves, else the best there is
         const int lo = nblk / 8 > 1 ? nblk / 8 : 1, hi = nblk / 3 > lo ? nblk / 3 : lo;
         double best = -1.0;
         for (int cnd = lo; cnd <= hi; ++cnd) {
             const long long tiles = (long long)cnd * tile_rows, waves = (tiles + sms - 1) / sms;
             const double eff = (double)tiles / (double)(waves * sms);
             if (eff > best + 1e-9) { best = eff; per = cnd; }
+            if (eff >= 0.97) { per = cnd; break; }
         }
     }
-    const int cw = per * 128, nchunks = (n + cw - 1) / cw;
+    const int cw = per * 128;
+    int nchunks = (n + cw - 1) / cw;
+    if (nchunks > 1 && n - (nchunks - 1) * cw < cw / 2) --nchunks;  // a short remainder rides with the last block
     static std::vector<cudaEvent_t> ev;  // [2j] block j uploaded, [2j+1] block j computed
     static int ev_device = -1;
     if (ev_device != g_ctx.device) {  // events belong to the device that was current when they were created
@@ -431,7 +435,7 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
         chk(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
         if (k > 0 && rc == FM_OK) rc = copy_h2d(da, ldda, a, lda, m, k, g_xfer.stream);
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
-            const int c0 = j * cw, w = n - c0 < cw ? n - c0 : cw;
+            const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
             if (k > 0) rc = copy_h2d(db + (size_t)c0 * lddb, lddb, b + (size_t)c0 * ldb, ldb, k, w, g_xfer.stream);
             if (beta != 0.0 && rc == FM_OK) rc = copy_h2d(dc + (size_t)c0 * lddc, lddc, c + (size_t)c0 * ldc, ldc, m, w, g_xfer.stream);
             chk(cudaEventRecord(ev[2 * j], g_xfer.stream));
@@ -447,7 +451,7 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
         }
         // downloads are queued after every upload: a copy to pageable memory blocks the host until it has run
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
-            const int c0 = j * cw, w = n - c0 < cw ? n - c0 : cw;
+            const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
             chk(cudaStreamWaitEvent(g_xfer.down, ev[2 * j + 1], 0));
             if (rc == FM_OK) rc = copy_d2h(c + (size_t)c0 * ldc, ldc, dc + (size_t)c0 * lddc, lddc, m, w, g_xfer.down);
         }
