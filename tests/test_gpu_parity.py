@@ -456,6 +456,68 @@ def test_expm_semigroup_property_large(fm):
     assert fm.norm(fm.minus(sq, E2), 1) / fm.norm(E2, 1) <= tol(n)
 
 
+def test_expm_batched_config5_shard(fm, ref):
+    """BASELINE config 5, one GPU's shard at full size: 512 items of 256 x 256 (A_i = N(0,1)/16) in one call.  Sampled items are
+    checked against the oracle's expm of the same bytes, every item against exp(A_i) exp(-A_i) == I summed over the batch."""
+    n, batch = 256, 512
+    rng = np.random.default_rng(5001)
+    host = rng.standard_normal(n * n * batch) / 16.0
+    src = fm.Flomat.from_numpy(host.reshape(-1, 1))
+    neg = fm.dot_times(src, -1.0)
+    dst, dstn = fm.Flomat.alloc(n * n * batch, 1), fm.Flomat.alloc(n * n * batch, 1)
+    s_out = np.zeros(batch)
+    fm.expm_batched(src.a, n, batch, dst.a, fm.EXPM_MIN_PRODUCTS, s_out)
+    fm.expm_batched(neg.a, n, batch, dstn.a, fm.EXPM_MIN_PRODUCTS)
+    got = dst.to_numpy().ravel()
+    for z in (0, 1, 255, 511):
+        item = host[z * n * n:(z + 1) * n * n].reshape(n, n, order="F")
+        assert s_out[z] == ref.scaling_exponent(item)
+        Ez = got[z * n * n:(z + 1) * n * n].reshape(n, n, order="F")
+        assert normwise_rel_err(Ez, ref.expm(np.asfortranarray(item))) <= tol(n), z
+    # all 512 items: P_z = exp(A_z) exp(-A_z) by one batched product, then || [P_0 .. P_511] - [I .. I] ||_1 over the n x (n*batch) strip
+    lib = fm.load()
+    prod = fm.Flomat.alloc(n, n * batch)
+    rc = lib.fm_dgemm_batched(n, n, n, 1.0, dst.a, n, n * n, dstn.a, n, n * n, 0.0, prod.a, n, n * n, -1.0, batch)  # diag: P_z - I
+    assert rc == 0, lib.fm_last_error()
+    e1 = fm.norm(fm.Flomat(n, n * batch, dst.a, n, dst._buf), 1)
+    assert fm.norm(prod, 1) <= tol(n) * e1 * e1
+
+
+def test_times_full_size_freivalds_and_linearity(fm):
+    """BASELINE config 4 at its full size on one GPU (n = 16384, 3 x 2 GiB, no CPU product possible): inputs from LAPACK's
+    generator on the device; Freivalds' check C x == A (B x) for random x and linearity in B, both normwise within 64 n eps."""
+    n = 16384
+    A, B = fm.randn(n, n, iseed=np.array([41, 1, 2, 3], dtype=np.int32)), fm.randn(n, n, iseed=np.array([42, 1, 2, 3], dtype=np.int32))
+    C = fm.times(A, B)
+    scale = fm.norm(A, 1) * fm.norm(B, 1)
+    for k in range(3):
+        x = fm.randn(n, 1, iseed=np.array([43 + k, 5, 6, 7], dtype=np.int32))
+        lhs = fm.flomat_times_vector(C, x)
+        rhs = fm.flomat_times_vector(A, fm.flomat_times_vector(B, x))
+        assert fm.norm(fm.minus(lhs, rhs), 1) / (scale * fm.norm(x, 1)) <= tol(n)
+    # (A)(2B) == 2 (AB) exactly (scaling by 2 commutes with every rounding), a bit-level check of the whole 16384^2 result
+    C2 = fm.times(A, fm.dot_times(B, 2.0))
+    assert fm.norm(fm.minus(C2, fm.dot_times(C, 2.0)), "max") == 0.0
+
+
+def test_expm_full_size_properties(fm):
+    """The metric's expm size (n = 8192, A = N(0,1)/sqrt(n), s = 8) on device-generated input: exp(A) exp(-A) == I and
+    exp(A)^2 == exp(2A), normwise within 64 n eps; both product orders of the polynomial agree."""
+    n = 8192
+    A = fm.dot_times(fm.randn(n, n, iseed=np.array([61, 3, 5, 7], dtype=np.int32)), 1.0 / math.sqrt(n))
+    E, s = fm.expm(A, fm.EXPM_MIN_PRODUCTS, return_s=True)
+    assert s == 8.0
+    Em = fm.expm(fm.dot_times(A, -1.0), fm.EXPM_MIN_PRODUCTS)
+    R = fm.minus(fm.times(E, Em), fm.eye(n))
+    assert fm.norm(R, 1) <= tol(n) * fm.norm(E, 1) * fm.norm(Em, 1)
+    del Em, R
+    E2 = fm.expm(fm.dot_times(A, 2.0), fm.EXPM_MIN_PRODUCTS)
+    assert fm.norm(fm.minus(fm.times(E, E), E2), 1) / fm.norm(E2, 1) <= tol(n)
+    del E2
+    Eref = fm.expm(A, fm.EXPM_REFERENCE_ORDER)
+    assert fm.norm(fm.minus(E, Eref), 1) / fm.norm(Eref, 1) <= tol(n)
+
+
 # ---------------------------------------------------------------- multi-GPU (needs >= 2 B200; skipped on a 1-GPU box)
 def test_colshard_fused_two_gpus(fm, tmp_path):
     """Column-sharded times with the all-gather fused into the GEMM epilogue (peer stores over NVLink), 2 ranks:
