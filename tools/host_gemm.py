@@ -35,3 +35,21 @@ for n in ns:
         print(f"n={n} {name}: {ms:.2f} ms  {flop / ms / 1e9:.2f} TFLOP/s end to end", flush=True)
     ref = fm.flomat_times(fm.matrix(hA), fm.matrix(hB)).to_numpy()
     print("  pinned result equals resident product:", np.array_equal(hC, ref), " pageable:", np.array_equal(pC, ref), flush=True)
+    # the reference's exact call (flomat.rkt:888 via :905): alpha = beta = 1 into a zero matrix, pageable memory
+    def ref_call():
+        pC.fill(0.0)
+        t0 = time.perf_counter()
+        lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, pA.ctypes.data, n, pB.ctypes.data, n, 1.0, pC.ctypes.data, n)
+        return (time.perf_counter() - t0) * 1e3
+    ref_call()
+    ms = min(ref_call() for _ in range(4))
+    print(f"n={n} cblas_dgemm alpha=beta=1, C=zeros (pageable): {ms:.2f} ms  {flop / ms / 1e9:.2f} TFLOP/s end to end", flush=True)
+    # raw staged copies of one n x n matrix
+    D = fm.Flomat.alloc(n, n)
+    def up():
+        lib.fm_upload(D.a, n, pA.ctypes.data, n, n, n); fm.sync()
+    def down():
+        lib.fm_download(pC.ctypes.data, n, D.a, n, n, n)
+    for name, fn in (("fm_upload pageable", up), ("fm_download pageable", down)):
+        ms = best(fn)
+        print(f"n={n} {name}: {ms:.2f} ms  {n * n * 8 / ms / 1e6:.1f} GB/s", flush=True)
