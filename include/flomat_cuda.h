@@ -152,6 +152,9 @@ int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const do
  * async != 0: returns without waiting, C is valid after fm_transfer_sync() / fm_sync(); use pinned host memory for a real overlap. */
 int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
                   double *c, int ldc, int async);
+/* the column blocks fm_dgemm_host cuts an m x n result into on a device with `sms` SMs (<= 0: 148): block width (a multiple of 128)
+ * and block count, the last block taking the remainder.  Host arithmetic only; callable without a GPU. */
+int fm_dgemm_host_plan(int m, int n, int sms, int *width, int *nblocks);
 /* as fm_dgemm (NN only) and then adds diag to C[i,i]: the `(plus (.* c I) (times A P))` step of mpoly, expm.rkt:176 */
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
                   double *c, int ldc, double diag);

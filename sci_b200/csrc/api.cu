@@ -379,6 +379,31 @@ int fm_dgemm(int transA, int transB, int m, int n, int k, double alpha, const do
     ep.beta = beta;
     return k_dgemm(transA, transB, m, n, k, a, lda, 0, b, ldb, 0, c, ldc, 0, 1, ep);
 }
+// The column blocks fm_dgemm_host uses for an m x n result on `sms` SMs: width (a multiple of 128 columns) and count; the last block
+// takes whatever is left (it may be up to half a block wider).  Pure host arithmetic, no device needed.
+int fm_dgemm_host_plan(int m, int n, int sms, int *width, int *nblocks) {
+    if (m <= 0 || n <= 0 || !width || !nblocks) return set_error(FM_ERR_ARG, "fm_dgemm_host_plan: bad arguments");
+    if (sms <= 0) sms = 148;
+    // about eight blocks: the narrowest one (shortest head and tail of the pipeline) whose 128 x 128 tiles fill >= 97 % of their
+    // waves of the persistent GEMM, else the best there is
+    const int tile_rows = (m + 127) / 128, nblk = (n + 127) / 128;
+    int per = 1;
+    const int lo = nblk / 8 > 1 ? nblk / 8 : 1, hi = nblk / 3 > lo ? nblk / 3 : lo;
+    double best = -1.0;
+    for (int cnd = lo; cnd <= hi; ++cnd) {
+        const long long tiles = (long long)cnd * tile_rows, waves = (tiles + sms - 1) / sms;
+        const double eff = (double)tiles / (double)(waves * sms);
+        if (eff > best + 1e-9) { best = eff; per = cnd; }
+        if (eff >= 0.97) { per = cnd; break; }
+    }
+    const int cw = per * 128;
+    int nchunks = (n + cw - 1) / cw;
+    if (nchunks > 1 && n - (nchunks - 1) * cw < cw / 2) --nchunks;  // a short remainder rides with the last block
+    *width = cw;
+    *nblocks = nchunks;
+    return FM_OK;
+}
+
 // C := alpha*A*B + beta*C with all three operands in HOST memory (what the unmodified reference passes to cblas_dgemm,
 // flomat.rkt:888): instead of upload / compute / download one after the other, B and C travel in column blocks -- A goes up once,
 // then block j of B is uploaded while the product of block j-1 runs and block j-2 of C comes down (uploads on the transfer stream,
@@ -399,23 +424,8 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
     double *dc = static_cast<double *>(fm_alloc_bytes((size_t)lddc * n * 8));
     int rc = FM_OK;
     if ((k > 0 && (!da || !db)) || !dc) rc = FM_ERR_NOMEM;
-    // column blocks: about eight, each a whole number of tile columns whose tiles come close to complete waves
-    const int tile_rows = (m + 127) / 128, nblk = (n + 127) / 128, sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
-    int per = 1;
-    {
-        // the narrowest block (shortest head and tail of the pipeline) whose tiles fill >= 97 % of their waves, else the best there is
-        const int lo = nblk / 8 > 1 ? nblk / 8 : 1, hi = nblk / 3 > lo ? nblk / 3 : lo;
-        double best = -1.0;
-        for (int cnd = lo; cnd <= hi; ++cnd) {
-            const long long tiles = (long long)cnd * tile_rows, waves = (tiles + sms - 1) / sms;
-            const double eff = (double)tiles / (double)(waves * sms);
-            if (eff > best + 1e-9) { best = eff; per = cnd; }
-            if (eff >= 0.97) { per = cnd; break; }
-        }
-    }
-    const int cw = per * 128;
-    int nchunks = (n + cw - 1) / cw;
-    if (nchunks > 1 && n - (nchunks - 1) * cw < cw / 2) --nchunks;  // a short remainder rides with the last block
+    int cw = 0, nchunks = 0;
+    fm_dgemm_host_plan(m, n, g_ctx.sm_count, &cw, &nchunks);
     static std::vector<cudaEvent_t> ev;  // [2j] block j uploaded, [2j+1] block j computed
     static int ev_device = -1;
     if (ev_device != g_ctx.device) {  // events belong to the device that was current when they were created

@@ -71,3 +71,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_dgemm_host_plan_covers_the_columns_in_full_waves():
+    """fm_dgemm_host_plan (host arithmetic of the host-operand GEMM pipeline, api.cu): blocks are whole 128-column tile columns,
+    cover [0, n) exactly with the remainder in the last block, and at the benchmark shapes their tiles fill >= 97 % of their waves."""
+    from ctypes import byref, c_int
+
+    from sci_b200 import _lib
+
+    lib = _lib.load()
+    for m, n, sms in [(8192, 8192, 148), (16384, 16384, 148), (4096, 4096, 148), (1024, 1024, 148), (700, 1300, 148), (129, 2055, 148),
+                      (8192, 64, 148), (1, 1, 148), (8192, 8192, 0), (5000, 100000, 132)]:
+        w, nb = c_int(-1), c_int(-1)
+        assert lib.fm_dgemm_host_plan(m, n, sms, byref(w), byref(nb)) == 0
+        w, nb = w.value, nb.value
+        assert w > 0 and w % 128 == 0 and nb >= 1
+        last = n - (nb - 1) * w
+        assert 0 < last < 2 * w, (m, n, w, nb)                # blocks 0 .. nb-2 are w wide, the last takes what is left
+        assert nb <= 12 or n > 12 * w, (m, n, w, nb)
+        if n >= 1024:
+            assert nb >= 2, (m, n, w, nb)                      # something to overlap
+        if (m, n) in ((8192, 8192), (16384, 16384)):
+            tiles = (w // 128) * ((m + 127) // 128)
+            s = sms or 148
+            waves = -(-tiles // s)
+            assert tiles / (waves * s) >= 0.97, (m, n, w, tiles)
+    assert lib.fm_dgemm_host_plan(0, 5, 148, byref(c_int()), byref(c_int())) != 0
