@@ -439,11 +439,21 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
         else ev.push_back(e);
     }
     auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == FM_OK) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: %s", cudaGetErrorString(e)); };
+    // developer switch: timestamps of every block's upload / product / download, printed after the call (tools/host_gemm_trace.py)
+    static const bool trace_on = getenv("FLOMAT_HOST_GEMM_TRACE") != nullptr;
+    const bool trace = trace_on && !async && rc == FM_OK;
+    std::vector<cudaEvent_t> tr;  // [0] start, [1] A uploaded, then per block: uploaded, product started, product done, downloaded
+    if (trace) {
+        tr.resize(2 + 4 * (size_t)nchunks);
+        for (auto &e : tr) cudaEventCreate(&e);
+    }
     if (rc == FM_OK) {
         // the staging blocks may be recycled ones that kernels queued so far still use
         chk(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
         chk(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
+        if (trace) cudaEventRecord(tr[0], g_xfer.stream);
         if (k > 0 && rc == FM_OK) rc = copy_h2d(da, ldda, a, lda, m, k, g_xfer.stream);
+        if (trace) cudaEventRecord(tr[1], g_xfer.stream);
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
             const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
             if (k > 0) rc = copy_h2d(db + (size_t)c0 * lddb, lddb, b + (size_t)c0 * ldb, ldb, k, w, g_xfer.stream);
@@ -451,6 +461,7 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
             chk(cudaEventRecord(ev[2 * j], g_xfer.stream));
             chk(cudaStreamWaitEvent(g_ctx.stream, ev[2 * j], 0));
             if (rc != FM_OK) break;
+            if (trace) { cudaEventRecord(tr[2 + 4 * j], g_xfer.stream); cudaEventRecord(tr[3 + 4 * j], g_ctx.stream); }
             GemmEpilogue ep;
             ep.alpha = alpha;
             ep.beta = beta;
@@ -458,12 +469,14 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
             else if (beta == 0.0) rc = k_fill(dc + (size_t)c0 * lddc, lddc, m, w, 0.0);  // BLAS: k = 0 leaves C := beta*C (beta = 0: no read of C)
             else rc = k_scal2d(m, w, beta, dc + (size_t)c0 * lddc, lddc);
             if (rc == FM_OK) chk(cudaEventRecord(ev[2 * j + 1], g_ctx.stream));
+            if (trace) cudaEventRecord(tr[4 + 4 * j], g_ctx.stream);
         }
         // downloads are queued after every upload: a copy to pageable memory blocks the host until it has run
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
             const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
             chk(cudaStreamWaitEvent(g_xfer.down, ev[2 * j + 1], 0));
             if (rc == FM_OK) rc = copy_d2h(c + (size_t)c0 * ldc, ldc, dc + (size_t)c0 * lddc, lddc, m, w, g_xfer.down);
+            if (trace) cudaEventRecord(tr[5 + 4 * j], g_xfer.down);
         }
         // whatever reuses the staging blocks (compute stream) comes after the last download
         chk(cudaEventRecord(g_xfer.tmp, g_xfer.down));
@@ -475,6 +488,14 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
         cudaStreamSynchronize(g_xfer.stream);
         cudaStreamSynchronize(g_ctx.stream);
         cudaStreamSynchronize(g_xfer.down);
+    }
+    if (trace) {
+        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0], tr[i]); return ms; };
+        fprintf(stderr, "[fm_dgemm_host] m=%d n=%d k=%d beta=%g: %d blocks of %d columns; A uploaded at %.2f ms\n", m, n, k, beta, nchunks, cw, at(1));
+        fprintf(stderr, "[fm_dgemm_host] block  uploaded  product start  product done  downloaded   (ms after the first upload was queued)\n");
+        for (int j = 0; j < nchunks; ++j)
+            fprintf(stderr, "[fm_dgemm_host] %5d  %8.2f  %13.2f  %12.2f  %10.2f\n", j, at(2 + 4 * j), at(3 + 4 * j), at(4 + 4 * j), at(5 + 4 * j));
+        for (auto &e : tr) cudaEventDestroy(e);
     }
     if (da) fm_free(da);
     if (db) fm_free(db);
