@@ -202,6 +202,8 @@ int fm_larnv(int idist, int32_t *iseed, long long n, double *x);
  * *s_out receives the scaling exponent 1+ceil(log2 ||A||_1) the reference computes (may be <= 0).
  * mode 0: reference Horner order (7+s products after dropping the two products with 0 and c*I);
  * mode 1: minimum-product regrouping (5+s products). */
+/* `out` may also be HOST memory: the last squaring then runs in column blocks whose device->host copies overlap the blocks
+ * still to be computed; a pinned buffer is valid after fm_transfer_sync() / fm_sync(), a pageable one on return. */
 int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
 /* batch of equally strided n x n matrices; s_out (host, `batch` doubles) may be NULL */
 int fm_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,

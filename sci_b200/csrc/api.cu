@@ -315,6 +315,22 @@ int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, 
     g_xfer.dirty = true;
     return FM_OK;
 }
+}  // extern "C"
+namespace fm {
+int download_behind_compute(double *host, size_t ldh, const double *dev, size_t ldd, size_t m, size_t n, bool last) {
+    FM_TRY(xfer_init());
+    FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
+    FM_CUDA(cudaStreamWaitEvent(g_xfer.down, g_xfer.tmp, 0));
+    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, g_xfer.down));
+    if (last) {
+        FM_CUDA(cudaEventRecord(g_xfer.tmp, g_xfer.down));
+        FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.tmp, 0));
+    }
+    g_xfer.dirty = true;
+    return FM_OK;
+}
+}  // namespace fm
+extern "C" {
 int fm_transfer_sync(void) {
     FM_TRY(ensure_init());
     if (g_xfer.stream) FM_CUDA(cudaStreamSynchronize(g_xfer.stream));
@@ -637,6 +653,9 @@ int fm_larnv(int idist, int32_t *iseed, long long n, double *x) {
 // =================================== expm ===================================
 int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host) {
     FM_TRY(ensure_init());
+    // a HOST result buffer: the last squaring is cut into column blocks whose downloads overlap the blocks still to be computed;
+    // the buffer is valid after fm_transfer_sync() / fm_sync() (pinned memory) or on return (pageable)
+    if (n > 0 && out && !is_device_ptr(out)) return k_expm_host_out(n, a, lda, out, ldo, mode, s_out, info_host);
     return k_expm(n, a, lda, out, ldo, mode, s_out, info_host);
 }
 int fm_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o, int batch, int mode,

@@ -120,5 +120,9 @@ int k_gemv(int trans, int m, int n, double alpha, const double *a, int lda, cons
 int k_larnv(int idist, int32_t *iseed_host, long long n, double *x);
 // expm.cu
 int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
+int k_expm_host_out(int n, const double *a, int lda, double *host_out, int ldh, int mode, double *s_out, int32_t *info_host);
+// host(m x n) := dev(m x n) on the download stream, behind the work queued on the compute stream so far and beside what is queued
+// next; `last`: the compute stream then waits for the downloads issued so far (their source may be reused afterwards).  api.cu
+int download_behind_compute(double *host, size_t ldh, const double *dev, size_t ldd, size_t m, size_t n, bool last);
 int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out);
 }  // namespace fm

@@ -63,7 +63,10 @@ double scaling_exponent(double norm1) {
 }
 
 // The whole pipeline for `batch` equally strided matrices.  Workspaces have leading dimension ldw and item stride sw.
-int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host) {
+// host_out: `out` is HOST memory (batch == 1): the last squaring runs in column blocks and each block is handed to the download stream
+// as soon as it is computed, so the device->host copy of the result overlaps the rest of the squaring instead of following it.
+int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host,
+                  bool host_out = false) {
     const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
     cudaStream_t st = ctx().stream;
     const int ldw = n + (n & 1);
@@ -167,6 +170,23 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     double *cur = num, *nxt = spare;
     bool uniform = true;  // every item squares the same number of times (always true for one matrix, the common case for a batch)
     for (int z = 1; z < batch; ++z) uniform = uniform && (h_rounds[z] == h_rounds[0]);
+    if (host_out) {  // (batch == 1, hence uniform)
+        if (max_rounds == 0) return download_behind_compute(out, ldo, cur, ldw, n, n, true);
+        for (int r = 0; r + 1 < max_rounds; ++r) {
+            GemmEpilogue ep;
+            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, n, n, cur, ldw, sw, cur, ldw, sw, nxt, ldw, sw, 1, ep));
+            double *t = cur; cur = nxt; nxt = t;
+        }
+        int cw = 0, nblocks = 0;
+        FM_TRY(fm_dgemm_host_plan(n, n, ctx().sm_count, &cw, &nblocks));
+        for (int j = 0; j < nblocks; ++j) {
+            const int c0 = j * cw, w = (j == nblocks - 1) ? n - c0 : cw;
+            GemmEpilogue ep;
+            FM_TRY(k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, w, n, cur, ldw, 0, cur + (size_t)c0 * ldw, ldw, 0, nxt + (size_t)c0 * ldw, ldw, 0, 1, ep));
+            FM_TRY(download_behind_compute(out + (size_t)c0 * ldo, ldo, nxt + (size_t)c0 * ldw, ldw, n, w, j == nblocks - 1));
+        }
+        return FM_OK;
+    }
     if (uniform) {
         if (max_rounds == 0) {
             if (batch == 1) return k_copy2d(out, ldo, cur, ldw, n, n);
@@ -202,6 +222,13 @@ int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, doub
     if (info_host) *info_host = 0;
     if (n == 0) return FM_OK;
     return expm_pipeline(n, a, lda, 0, out, ldo, 0, 1, mode, s_out);
+}
+
+int k_expm_host_out(int n, const double *a, int lda, double *host_out, int ldh, int mode, double *s_out, int32_t *info_host) {
+    if (n < 0 || lda < (n > 1 ? n : 1) || ldh < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm: bad dimensions");
+    if (info_host) *info_host = 0;
+    if (n == 0) return FM_OK;
+    return expm_pipeline(n, a, lda, 0, host_out, ldh, 0, 1, mode, s_out, true);
 }
 
 int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out) {

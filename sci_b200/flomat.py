@@ -711,6 +711,18 @@ def expm(a: Flomat, mode: int = EXPM_REFERENCE_ORDER, return_s: bool = False):
     return (out, s.value) if return_s else out
 
 
+def expm_to_host(a: Flomat, out: np.ndarray, mode: int = EXPM_REFERENCE_ORDER, return_s: bool = False):
+    """`expm` (expm.rkt:203) with the result delivered into the column-major float64 host array `out`: the last squaring runs in
+    column blocks whose downloads overlap the blocks still to be computed.  A pinned `out` is valid after transfer_sync()."""
+    _check_square(a, "expm")
+    if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (a.m, a.n) and out.flags.f_contiguous):
+        raise ValueError("expm_to_host: expected a column-major float64 array of the matrix's shape")
+    s = c_double()
+    info = c_int32()
+    check(_L().fm_expm(a.m, a.a, a.lda, out.ctypes.data, max(1, a.m), int(mode), byref(s), byref(info)), "fm_expm")
+    return (out, s.value) if return_s else out
+
+
 def expm_batched(a_ptr: int, n: int, batch: int, out_ptr: int, mode: int = EXPM_REFERENCE_ORDER, s_out: np.ndarray | None = None):
     """Batch of `batch` dense n x n matrices stored back to back (stride n*n) at device address a_ptr."""
     sp = s_out.ctypes.data if s_out is not None else None

@@ -168,3 +168,34 @@ def test_compat_dgesv_pageable_operands_through_staging(fm, ref):
     assert normwise_rel_err(A, want_lu) <= tol(n)
     assert normwise_rel_err(B, ref.mldivide(a, b)) <= tol(n) * 50  # cond(A) slack as in test_compat_lapack_symbols_host_pointers
     assert np.abs(a @ B - b).max() <= 1e-9 * np.abs(b).max() * n
+
+
+# ---------------------------------------------------------------- expm with the result delivered to host memory
+@pytest.mark.parametrize("n,pin", [(8, False), (64, True), (700, False), (1500, True), (2304, False)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_expm_to_host_matches_device_result(fm, n, pin, mode):
+    """fm_expm with a HOST result pointer: the last squaring runs in column blocks whose downloads overlap the remaining blocks.
+    Same arithmetic as the resident call up to the tile configuration of the last product: normwise within 64 n eps."""
+    rng = np.random.default_rng(n)
+    a = np.asfortranarray(rng.standard_normal((n, n)) / np.sqrt(n))
+    A = fm.matrix(a)
+    want, s_want = fm.expm(A, mode, return_s=True)
+    want = want.to_numpy()
+    out = pinned((n, n)) if pin else np.empty((n, n), order="F")
+    out[...] = np.nan
+    _, s = fm.expm_to_host(A, out, mode, return_s=True)
+    fm.transfer_sync()
+    assert s == s_want
+    assert np.isfinite(out).all()
+    assert normwise_rel_err(out, want) <= tol(n)
+
+
+def test_expm_to_host_without_squaring(fm):
+    """s <= 0 (reference behaviour, expm.rkt:205-210: no squaring at all): the result comes straight from the solve."""
+    a = np.asfortranarray(np.diag([0.1, 0.05, 0.02]))
+    A = fm.matrix(a)
+    want = fm.expm(A).to_numpy()
+    out = np.empty((3, 3), order="F")
+    fm.expm_to_host(A, out)
+    fm.transfer_sync()
+    assert np.array_equal(out, want)
