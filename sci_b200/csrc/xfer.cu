@@ -17,8 +17,13 @@
 namespace fm {
 namespace {
 
-constexpr size_t BOUNCE_BYTES = (size_t)32 << 20;  // per buffer
-constexpr int NBOUNCE = 4;
+constexpr int MAX_BOUNCE = 8;
+// ring geometry; FLOMAT_CUDA_BOUNCE_MB / FLOMAT_CUDA_BOUNCE_COUNT are developer switches for sweeps (tools/host_gemm.py)
+const size_t BOUNCE_BYTES = (size_t)(getenv("FLOMAT_CUDA_BOUNCE_MB") && atoi(getenv("FLOMAT_CUDA_BOUNCE_MB")) > 0 ? atoi(getenv("FLOMAT_CUDA_BOUNCE_MB")) : 32) << 20;
+const int NBOUNCE = [] {
+    const int c = getenv("FLOMAT_CUDA_BOUNCE_COUNT") ? atoi(getenv("FLOMAT_CUDA_BOUNCE_COUNT")) : 4;
+    return c < 2 ? 2 : (c > MAX_BOUNCE ? MAX_BOUNCE : c);
+}();
 constexpr size_t MIN_STAGED_BYTES = (size_t)4 << 20;  // below this the driver's own path is as good
 
 // persistent workers; the calling thread takes part as worker 0.  Leaked on purpose: the library may be unloaded at exit while a
@@ -110,9 +115,9 @@ CopyPool &pool() {
 }
 
 struct Bounce {
-    double *buf[NBOUNCE] = {};
-    cudaEvent_t ev[NBOUNCE] = {};
-    bool busy[NBOUNCE] = {};
+    double *buf[MAX_BOUNCE] = {};
+    cudaEvent_t ev[MAX_BOUNCE] = {};
+    bool busy[MAX_BOUNCE] = {};
     int device = -1;
 };
 Bounce g_b;
