@@ -98,3 +98,28 @@ def test_dgemm_host_plan_covers_the_columns_in_full_waves():
             waves = -(-tiles // s)
             assert tiles / (waves * s) >= 0.97, (m, n, w, tiles)
     assert lib.fm_dgemm_host_plan(0, 5, 148, byref(c_int()), byref(c_int())) != 0
+
+
+def test_host_operand_entry_points_check_arguments_before_device_work():
+    """times_host / expm_to_host (host mirror of flomat* and expm on host matrices): layout and dimension errors are raised on the
+    host, with the reference's messages where it has one (check-product-dimensions, flomat.rkt:340)."""
+    import numpy as np
+
+    from sci_b200.flomat import Flomat, expm_to_host, times_host
+
+    a, b = np.zeros((4, 3), order="F"), np.zeros((4, 5), order="F")
+    with pytest.raises(ValueError, match="compatible dimensions"):
+        times_host(a, b)
+    with pytest.raises(ValueError, match="column-major"):
+        times_host(np.zeros((4, 3)), np.zeros((3, 5)))          # C-ordered
+    with pytest.raises(ValueError, match="column-major"):
+        times_host(np.zeros((4, 3), order="F", dtype=np.float32), np.zeros((3, 5), order="F"))
+    with pytest.raises(ValueError, match="wrong dimensions"):
+        times_host(np.zeros((4, 3), order="F"), np.zeros((3, 5), order="F"), np.zeros((4, 4), order="F"))
+    sq = Flomat(3, 3, 0, 3, None)
+    with pytest.raises(ValueError):
+        expm_to_host(Flomat(2, 3, 0, 2, None), np.zeros((2, 3), order="F"))   # check-square
+    with pytest.raises(ValueError, match="column-major"):
+        expm_to_host(sq, np.zeros((3, 4), order="F"))
+    with pytest.raises(ValueError, match="column-major"):
+        expm_to_host(sq, np.zeros((3, 3), dtype=np.float32, order="F"))
