@@ -14,6 +14,8 @@
  *     CUDA failures never abort the process and never fall back to a CPU path.
  *   - device-tier calls are asynchronous on the library stream (fm_set_stream / default: legacy stream 0)
  *     unless they return a scalar to the host.
+ *   - threading: the reference calls from ONE OS thread.  Calls that target the same device must be serialised by the
+ *     caller; fm_last_error() is thread-local.
  */
 #ifndef FLOMAT_CUDA_H
 #define FLOMAT_CUDA_H
@@ -166,8 +168,12 @@ int fm_dgemm_batched(int m, int n, int k, double alpha, const double *a, int lda
 /* LU family, device pointers (a, b, ipiv, info all in HBM; info is one int32 per matrix) */
 int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info);
 int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb);
+/* dgesv semantics (flomat.rkt:2112): with info > 0 (exactly singular U) the solve is skipped and B is left untouched, which is
+ * what flomat-solve-many! (:2135-2142, info ignored) then returns.  Reads info back once (4 bytes, syncs). */
 int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int ldb, int32_t *info);
-int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info); /* a := inv from its LU */
+/* a := inv from its LU; info (device, may be NULL) = i if U(i,i) is exactly zero, in which case a keeps the LU factors
+ * (dgetri/dtrtri semantics, flomat.rkt:1754-1779).  Reads the scan result back once (syncs). */
+int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info);
 /* flomat-determinant-from-plu (flomat.rkt:1837): sign(ipiv) * left-to-right product of diag(LU); syncs */
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out);
 
@@ -204,6 +210,8 @@ int fm_larnv(int idist, int32_t *iseed, long long n, double *x);
  * mode 1: minimum-product regrouping (5+s products). */
 /* `out` may also be HOST memory: the last squaring then runs in column blocks whose device->host copies overlap the blocks
  * still to be computed; a pinned buffer is valid after fm_transfer_sync() / fm_sync(), a pageable one on return. */
+/* *info_host (may be NULL) receives the info of the inner dgesv (0, or i for an exactly singular Pade denominator, in which case the
+ * result is what the reference computes: dgesv leaves num untouched and the squarings run on it, flomat.rkt:2135-2142). */
 int fm_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
 /* batch of equally strided n x n matrices; s_out (host, `batch` doubles) may be NULL */
 int fm_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,

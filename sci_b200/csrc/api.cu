@@ -548,18 +548,39 @@ int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, do
     FM_TRY(ensure_init());
     return k_getrs(n, nrhs, lu, lda, 0, ipiv, 0, b, ldb, 0, 1);
 }
+// one device int32 to the host (syncs the library stream)
+static int read_i32(const int32_t *dev, int32_t *out) {
+    int32_t *h = reinterpret_cast<int32_t *>(g_ctx.h_scalar + 32);
+    FM_CUDA(cudaMemcpyAsync(h, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    *out = *h;
+    return FM_OK;
+}
 int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int ldb, int32_t *info) {
     FM_TRY(ensure_init());
+    if (!info) return set_error(FM_ERR_ARG, "fm_gesv: info is NULL");
     FM_TRY(k_getrf(n, n, a, lda, 0, ipiv, 0, info, 1));
-    // LAPACK skips the solve when info > 0; the triangular solves below then divide by the exact zero pivot and
-    // produce inf/NaN, which is what a caller that ignores info (flomat.rkt:2140-2142) observes either way.
+    // LAPACK's dgesv solves only when the factorisation succeeded; with info > 0 B is left untouched, so a caller that ignores
+    // info (flomat-solve-many!, flomat.rkt:2135-2142) gets its copy of B back.  One 4-byte readback decides.
+    int32_t hinfo = 0;
+    FM_TRY(read_i32(info, &hinfo));
+    if (hinfo != 0) return FM_OK;
     return k_getrs(n, nrhs, a, lda, 0, ipiv, 0, b, ldb, 0, 1);
 }
 int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
     FM_TRY(ensure_init());
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "fm_getri: bad dimensions");
-    if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), g_ctx.stream));
-    if (n == 0) return FM_OK;
+    int32_t *d_info = info ? info : reinterpret_cast<int32_t *>(g_ctx.d_scalar + 16);
+    if (n == 0) {
+        if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), g_ctx.stream));
+        return FM_OK;
+    }
+    // LAPACK's dgetri (through dtrtri) returns info = i for an exactly zero U(i,i) before any work: A stays the LU factors, which
+    // is what `inv` of a singular matrix hands back in the reference (flomat-inverse!, flomat.rkt:1770-1779, info ignored)
+    FM_TRY(k_first_zero_diag(n, a, lda, d_info));
+    int32_t hinfo = 0;
+    FM_TRY(read_i32(d_info, &hinfo));
+    if (hinfo != 0) return FM_OK;
     return k_getri(n, a, lda, ipiv);
 }
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
@@ -783,8 +804,9 @@ struct StagedVec {
     int out() {
         if (!owned) return FM_OK;
         const long long ainc = inch < 0 ? -(long long)inch : inch;
-        if (ainc <= 1) FM_CUDA(cudaMemcpyAsync(host, dev, (size_t)n * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-        else FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ainc * 8, dev, 8, 8, n, cudaMemcpyDeviceToHost, g_ctx.stream));
+        const int len = (inch == 0) ? 1 : n;  // as staged by in(): a stride-0 vector is one element
+        if (ainc <= 1) FM_CUDA(cudaMemcpyAsync(host, dev, (size_t)len * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+        else FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ainc * 8, dev, 8, 8, len, cudaMemcpyDeviceToHost, g_ctx.stream));
         FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
         return FM_OK;
     }
@@ -794,7 +816,7 @@ struct StagedVec {
 void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY) {
     if (n <= 0) return;
     int rc = ensure_init();
-    if (rc == FM_OK && (incX < 0 || incY < 0)) rc = set_error(FM_ERR_ARG, "cblas_daxpy: negative increments are not used by flomat and not supported");
+    if (rc == FM_OK && (incX < 0 || incY <= 0)) rc = set_error(FM_ERR_ARG, "cblas_daxpy: negative increments (and incY = 0) are not used by flomat and not supported");
     if (rc == FM_OK) {
         StagedVec x, y;
         rc = x.in(X, incX, n, true);
@@ -807,7 +829,7 @@ void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int 
 void cblas_dcopy(int n, const double *X, int incX, double *Y, int incY) {
     if (n <= 0) return;
     int rc = ensure_init();
-    if (rc == FM_OK && (incX < 0 || incY < 0)) rc = set_error(FM_ERR_ARG, "cblas_dcopy: negative increments are not used by flomat and not supported");
+    if (rc == FM_OK && (incX < 0 || incY <= 0)) rc = set_error(FM_ERR_ARG, "cblas_dcopy: negative increments (and incY = 0) are not used by flomat and not supported");
     if (rc == FM_OK) {
         StagedVec x, y;
         rc = x.in(X, incX, n, true);
@@ -851,6 +873,8 @@ double cblas_ddot(int n, const double *X, int incX, const double *Y, int incY) {
     if (n <= 0) return 0.0;
     double out = 0.0;
     int rc = ensure_init();
+    // incX = 0 / incY = 0 are legal here (`unsafe-sum`, flomat.rkt:2074: ddot against one 1.0); negative strides are not used by flomat
+    if (rc == FM_OK && (incX < 0 || incY < 0)) rc = set_error(FM_ERR_ARG, "cblas_ddot: negative increments are not used by flomat and not supported");
     if (rc == FM_OK) {
         StagedVec x, y;
         rc = x.in(X, incX, n, true);
@@ -1033,18 +1057,14 @@ void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, doubl
             if (!d_ipiv) rc = FM_ERR_NOMEM;
             else rc = fm_upload_i32(d_ipiv, ipiv, (size_t)*n);
         }
-        // LAPACK dgetri: info = i if U(i,i) is exactly zero (singular), checked before any work
-        if (rc == FM_OK) {
-            double d = 1.0;
-            rc = fm_det(*n, A.dev, A.ld, d_ipiv, &d);  // product of the diagonal: exact zero iff some U(i,i) == 0
-            if (rc == FM_OK && d == 0.0) {
-                std::vector<double> diag((size_t)*n);
-                cudaMemcpy2D(diag.data(), 8, A.dev, ((size_t)A.ld + 1) * 8, 8, *n, cudaMemcpyDeviceToHost);
-                for (int i = 0; i < *n; ++i)
-                    if (diag[i] == 0.0) { *info = i + 1; break; }
-            }
-        }
-        if (rc == FM_OK && *info == 0) rc = fm_getri(*n, A.dev, A.ld, d_ipiv, nullptr);
+        // LAPACK dgetri: info = i if U(i,i) is exactly zero (singular), checked before any work (fm_getri scans the diagonal)
+        int32_t *d_info = rc == FM_OK ? static_cast<int32_t *>(fm_alloc_bytes(16)) : nullptr;
+        if (rc == FM_OK && !d_info) rc = FM_ERR_NOMEM;
+        if (rc == FM_OK) rc = fm_getri(*n, A.dev, A.ld, d_ipiv, d_info);
+        int32_t hinfo = 0;
+        if (rc == FM_OK) rc = read_i32(d_info, &hinfo);
+        if (rc == FM_OK) *info = hinfo;
+        if (d_info) fm_free(d_info);
         if (rc == FM_OK && *info == 0) rc = A.out();
         if (rc == FM_OK) cudaStreamSynchronize(g_ctx.stream);
         if (!ipiv_dev && d_ipiv) fm_free(d_ipiv);

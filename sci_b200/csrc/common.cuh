@@ -107,6 +107,7 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);
 int k_getri(int n, double *a, int lda, const int32_t *ipiv);
+int k_first_zero_diag(int n, const double *lu, int lda, int32_t *d_out);  // d_out: device int32, 1-based index or 0
 int k_potrf(char uplo, int n, double *a, int lda, int32_t *info);  // info: device int32
 // level12.cu
 int k_transpose(int m, int n, const double *a, int lda, double *b, int ldb);

@@ -65,8 +65,20 @@ double scaling_exponent(double norm1) {
 // The whole pipeline for `batch` equally strided matrices.  Workspaces have leading dimension ldw and item stride sw.
 // host_out: `out` is HOST memory (batch == 1): the last squaring runs in column blocks and each block is handed to the download stream
 // as soon as it is computed, so the device->host copy of the result overlaps the rest of the squaring instead of following it.
+// The LU's info words are copied to pinned host memory right behind the factorisation and the rest of the pipeline is queued without
+// waiting for them (no bubble between the solve and the squarings); `info_ready` is recorded behind that copy.  The caller checks the
+// words afterwards and, in the (practically unreachable) case of an exactly singular Pade denominator, runs the pipeline again with
+// `honour_singular`: LAPACK's dgesv leaves B untouched when info > 0 and the reference ignores info (flomat-solve-many!,
+// flomat.rkt:2135-2142), so such an item continues with R = num.
+struct InfoBack {
+    int32_t *h = nullptr;  // pinned, `cap` words
+    int cap = 0;
+    cudaEvent_t ready = nullptr;
+};
+InfoBack g_info;
+
 int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host,
-                  bool host_out = false) {
+                  bool host_out = false, bool honour_singular = false) {
     const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
     cudaStream_t st = ctx().stream;
     const int ldw = n + (n & 1);
@@ -165,7 +177,35 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     // the workspaces of a batch are contiguous (item stride = ldw*n), i.e. one ldw x (n*batch) matrix: one launch
     FM_TRY(k_addsub(n, n * batch, E, ldw, O, ldw, num, ldw, den, ldw));
     FM_TRY(k_getrf(n, n, den, ldw, sw, d_ipiv, n, d_info, batch));
-    FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
+    if (g_info.cap < batch) {
+        if (g_info.h) cudaFreeHost(g_info.h);
+        g_info.h = nullptr;
+        g_info.cap = 0;
+        FM_CUDA(cudaMallocHost(&g_info.h, (size_t)(batch < 64 ? 64 : batch) * sizeof(int32_t)));
+        g_info.cap = batch < 64 ? 64 : batch;
+    }
+    if (!g_info.ready) FM_CUDA(cudaEventCreateWithFlags(&g_info.ready, cudaEventDisableTiming));
+    FM_CUDA(cudaMemcpyAsync(g_info.h, d_info, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaEventRecord(g_info.ready, st));
+    if (!honour_singular) {
+        FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
+    } else {
+        // second pass after a singular denominator was seen: items with info > 0 keep num (dgesv leaves B untouched)
+        FM_CUDA(cudaEventSynchronize(g_info.ready));
+        std::vector<int> bad;
+        for (int z = 0; z < batch; ++z)
+            if (g_info.h[z] != 0) bad.push_back(z);
+        if (batch == 1) {
+            if (bad.empty()) FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, 1));
+        } else {
+            double *keep = bad.empty() ? nullptr : static_cast<double *>(fm_alloc_bytes((size_t)sw * bad.size() * sizeof(double)));
+            if (!bad.empty() && !keep) return FM_ERR_NOMEM;
+            for (size_t i = 0; i < bad.size(); ++i) FM_TRY(k_copy2d(keep + i * sw, ldw, num + bad[i] * sw, ldw, n, n));
+            FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
+            for (size_t i = 0; i < bad.size(); ++i) FM_TRY(k_copy2d(num + bad[i] * sw, ldw, keep + i * sw, ldw, n, n));
+            if (keep) fm_free(keep);
+        }
+    }
     // ---- repeated squaring (expm.rkt:209-210), per-item round counts ----
     double *cur = num, *nxt = spare;
     bool uniform = true;  // every item squares the same number of times (always true for one matrix, the common case for a batch)
@@ -217,25 +257,40 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
 
 }  // namespace
 
+namespace {
+// run the pipeline, then look at the LU's info words (they arrived long before the squarings finish); a singular denominator
+// sends the call through the pipeline a second time with dgesv's "B untouched" rule applied.  Returns the first nonzero info.
+int expm_checked(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out,
+                 bool host_out, int32_t *info_host) {
+    FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false));
+    FM_CUDA(cudaEventSynchronize(g_info.ready));
+    int32_t first = 0;
+    for (int z = 0; z < batch && first == 0; ++z) first = g_info.h[z];
+    if (info_host) *info_host = first;
+    if (first == 0) return FM_OK;
+    return expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, true);
+}
+}  // namespace
+
 int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host) {
     if (n < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm: bad dimensions");
     if (info_host) *info_host = 0;
     if (n == 0) return FM_OK;
-    return expm_pipeline(n, a, lda, 0, out, ldo, 0, 1, mode, s_out);
+    return expm_checked(n, a, lda, 0, out, ldo, 0, 1, mode, s_out, false, info_host);
 }
 
 int k_expm_host_out(int n, const double *a, int lda, double *host_out, int ldh, int mode, double *s_out, int32_t *info_host) {
     if (n < 0 || lda < (n > 1 ? n : 1) || ldh < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm: bad dimensions");
     if (info_host) *info_host = 0;
     if (n == 0) return FM_OK;
-    return expm_pipeline(n, a, lda, 0, host_out, ldh, 0, 1, mode, s_out, true);
+    return expm_checked(n, a, lda, 0, host_out, ldh, 0, 1, mode, s_out, true, info_host);
 }
 
 int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out) {
     if (n < 0 || batch < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm_batched: bad dimensions");
     if (n == 0 || batch == 0) return FM_OK;
     if (batch > 65535) return set_error(FM_ERR_ARG, "expm_batched: at most 65535 items per call");
-    return expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out);
+    return expm_checked(n, a, lda, sa, out, ldo, so, batch, mode, s_out, false, nullptr);
 }
 
 }  // namespace fm

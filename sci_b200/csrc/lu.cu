@@ -2179,6 +2179,27 @@ extern "C" int fm_lu_prof(long long *out32) {
 namespace fm {
 #endif
 
+// LAPACK's singularity test of DGETRI / DTRTRI: the 1-based index of the first exactly-zero U(i,i), 0 if there is none.
+// (Not inferred from the determinant: an overflowed partial product times the zero pivot is NaN, not 0.)
+__global__ void __launch_bounds__(256) first_zero_diag_kernel(int n, const double *lu, long long lda, int32_t *out) {
+    __shared__ int s_min;
+    if (threadIdx.x == 0) s_min = 0x7fffffff;
+    __syncthreads();
+    int mine = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (lu[i * (lda + 1)] == 0.0) { mine = i + 1; break; }  // indices grow with i: the first hit is this thread's minimum
+    if (mine != 0x7fffffff) atomicMin(&s_min, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s_min == 0x7fffffff ? 0 : s_min;
+}
+
+int k_first_zero_diag(int n, const double *lu, int lda, int32_t *d_out) {
+    if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "getri: bad dimensions");
+    first_zero_diag_kernel<<<1, 256, 0, ctx().stream>>>(n, lu, lda, d_out);
+    FM_LAUNCH_CHECK();
+    return FM_OK;
+}
+
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out) {
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "det: bad dimensions");
     det_kernel<<<1, 256, 0, ctx().stream>>>(n, lu, lda, ipiv, d_out);

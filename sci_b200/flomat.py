@@ -458,6 +458,56 @@ def mldivide(a: Flomat, b: Flomat) -> Flomat:
     return x
 
 
+def result_flcolumn(b) -> Flomat:
+    """result-flcolumn (flomat.rkt:1896): a vector or a list becomes an m x 1 matrix, a matrix passes through unchanged."""
+    if isinstance(b, Flomat):
+        return b
+    return Flomat.from_numpy(np.asarray(b, dtype=np.float64).reshape(-1, 1))
+
+
+def flomat_augment(*cols: Flomat) -> Flomat:
+    """flomat-augment (flomat.rkt:1223): [C1 C2 ...] side by side, a new matrix (one device copy per piece)."""
+    if not cols:
+        raise ValueError("flomat-augment: expected at least one matrix")
+    m = cols[0].m
+    if any(c.m != m for c in cols):
+        raise ValueError("flomat-augment: all arguments must have same number of rows")
+    out = Flomat.alloc(m, sum(c.n for c in cols))
+    j = 0
+    for c in cols:
+        v = out.sub(0, j, m, c.n)
+        check(_L().fm_copy2d(v.a, v.lda, c.a, c.lda, m, c.n), "fm_copy2d")
+        j += c.n
+    return out
+
+
+def flomat_solve_many_bang(a: Flomat, b: Flomat) -> Flomat:
+    """flomat-solve-many! (flomat.rkt:2135): dgesv in place, A and B overwritten, info ignored; returns B."""
+    _check_square(a, "flomat-solve-many!")
+    if b.m != a.m:
+        raise ValueError("flomat-solve-many!: A and B must have the same number of rows")
+    piv = _pivots(a.m)
+    check(_L().fm_gesv(a.m, b.n, a.a, a.lda, piv.ptr, b.a, b.lda, piv.info_ptr), "fm_gesv")
+    return b
+
+
+def flomat_solve_many(a: Flomat, bs_or_b) -> Flomat:
+    """flomat-solve-many (flomat.rkt:2145): B is a matrix (copied) or a LIST of columns (augmented); A is copied."""
+    if isinstance(bs_or_b, (list, tuple)):
+        b = flomat_augment(*[result_flcolumn(c) for c in bs_or_b])
+    else:
+        b = copy_flomat(bs_or_b)
+    return flomat_solve_many_bang(copy_flomat(a), b)
+
+
+flomat_left_divide = flomat_solve_many  # flomat.rkt:2159
+
+
+def flomat_solve(a: Flomat, b) -> Flomat:
+    """flomat-solve (flomat.rkt:2126): one right-hand side column; copies A and b, dgesv with nrhs = 1, info ignored."""
+    return flomat_solve_many_bang(copy_flomat(a), copy_flomat(result_flcolumn(b)))
+
+
 def inv(a: Flomat) -> Flomat:
     """`inv` (flomat.rkt:3297) -> flomat-inverse! :1770: copy, dgetrf, dgetri."""
     _check_square(a, "flomat-inverse!")
