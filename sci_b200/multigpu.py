@@ -185,7 +185,6 @@ class ColShardTimes:
             out["nccl_ms"] = ms2
             out["nccl_tflops_total"] = flops / (ms2 * 1e-3) / 1e12
         out["tflops_per_gpu"] = out["fused_tflops_total"] / self.world
-        out["pct_of_fp64_peak_per_gpu"] = 100.0 * out["tflops_per_gpu"] / 37.0
         return out
 
     def close(self):
@@ -197,3 +196,117 @@ class ColShardTimes:
         self.peers = []
         self.lib.fm_free(self.c_ptr)
         self.c_ptr = None
+
+
+class ShardedJob:
+    """BASELINE configs 4 and 5 as ONE job sharded over `world` ranks (the N > 1 workload of bench.py, total work fixed):
+
+      * `times` at size n: A replicated, B and C in column blocks, the all-gather of C fused into the GEMM epilogue (ColShardTimes);
+      * `items` independent expm of n_item x n_item matrices, `item_block` of them per rank, no collective.
+
+    step()      device-resident inputs (what `value` times)
+    e2e_step()  the same job from pinned HOST buffers: every rank uploads ITS column block of A and of B and its items; A is then
+                all-gathered over NVLink (NCCL, in place) instead of travelling world times over PCIe; the rank's block of C and
+                its expm results go back to the host beside the kernels that follow them.
+    """
+
+    def __init__(self, n: int, items: int, n_item: int, world: int, rank: int, mode: int, seed: int = 4001):
+        import torch
+
+        from . import flomat as F
+
+        self.F, self.torch = F, torch
+        self.cs = ColShardTimes(n, world, rank, seed=seed)
+        self.lib, self.check, self.dist = self.cs.lib, self.cs.check, self.cs.dist
+        self.n, self.world, self.rank, self.mode = n, world, rank, mode
+        self.n_item = n_item
+        self.z0, self.nitems = item_block(items, world, rank)
+        self.items_total = items
+        dev = self.cs.A.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(5001 + rank)
+        per = n_item * n_item
+        self.src = torch.randn(per * max(self.nitems, 1), dtype=torch.float64, device=dev, generator=g) / 16.0  # SURVEY 8d config 5
+        self.dst = torch.empty_like(self.src)
+        self.s_out = np.zeros(max(self.nitems, 1))
+        self._host = None
+
+    # ---- device-resident step ------------------------------------------------------------------------------------------------
+    def step(self):
+        self.cs.step_fused()
+        if self.nitems:
+            self.F.expm_batched(self.src.data_ptr(), self.n_item, self.nitems, self.dst.data_ptr(), self.mode, self.s_out)
+
+    def flops(self, expm_flops_min) -> float:
+        """Algorithmic work of this rank's share: its column block of the product + W_min of its items (needs one step() first)."""
+        w = 2.0 * self.n * self.n * self.cs.nloc
+        if self.nitems:
+            w += float(sum(expm_flops_min(self.n_item, sv) for sv in self.s_out[: self.nitems]))
+        return w
+
+    # ---- end to end from host buffers ----------------------------------------------------------------------------------------
+    def _host_buffers(self):
+        if self._host is None:
+            torch, n, nloc, per = self.torch, self.n, max(self.cs.nloc, 1), self.n_item * self.n_item
+            pin = lambda count: torch.empty(count, dtype=torch.float64, pin_memory=True)  # noqa: E731
+            h = {"a": pin(n * nloc), "b": pin(n * nloc), "c": pin(n * nloc), "x": pin(per * max(self.nitems, 1)), "e": pin(per * max(self.nitems, 1))}
+            j0 = self.cs.j0
+            h["a"].copy_(self.cs.A[j0 * n:(j0 + nloc) * n])
+            h["b"].copy_(self.cs.B[: n * nloc])
+            h["x"].copy_(self.src)
+            torch.cuda.synchronize()
+            self._host = h
+        return self._host
+
+    def e2e_bytes(self):
+        n, nloc, per = self.n, self.cs.nloc, self.n_item * self.n_item
+        return {"h2d": 8 * (2 * n * nloc + per * self.nitems), "d2h": 8 * (n * nloc + per * self.nitems)}
+
+    def e2e_step(self):
+        lib, cs, n, nloc, j0 = self.lib, self.cs, self.n, self.cs.nloc, self.cs.j0
+        h = self._host_buffers()
+        if nloc:
+            self.check(lib.fm_upload_async(cs.A.data_ptr() + 8 * j0 * n, n, h["a"].data_ptr(), n, n, nloc), "fm_upload_async")
+            self.check(lib.fm_upload_async(cs.B.data_ptr(), n, h["b"].data_ptr(), n, n, nloc), "fm_upload_async")
+        if self.world > 1:
+            allgather_columns(cs.A, n, n, self.world, self.rank, self.dist)  # A over NVLink instead of `world` times over PCIe
+        cs.step_fused()
+        per = self.n_item * self.n_item
+        if nloc:
+            self.check(lib.fm_download_async(h["c"].data_ptr(), n, cs.c_ptr + 8 * j0 * n, n, n, nloc), "fm_download_async")
+        if self.nitems:
+            x = self.F.Flomat.alloc(per, self.nitems)  # a recycled block: the allocator orders the upload behind its last readers
+            self.check(lib.fm_upload_async(x.a, per, h["x"].data_ptr(), per, per, self.nitems), "fm_upload_async")
+            self.F.expm_batched(x.a, self.n_item, self.nitems, self.dst.data_ptr(), self.mode, None)
+            self.check(lib.fm_download_async(h["e"].data_ptr(), per, self.dst.data_ptr(), per, per, self.nitems), "fm_download_async")
+        self.check(lib.fm_transfer_sync(), "fm_transfer_sync")
+
+    # ---- verification (asserted by bench.py) -----------------------------------------------------------------------------------
+    def verify(self, sample_items: int = 16) -> dict:
+        """times: every rank's assembled C is complete, identical across ranks and right on sampled columns (ColShardTimes.verify);
+        expm: exp(A_z) exp(-A_z) == I within 64 n eps ||.||_1 ||.||_1 for a sample of this rank's items (all on the device)."""
+        torch, F = self.torch, self.F
+        out = {"times_ok": self.cs.verify(), "expm_ok": True}
+        k = min(sample_items, self.nitems)
+        if k:
+            ni, per = self.n_item, self.n_item * self.n_item
+            neg = (-self.src[: per * k]).contiguous()
+            e_pos, e_neg = torch.empty_like(neg), torch.empty_like(neg)
+            F.expm_batched(self.src.data_ptr(), ni, k, e_pos.data_ptr(), self.mode, None)
+            F.expm_batched(neg.data_ptr(), ni, k, e_neg.data_ptr(), self.mode, None)
+            p = torch.bmm(e_pos.view(k, ni, ni), e_neg.view(k, ni, ni))  # (row-major views = transposes: E_neg^T E_pos^T)^T, still I)
+            eye = torch.eye(ni, dtype=torch.float64, device=p.device)
+            err = (p - eye).abs().sum(dim=1).amax(dim=1)
+            bound = 64 * ni * 2.0 ** -52 * e_pos.view(k, ni, ni).abs().sum(dim=2).amax(dim=1) * e_neg.view(k, ni, ni).abs().sum(dim=2).amax(dim=1)
+            # the timed run's results for these items (a different batch size picks other tile shapes: same values within rounding)
+            d = (e_pos - self.dst[: per * k]).view(k, ni, ni).abs().sum(dim=2).amax(dim=1)
+            same = bool((d <= 64 * ni * 2.0 ** -52 * e_pos.view(k, ni, ni).abs().sum(dim=2).amax(dim=1)).all().item())
+            out["expm_ok"] = bool((err <= bound).all().item()) and bool(torch.isfinite(p).all().item()) and same
+        flag = torch.tensor([1.0 if (out["times_ok"] and out["expm_ok"]) else 0.0], device=self.cs.A.device)
+        if self.world > 1:
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        out["all_ranks_ok"] = bool(flag.item() == 1.0)
+        return out
+
+    def close(self):
+        self.cs.close()
