@@ -16,11 +16,11 @@ the old weak-scaling number (one n = 8192 step per GPU) stays under "replicas".
 
 e2e = the same step through the host API with HOST buffers: uploads from pinned memory, compute, downloads, every step.
 cpu_baseline / --impl reference = the reference's own CPU path: its call sequence (oracle/flomat_oracle.py) on OpenBLAS with all host
-threads.  The reference arm's step is a BOUNDED SAMPLE at the full sizes: every distinct foreign call of the step is executed once
-per step on the full-size operands and the step time is the sum over the call sequence the reference executes (multiplicities in
-`cpu_baseline.sample`); a whole real step costs ~35 s of CPU and does not fit K = 20 steps into the driver's per-run limit.  The GPU
-arm's own `cpu_baseline` at N = 1 runs ONE real full step (times n = 8192 + expm n = 8192, 11+s dgemms) and prints the sampled
-estimate beside it, so the extrapolation is checked in every run.
+threads.  At N = 1 the reference arm runs K REAL full steps (times n = 8192 + expm n = 8192: 11+s dgemms + dgesv, ~25 s each on 16
+cores) whenever K of them fit --ref-budget-s (640 s; the driver's tightest per-run limit is 870 s); otherwise, and for the sharded
+N > 1 job, its step is a BOUNDED SAMPLE at the full sizes: every distinct foreign call of the step executed once on the full-size
+operands, step time = the sum over the call sequence the reference executes (multiplicities in `cpu_baseline.sample`).  The GPU
+arm's own `cpu_baseline` at N = 1 runs ONE real full step and prints the sampled estimate beside it (measured: within 2-3 %).
 """
 from __future__ import annotations
 
@@ -217,7 +217,14 @@ class CpuShardedStep:
 
     def sampled(self) -> tuple[float, dict]:
         t_blk, _ = _t(lambda: self.F.times(self.a, self.b))
+        # small products do not scale to every core: give the reference the better of all threads and 8 threads for the items
         t_items, _ = _t(lambda: [self.F.expm(x) for x in self.xs])
+        all_threads = self.prov.threads()
+        if hasattr(self.prov, "_set") and all_threads > 8:
+            self.prov._set(8)
+            t8, _ = _t(lambda: [self.F.expm(x) for x in self.xs])
+            self.prov._set(all_threads)
+            t_items = min(t_items, t8)
         t = self.blocks * t_blk + (self.items / self.k) * t_items
         return t, {"seconds_once": {"times_column_block": t_blk, f"expm_{self.k}_items": t_items},
                    "multiplicity": {"times_column_block": self.blocks, f"expm_{self.k}_items": self.items / self.k}}
@@ -234,16 +241,24 @@ def run_reference(args):
         return
     world = args.gpus
     job = CpuMetricStep(args.n) if world == 1 else CpuShardedStep(args.colshard_n, args.batch_items, args.batch_n)
-    warm = 1 if args.warmup > 0 else 0  # BLAS threads are spun up in the constructor; more warm-up buys nothing on the CPU
+    t_est, detail = job.sampled()  # doubles as the warm-up (BLAS threads, page faults); more warm-up buys nothing on the CPU
+    # N = 1: K REAL full steps whenever they fit the budget (a real step is ~25 s on 16 cores: K = 20 fits the driver's per-run limit
+    # of 870 s); otherwise, and for the sharded job (thousands of identical independent pieces), the bounded sample at full size
+    real = world == 1 and args.steps * t_est <= args.ref_budget_s
     times = []
-    for it in range(warm + args.steps):
-        t, _detail = job.sampled()
-        if it >= warm:
+    for _ in range(args.steps):
+        if real:
+            times.append(job.full())
+        else:
+            t, detail = job.sampled()
             times.append(t)
     t = sum(times) / len(times)
     value = job.flops / t / 1e9
-    cb = {"value": value, "unit": "GFLOP/s", "cores": job.prov.threads(), "kind": "port", "sample": job.describe(t),
-          "warmup_steps_run": warm, "detail": _detail}
+    sample = (f"{args.steps} REAL full steps of the reference call sequence (flomat.rkt:888, expm.rkt:193-210) on {job.prov.name}: times n={args.n} + "
+              f"expm n={args.n} (s={int(job.s)}, {11 + max(int(job.s), 0)} dgemms + dgesv executed, W_min counted), {t:.1f} s per step"
+              if real else job.describe(t))
+    cb = {"value": value, "unit": "GFLOP/s", "cores": job.prov.threads(), "kind": "port", "sample": sample, "real_full_steps": bool(real),
+          "warmup_steps_run": 1, "sampled_estimate_s": t_est, "detail": detail}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "cpu_baseline": cb,
@@ -443,10 +458,58 @@ def sharded_job(G: Gpu, args, steps: int, warmup: int, with_e2e: bool, sampler: 
         b = job.e2e_bytes()
         h2d, d2h = G.sum_over_ranks(b["h2d"], b["d2h"])
         out["e2e_bytes"] = (int(h2d), int(d2h))
-        out["e2e_api"] = ("per step and rank, pinned host buffers: own column block of A and of B up (fm_upload_async) -> A all-gathered over "
-                          "NVLink (NCCL, in place) -> fused column-sharded GEMM -> own block of C down beside the expm batch; own items up "
-                          "beside the GEMM -> fm_expm_batched -> results down; bytes are totals over all ranks")
+        out["e2e_api"] = ("per step and rank, pinned host buffers: own column slice of A up (fm_upload_async) -> A all-gathered over NVLink "
+                          "(NCCL, in place) -> own block of B / C in sub-blocks: upload i+1 | fused column-sharded GEMM i | download i-1; own "
+                          "items up beside the GEMMs -> fm_expm_batched -> results down; bytes are totals over all ranks")
     job.close()
+    return out
+
+
+def single_process_mg(G: Gpu, args) -> dict:
+    """The single-process entry points (fm_mg_*: ONE process, ONE calling thread, every device of the box -- the form `flomat*` can
+    use, flomat.rkt:905-914) driven from rank 0 while the other ranks wait on the host: config 4 with device operands on device 0,
+    with pinned and with pageable host operands, and config 5 with device operands."""
+    import numpy as np
+
+    fm, lib, torch, n = G.fm, G.lib, G.torch, args.colshard_n
+    ndev = fm.mg_init(G.world)
+    out = {"devices": ndev, "n": n}
+    A, B = G.dev_randn(n, n, 4001), G.dev_randn(n, n, 4002)
+    C = fm.Flomat.alloc(n, n)
+    ms = G.best_ms(lambda: fm.times_mg(A, B, C, 1.0, 0.0))
+    ok = fm.norm(fm.minus(C, fm.times(A, B)), "max") == 0.0  # bit for bit what one device computes
+    out["dgemm_device_operands"] = {"ms": ms, "tflops_total": 2.0 * n ** 3 / ms / 1e9, "equals_single_device": bool(ok),
+                                    "includes": "A and the blocks of B travel from device 0 over NVLink inside the call; C is assembled on device 0 by the peer-store epilogue"}
+    hA, hB = A.to_numpy(), B.to_numpy()  # pageable
+    hC = np.empty((n, n), order="F")
+    best = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter(); fm.times_host_mg(hA, hB, hC, 1.0, 0.0); best = min(best, (time.perf_counter() - t0) * 1e3)
+    samp = np.random.default_rng(1).integers(0, n, 64)
+    want = C.to_numpy()
+    ok_h = bool(np.array_equal(hC[:, samp], want[:, samp]))
+    out["dgemm_host_pageable"] = {"ms": best, "tflops_end_to_end": 2.0 * n ** 3 / best / 1e9, "equals_device_result": ok_h,
+                                  "h2d_bytes": 2 * n * n * 8, "d2h_bytes": n * n * 8}
+    del want
+    pin = lambda: torch.empty((n, n), dtype=torch.float64, pin_memory=True).numpy().T  # noqa: E731  (F-contiguous views)
+    pA, pB, pC = pin(), pin(), pin()
+    pA[...] = hA; pB[...] = hB
+    del hA, hB, hC
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter(); fm.times_host_mg(pA, pB, pC, 1.0, 0.0); best = min(best, (time.perf_counter() - t0) * 1e3)
+    out["dgemm_host_pinned"] = {"ms": best, "tflops_end_to_end": 2.0 * n ** 3 / best / 1e9}
+    del pA, pB, pC, A, B, C
+    ni, items = args.batch_n, args.batch_items
+    g = torch.Generator(device=G.dev); g.manual_seed(5001)
+    src = torch.randn(ni * ni * items, dtype=torch.float64, device=G.dev, generator=g) / 16.0
+    dst = torch.empty_like(src)
+    s_out = np.zeros(items)
+    mode = fm.EXPM_MIN_PRODUCTS if args.expm_mode == 1 else fm.EXPM_REFERENCE_ORDER
+    ms = G.best_ms(lambda: fm.expm_batched_mg(src.data_ptr(), ni, items, dst.data_ptr(), mode, s_out))
+    w = float(sum(expm_flops_min(ni, sv) for sv in s_out))
+    out["expm_batched_device_operands"] = {"items": items, "n": ni, "ms": ms, "tflops_wmin_total": w / ms / 1e9}
+    out["ok"] = bool(ok and ok_h)
     return out
 
 
@@ -509,6 +572,22 @@ def run_gpu(args):
             r.pop("host")
             line["replicas"] = {"workload": f"one (times + expm) n={args.n} instance per GPU, no collective (weak scaling)",
                                 "gflops_total": world * r["flops_step"] / (r["ms_step"] * 1e-3) / 1e9, "ms_per_step": r["ms_step"]}
+
+    if world > 1 and not args.no_single_process:
+        # the other ranks wait on the HOST (a store key, no NCCL kernel spinning on their GPUs) while rank 0 drives every device
+        store = G.dist.distributed_c10d._get_default_store()
+        G.barrier()
+        if rank == 0:
+            try:
+                sp = single_process_mg(G, args)
+                line["single_process_mg"] = sp
+                if not sp["ok"]:
+                    failed.append(f"single-process multi-GPU verification failed: {sp}")
+            finally:
+                store.set("single_process_mg_done", "1")
+        else:
+            store.wait(["single_process_mg_done"])
+        G.barrier()
 
     extra = {}
     if world == 1 and not args.no_extra_configs:
@@ -639,6 +718,8 @@ def main():
     ap.add_argument("--no-extra-configs", action="store_true", help="skip sharded_job_n1 and the solve / expm512 / elementwise / compat sub-measurements")
     ap.add_argument("--no-compat-expm", action="store_true")
     ap.add_argument("--no-replicas", action="store_true")
+    ap.add_argument("--no-single-process", action="store_true", help="skip the fm_mg_* (one process, all devices) sub-measurement at N > 1")
+    ap.add_argument("--ref-budget-s", type=float, default=640.0, help="--impl reference at N=1 runs real full steps if K of them fit this many seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

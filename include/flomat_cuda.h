@@ -99,13 +99,14 @@ void dlarnv_(const int *idist, int32_t *iseed, const int *n, double *x);
  * ---------------------------------------------------------------------------------------------- */
 
 /* library / device */
-int fm_init(int device);                 /* idempotent; selects the device and creates the context */
+int fm_init(int device);                 /* idempotent; binds the CALLING THREAD to the device and creates its context on first use;
+                                            a process may use several devices (one context each), a thread one at a time */
 int fm_device_count(void);
 int fm_set_stream(void *cuda_stream);    /* cudaStream_t; NULL = legacy default stream */
 int fm_sync(void);                       /* wait for everything queued on the library stream */
 const char *fm_last_error(void);         /* thread-local, never NULL */
 const char *fm_version(void);
-uint64_t fm_kernel_launches(void);       /* number of kernels this library has launched so far */
+uint64_t fm_kernel_launches(void);       /* number of kernels this library has launched so far (all devices) */
 
 /* memory: alloc-flomat / free; upload & download are the explicit host sync points */
 double *fm_alloc(int m, int n);                          /* m*n doubles of HBM, lda = m; NULL on failure */
@@ -230,6 +231,30 @@ int fm_ipc_close(void *dev);
 /* C[:, j0:j0+nloc] := A * Bloc, stored to the local C and to every peer_c[r] (r < npeers, may be 0) */
 int fm_dgemm_colshard(int m, int nloc, int k, const double *a, int lda, const double *bloc, int ldb, double *c, int ldc,
                       int j0, double *const *peer_c, int npeers);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tier 3b: multi-GPU from ONE process and ONE calling thread -- the form the reference can use: `flomat*` is one call from one
+ * Racket OS thread (flomat.rkt:905-914 -> :888).  fm_mg_init starts one worker thread per device (rank 0 = the caller's device)
+ * and enables peer access between all pairs of the group (<= 8 devices of one NVSwitch domain).
+ *
+ * fm_mg_dgemm: C := alpha A B + beta C sharded by column blocks of B and C, A replicated.  Operands are either
+ *   all HOST memory  -- each device uploads its own slice of A over its own PCIe link, the slices are all-gathered over NVLink,
+ *                       and block j of B / C runs through device j's upload | product | download pipeline; returns when C is complete;
+ *   all DEVICE memory on the caller's device -- the other devices pull A and their block of B over NVLink and their GEMM epilogues
+ *                       store the finished tiles of C directly into the caller's C (fused peer-store epilogue); asynchronous: the
+ *                       caller's library stream waits for one event per device (fm_sync / any later fm_* call sees the result).
+ * Only the untransposed product is sharded; trans flags other than 111/111 are rejected (use fm_dgemm).
+ * fm_mg_expm_batched: as fm_expm_batched with the items split into one contiguous block per device (no exchange); host operands
+ *   or device operands on the caller's device.  s_out (host, `batch` doubles, may be NULL).
+ * LU / solve / inv / det are single-GPU (north_star).
+ * ---------------------------------------------------------------------------------------------- */
+int fm_mg_init(int ndev);                 /* <= 0: all visible devices (at most 8); idempotent for the same count */
+int fm_mg_device_count(void);             /* devices of the group, 0 before fm_mg_init */
+int fm_mg_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double *a, int lda, const double *b,
+                int ldb, double beta, double *c, int ldc);
+int fm_mg_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,
+                       int batch, int mode, double *s_out);
+int fm_mg_sync(void);                     /* wait for every device of the group */
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,12 @@ SIGNATURES = {
     "fm_ipc_open": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "fm_ipc_close": (c_int, [c_void_p]),
     "fm_dgemm_colshard": (c_int, [c_int, c_int, c_int, _DP, c_int, _DP, c_int, _DP, c_int, c_int, c_void_p, c_int]),
+    # tier 3b: one process, one calling thread, all devices
+    "fm_mg_init": (c_int, [c_int]),
+    "fm_mg_device_count": (c_int, []),
+    "fm_mg_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
+    "fm_mg_expm_batched": (c_int, [c_int, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "fm_mg_sync": (c_int, []),
 }
 
 

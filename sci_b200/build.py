@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libflomat_cuda.so")
-SOURCES = ["api.cu", "ewise.cu", "norm.cu", "dgemm.cu", "lu.cu", "expm.cu", "level12.cu", "xfer.cu"]
+SOURCES = ["api.cu", "ewise.cu", "norm.cu", "dgemm.cu", "lu.cu", "expm.cu", "level12.cu", "xfer.cu", "mg.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, os.pardir, "include", "flomat_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--cudart", "shared"]

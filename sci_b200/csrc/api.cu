@@ -10,13 +10,18 @@
 #include <vector>
 #include <utility>
 #include <cmath>
+#include <mutex>
 
 namespace fm {
 
 static thread_local char g_err[512] = "";
-static Context g_ctx;
+static Context g_ctxs[FM_MAX_DEVICES];
+static thread_local int t_dev = -1;  // the device this host thread is bound to
+static int g_default_dev = -1;       // the first device any thread bound: the home of threads that never called fm_init
+static std::mutex g_init_mu;
 
-Context &ctx() { return g_ctx; }
+Context &ctx() { return g_ctxs[t_dev >= 0 ? t_dev : (g_default_dev >= 0 ? g_default_dev : 0)]; }
+int bound_device() { return t_dev; }
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -33,33 +38,43 @@ static int init_device(int device) {
     if (e != cudaSuccess || count == 0)
         return set_error(FM_ERR_NOGPU, "no CUDA device available (%s); libflomat_cuda has no CPU fallback",
                          e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0 || device >= count) return set_error(FM_ERR_ARG, "fm_init: device %d out of range (0..%d)", device, count - 1);
-    cudaDeviceProp prop;
-    FM_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return set_error(FM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
-    FM_CUDA(cudaSetDevice(device));
-    Context &c = g_ctx;
-    if (c.ready && c.device == device) return FM_OK;
-    c.device = device;
-    c.sm_count = prop.multiProcessorCount;
-    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    c.scratch = nullptr;
-    c.scratch_bytes = 0;
-    FM_CUDA(cudaMalloc(&c.d_scalar, 64 * sizeof(double)));
-    FM_CUDA(cudaMallocHost(&c.h_scalar, 64 * sizeof(double)));
-    c.ready = true;
+    if (device < 0 || device >= count || device >= FM_MAX_DEVICES)
+        return set_error(FM_ERR_ARG, "fm_init: device %d out of range (0..%d)", device, (count < FM_MAX_DEVICES ? count : FM_MAX_DEVICES) - 1);
+    FM_CUDA(cudaSetDevice(device));  // (the CUDA current device is per host thread as well)
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    Context &c = g_ctxs[device];
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        FM_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return set_error(FM_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        c.device = device;
+        c.sm_count = prop.multiProcessorCount;
+        c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+        FM_CUDA(cudaMalloc(&c.d_scalar, 64 * sizeof(double)));
+        FM_CUDA(cudaMallocHost(&c.h_scalar, 64 * sizeof(double)));
+        c.ready = true;
+    }
+    t_dev = device;
+    if (g_default_dev < 0) g_default_dev = device;
     return FM_OK;
 }
 
+int bind_device(int device) { return init_device(device); }
+unsigned long long launches_of_device(int d) { return (d >= 0 && d < FM_MAX_DEVICES) ? g_ctxs[d].launches : 0ull; }
+const char *error_text() { return g_err; }
+
 int ensure_init() {
-    if (g_ctx.ready) return FM_OK;
+    if (t_dev >= 0) return FM_OK;  // bound threads have a ready context
+    if (g_default_dev >= 0) return init_device(g_default_dev);
     const char *dev = getenv("FLOMAT_CUDA_DEVICE");
     return init_device(dev ? atoi(dev) : 0);
 }
 
 void *scratch(size_t bytes) {
-    Context &c = g_ctx;
+    Context &c = ctx();
     if (bytes <= c.scratch_bytes) return c.scratch;
     if (c.scratch) cudaFree(c.scratch);  // implicit device sync: nothing in flight still uses it
     c.scratch = nullptr;
@@ -75,12 +90,14 @@ void *scratch(size_t bytes) {
 }
 
 // ---- pointer classification + staging for the compat tier --------------------------------------
-static bool is_device_ptr(const void *p) {
+bool is_device_pointer(const void *p, int *device_out) {
     if (!p) return false;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (device_out) *device_out = at.device;
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
+static bool is_device_ptr(const void *p) { return is_device_pointer(p, nullptr); }
 
 // A host matrix staged into HBM for the duration of one compat call.
 struct Staged {
@@ -101,15 +118,15 @@ struct Staged {
         }
         owned = true;
         if (copy_in)
-            FM_TRY(copy_h2d(dev, ld, host, ldh, rows, cols, g_ctx.stream));
+            FM_TRY(copy_h2d(dev, ld, host, ldh, rows, cols, ctx().stream));
         return FM_OK;
     }
     int out() {
         if (!owned) return FM_OK;
-        FM_TRY(copy_d2h(host, ldh, dev, ld, m, n, g_ctx.stream));
+        FM_TRY(copy_d2h(host, ldh, dev, ld, m, n, ctx().stream));
         return FM_OK;
     }
-    ~Staged() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); fm_free(dev); } }
+    ~Staged() { if (owned && dev) { cudaStreamSynchronize(ctx().stream); fm_free(dev); } }
 };
 
 static void report(const char *who, int rc) {
@@ -127,19 +144,23 @@ int fm_init(int device) { return init_device(device); }
 int fm_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; } return c; }
 int fm_set_stream(void *s) {
     FM_TRY(ensure_init());
-    if (g_ctx.stream != static_cast<cudaStream_t>(s)) cudaStreamSynchronize(g_ctx.stream);  // cached blocks are reused in stream order
-    g_ctx.stream = static_cast<cudaStream_t>(s);
+    if (ctx().stream != static_cast<cudaStream_t>(s)) cudaStreamSynchronize(ctx().stream);  // cached blocks are reused in stream order
+    ctx().stream = static_cast<cudaStream_t>(s);
     return FM_OK;
 }
 int fm_transfer_sync(void);
 int fm_sync(void) {
     FM_TRY(ensure_init());
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     return fm_transfer_sync();
 }
 const char *fm_last_error(void) { return g_err; }
 const char *fm_version(void) { return "libflomat_cuda 0.1 (sm_100a)"; }
-uint64_t fm_kernel_launches(void) { return g_ctx.launches; }
+uint64_t fm_kernel_launches(void) {  // all devices of the process (fm_mg_* launch from worker threads on every device)
+    uint64_t total = 0;
+    for (int d = 0; d < FM_MAX_DEVICES; ++d) total += fm::launches_of_device(d);
+    return total;
+}
 
 // =================================== memory ===================================
 // fm_alloc / fm_free sit where the reference has GC'd `malloc` (flomat.rkt:437-441): cheap and called for every
@@ -155,7 +176,8 @@ struct Xfer {
     cudaEvent_t last = nullptr, tmp = nullptr;
     bool dirty = false;  // transfers issued since the last fm_transfer_sync
 };
-Xfer g_xfer;
+PerDevice<Xfer> g_xfer_pd;
+Xfer &xfer() { return g_xfer_pd(); }
 struct Block {
     size_t bytes = 0;
     cudaEvent_t freed = nullptr;  // recorded on the compute stream when the block was last given back (only once transfers are in use)
@@ -174,9 +196,9 @@ struct BlockCache {
     }
     void trim() {
         if (free_blocks.empty()) return;
-        cudaStreamSynchronize(g_ctx.stream);
-        if (g_xfer.stream) cudaStreamSynchronize(g_xfer.stream);
-        if (g_xfer.down) cudaStreamSynchronize(g_xfer.down);
+        cudaStreamSynchronize(ctx().stream);
+        if (xfer().stream) cudaStreamSynchronize(xfer().stream);
+        if (xfer().down) cudaStreamSynchronize(xfer().down);
         for (auto &kv : free_blocks) {
             if (kv.second.second.freed) cudaEventDestroy(kv.second.second.freed);
             cudaFree(kv.second.first);
@@ -192,13 +214,14 @@ struct BlockCache {
         return nullptr;
     }
 };
-BlockCache g_cache;
+PerDevice<BlockCache> g_cache_pd;
+BlockCache &cache() { return g_cache_pd(); }
 int xfer_init() {
-    if (g_xfer.stream) return FM_OK;
-    FM_CUDA(cudaStreamCreateWithFlags(&g_xfer.stream, cudaStreamNonBlocking));
-    FM_CUDA(cudaStreamCreateWithFlags(&g_xfer.down, cudaStreamNonBlocking));
-    FM_CUDA(cudaEventCreateWithFlags(&g_xfer.last, cudaEventDisableTiming));
-    FM_CUDA(cudaEventCreateWithFlags(&g_xfer.tmp, cudaEventDisableTiming));
+    if (xfer().stream) return FM_OK;
+    FM_CUDA(cudaStreamCreateWithFlags(&xfer().stream, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamCreateWithFlags(&xfer().down, cudaStreamNonBlocking));
+    FM_CUDA(cudaEventCreateWithFlags(&xfer().last, cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&xfer().tmp, cudaEventDisableTiming));
     return FM_OK;
 }
 }  // namespace
@@ -207,20 +230,20 @@ void *fm_alloc_bytes(size_t bytes) {
     if (ensure_init() != FM_OK) return nullptr;
     if (bytes == 0) bytes = 16;
     bytes = (bytes + 511) & ~(size_t)511;
-    auto it = g_cache.free_blocks.find(bytes);
-    if (it != g_cache.free_blocks.end()) {
+    auto it = cache().free_blocks.find(bytes);
+    if (it != cache().free_blocks.end()) {
         void *p = it->second.first;
         Block blk = it->second.second;
-        g_cache.free_blocks.erase(it);
-        g_cache.cached_bytes -= bytes;
+        cache().free_blocks.erase(it);
+        cache().cached_bytes -= bytes;
         blk.fresh = false;
-        g_cache.live[p] = blk;
+        cache().live[p] = blk;
         return p;
     }
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
-        g_cache.trim();  // give the cached blocks back and try once more
+        cache().trim();  // give the cached blocks back and try once more
         if (cudaMalloc(&p, bytes) != cudaSuccess) {
             cudaGetLastError();
             set_error(FM_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
@@ -229,7 +252,7 @@ void *fm_alloc_bytes(size_t bytes) {
     }
     Block blk;
     blk.bytes = bytes;
-    g_cache.live[p] = blk;
+    cache().live[p] = blk;
     return p;
 }
 double *fm_alloc(int m, int n) {
@@ -238,46 +261,55 @@ double *fm_alloc(int m, int n) {
 }
 int fm_free(void *dev) {
     if (!dev) return FM_OK;
-    auto it = g_cache.live.find(dev);
-    if (it == g_cache.live.end()) {  // not ours (or freed twice): plain cudaFree reports the error
-        FM_CUDA(cudaFree(dev));
+    auto it = cache().live.find(dev);
+    if (it == cache().live.end()) {
+        // a block of another device's cache (freed from a thread bound elsewhere): give it straight back to the driver
+        for (int d = 0; d < FM_MAX_DEVICES; ++d) {
+            BlockCache &other = g_cache_pd.v[d];
+            auto jt = other.live.find(dev);
+            if (&other == &cache() || jt == other.live.end()) continue;
+            if (jt->second.freed) cudaEventDestroy(jt->second.freed);
+            other.live.erase(jt);
+            break;
+        }
+        FM_CUDA(cudaFree(dev));  // not ours at all (or freed twice): plain cudaFree reports the error
         return FM_OK;
     }
     Block blk = it->second;
-    g_cache.live.erase(it);
-    if (g_xfer.stream) {
+    cache().live.erase(it);
+    if (xfer().stream) {
         // a transfer may still be reading or writing the block: whatever reuses it on the compute stream comes after the transfers
-        if (g_xfer.dirty) FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.last, 0));
+        if (xfer().dirty) FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().last, 0));
         // and a later asynchronous upload into the recycled block must wait for the kernels queued up to now
         if (!blk.freed) FM_CUDA(cudaEventCreateWithFlags(&blk.freed, cudaEventDisableTiming));
-        FM_CUDA(cudaEventRecord(blk.freed, g_ctx.stream));
+        FM_CUDA(cudaEventRecord(blk.freed, ctx().stream));
     }
-    if (g_cache.cached_bytes + blk.bytes > g_cache.limit()) {
+    if (cache().cached_bytes + blk.bytes > cache().limit()) {
         if (blk.freed) cudaEventDestroy(blk.freed);
         FM_CUDA(cudaFree(dev));
         return FM_OK;
     }
-    g_cache.free_blocks.emplace(blk.bytes, std::make_pair(dev, blk));
-    g_cache.cached_bytes += blk.bytes;
+    cache().free_blocks.emplace(blk.bytes, std::make_pair(dev, blk));
+    cache().cached_bytes += blk.bytes;
     return FM_OK;
 }
 int fm_trim_cache(void) {
     FM_TRY(ensure_init());
-    g_cache.trim();
+    cache().trim();
     return FM_OK;
 }
 int fm_upload(double *dev, int ldd, const double *host, int ldh, int m, int n) {
     FM_TRY(ensure_init());
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_upload: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
-    return copy_h2d(dev, ldd, host, ldh, m, n, g_ctx.stream);  // pageable host memory is staged by the library's own copy threads
+    return copy_h2d(dev, ldd, host, ldh, m, n, ctx().stream);  // pageable host memory is staged by the library's own copy threads
 }
 int fm_download(double *host, int ldh, const double *dev, int ldd, int m, int n) {
     FM_TRY(ensure_init());
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
-    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     return FM_OK;
 }
 // Asynchronous transfers on the library's transfer stream.  Upload: the copy may run while kernels queued BEFORE the call are still
@@ -290,17 +322,17 @@ int fm_upload_async(double *dev, int ldd, const double *host, int ldh, int m, in
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_upload_async: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
     FM_TRY(xfer_init());
-    Block *blk = g_cache.find(dev);
+    Block *blk = cache().find(dev);
     if (blk && blk->freed) {
-        FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, blk->freed, 0));
+        FM_CUDA(cudaStreamWaitEvent(xfer().stream, blk->freed, 0));
     } else if (!blk || !blk->fresh) {  // unknown history: behind everything queued so far
-        FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
-        FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
+        FM_CUDA(cudaEventRecord(xfer().tmp, ctx().stream));
+        FM_CUDA(cudaStreamWaitEvent(xfer().stream, xfer().tmp, 0));
     }
-    FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ldd * 8, host, (size_t)ldh * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, g_xfer.stream));
-    FM_CUDA(cudaEventRecord(g_xfer.last, g_xfer.stream));
-    FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.last, 0));
-    g_xfer.dirty = true;
+    FM_CUDA(cudaMemcpy2DAsync(dev, (size_t)ldd * 8, host, (size_t)ldh * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, xfer().stream));
+    FM_CUDA(cudaEventRecord(xfer().last, xfer().stream));
+    FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().last, 0));
+    xfer().dirty = true;
     return FM_OK;
 }
 int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, int n) {
@@ -308,57 +340,57 @@ int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, 
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download_async: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
     FM_TRY(xfer_init());
-    FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
-    FM_CUDA(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
-    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, g_xfer.stream));
-    FM_CUDA(cudaEventRecord(g_xfer.last, g_xfer.stream));
-    g_xfer.dirty = true;
+    FM_CUDA(cudaEventRecord(xfer().tmp, ctx().stream));
+    FM_CUDA(cudaStreamWaitEvent(xfer().stream, xfer().tmp, 0));
+    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, xfer().stream));
+    FM_CUDA(cudaEventRecord(xfer().last, xfer().stream));
+    xfer().dirty = true;
     return FM_OK;
 }
 }  // extern "C"
 namespace fm {
 int download_behind_compute(double *host, size_t ldh, const double *dev, size_t ldd, size_t m, size_t n, bool last) {
     FM_TRY(xfer_init());
-    FM_CUDA(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
-    FM_CUDA(cudaStreamWaitEvent(g_xfer.down, g_xfer.tmp, 0));
-    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, g_xfer.down));
+    FM_CUDA(cudaEventRecord(xfer().tmp, ctx().stream));
+    FM_CUDA(cudaStreamWaitEvent(xfer().down, xfer().tmp, 0));
+    FM_TRY(copy_d2h(host, ldh, dev, ldd, m, n, xfer().down));
     if (last) {
-        FM_CUDA(cudaEventRecord(g_xfer.tmp, g_xfer.down));
-        FM_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_xfer.tmp, 0));
+        FM_CUDA(cudaEventRecord(xfer().tmp, xfer().down));
+        FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().tmp, 0));
     }
-    g_xfer.dirty = true;
+    xfer().dirty = true;
     return FM_OK;
 }
 }  // namespace fm
 extern "C" {
 int fm_transfer_sync(void) {
     FM_TRY(ensure_init());
-    if (g_xfer.stream) FM_CUDA(cudaStreamSynchronize(g_xfer.stream));
-    if (g_xfer.down) FM_CUDA(cudaStreamSynchronize(g_xfer.down));
-    g_xfer.dirty = false;
+    if (xfer().stream) FM_CUDA(cudaStreamSynchronize(xfer().stream));
+    if (xfer().down) FM_CUDA(cudaStreamSynchronize(xfer().down));
+    xfer().dirty = false;
     return FM_OK;
 }
 int fm_get(const double *dev, size_t index, double *out) {
     FM_TRY(ensure_init());
-    FM_CUDA(cudaMemcpyAsync(out, dev + index, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    FM_CUDA(cudaMemcpyAsync(out, dev + index, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     return FM_OK;
 }
 int fm_set(double *dev, size_t index, double value) {
     FM_TRY(ensure_init());
-    FM_CUDA(cudaMemcpyAsync(dev + index, &value, sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    FM_CUDA(cudaMemcpyAsync(dev + index, &value, sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     return FM_OK;
 }
 int fm_upload_i32(int32_t *dev, const int32_t *host, size_t n) {
     FM_TRY(ensure_init());
-    FM_CUDA(cudaMemcpyAsync(dev, host, n * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    FM_CUDA(cudaMemcpyAsync(dev, host, n * 4, cudaMemcpyHostToDevice, ctx().stream));
     return FM_OK;
 }
 int fm_download_i32(int32_t *host, const int32_t *dev, size_t n) {
     FM_TRY(ensure_init());
-    FM_CUDA(cudaMemcpyAsync(host, dev, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    FM_CUDA(cudaMemcpyAsync(host, dev, n * 4, cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     return FM_OK;
 }
 
@@ -379,10 +411,10 @@ int fm_addsub(int m, int n, const double *e, int lde, const double *o, int ldo, 
 
 int fm_norm(char type, int m, int n, const double *a, int lda, double *out) {
     FM_TRY(ensure_init());
-    FM_TRY(k_norm_device(type, m, n, a, lda, g_ctx.d_scalar));
-    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
-    *out = g_ctx.h_scalar[0];
+    FM_TRY(k_norm_device(type, m, n, a, lda, ctx().d_scalar));
+    FM_CUDA(cudaMemcpyAsync(ctx().h_scalar, ctx().d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = ctx().h_scalar[0];
     return FM_OK;
 }
 
@@ -433,25 +465,36 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
     if (lda < (m > 1 ? m : 1) || ldb < (k > 1 ? k : 1) || ldc < (m > 1 ? m : 1)) return set_error(FM_ERR_ARG, "fm_dgemm_host: leading dimension too small");
     if (m == 0 || n == 0) return FM_OK;
     if (is_device_ptr(a) || is_device_ptr(b) || is_device_ptr(c)) return set_error(FM_ERR_ARG, "fm_dgemm_host: operands must be host memory (use fm_dgemm)");
+    return dgemm_host_pipeline(m, n, k, alpha, a, lda, nullptr, 0, b, ldb, beta, c, ldc, async);
+}
+}  // extern "C"
+namespace fm {
+int xfer_streams(cudaStream_t *up, cudaStream_t *down) {
     FM_TRY(xfer_init());
-    const int ldda = m + (m & 1) < 2 ? 2 : m + (m & 1), lddb = k + (k & 1) < 2 ? 2 : k + (k & 1), lddc = ldda;
-    double *da = k > 0 ? static_cast<double *>(fm_alloc_bytes((size_t)ldda * k * 8)) : nullptr;
+    if (up) *up = xfer().stream;
+    if (down) *down = xfer().down;
+    xfer().dirty = true;  // the caller is about to use them: fm_free / fm_transfer_sync must take them into account
+    return FM_OK;
+}
+// The column-block pipeline behind fm_dgemm_host.  a_dev != nullptr: A is already (or will be, by work queued on the UPLOAD stream)
+// resident at a_dev with leading dimension ldda -- fm_mg_dgemm assembles it there over PCIe + NVLink -- and a_host is not read.
+int dgemm_host_pipeline(int m, int n, int k, double alpha, const double *a, int lda, const double *a_dev, int ldda_in, const double *b, int ldb,
+                        double beta, double *c, int ldc, int async) {
+    FM_TRY(xfer_init());
+    const int ldda = a_dev ? ldda_in : (m + (m & 1) < 2 ? 2 : m + (m & 1)), lddb = k + (k & 1) < 2 ? 2 : k + (k & 1);
+    const int lddc = m + (m & 1) < 2 ? 2 : m + (m & 1);
+    double *da = a_dev ? const_cast<double *>(a_dev) : (k > 0 ? static_cast<double *>(fm_alloc_bytes((size_t)ldda * k * 8)) : nullptr);
     double *db = k > 0 ? static_cast<double *>(fm_alloc_bytes((size_t)lddb * n * 8)) : nullptr;
     double *dc = static_cast<double *>(fm_alloc_bytes((size_t)lddc * n * 8));
     int rc = FM_OK;
     if ((k > 0 && (!da || !db)) || !dc) rc = FM_ERR_NOMEM;
     int cw = 0, nchunks = 0;
-    fm_dgemm_host_plan(m, n, g_ctx.sm_count, &cw, &nchunks);
-    static std::vector<cudaEvent_t> ev;  // [2j] block j uploaded, [2j+1] block j computed
-    static int ev_device = -1;
-    if (ev_device != g_ctx.device) {  // events belong to the device that was current when they were created
-        for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        ev.clear();
-        ev_device = g_ctx.device;
-    }
+    fm_dgemm_host_plan(m, n, ctx().sm_count, &cw, &nchunks);
+    static PerDevice<std::vector<cudaEvent_t>> ev_pd;  // [2j] block j uploaded, [2j+1] block j computed; events belong to their device
+    std::vector<cudaEvent_t> &ev = ev_pd();
     while (rc == FM_OK && (int)ev.size() < 2 * nchunks) {
         cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: event creation failed");
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "dgemm_host_pipeline: event creation failed");
         else ev.push_back(e);
     }
     auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == FM_OK) rc = set_error(FM_ERR_CUDA, "fm_dgemm_host: %s", cudaGetErrorString(e)); };
@@ -465,45 +508,45 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
     }
     if (rc == FM_OK) {
         // the staging blocks may be recycled ones that kernels queued so far still use
-        chk(cudaEventRecord(g_xfer.tmp, g_ctx.stream));
-        chk(cudaStreamWaitEvent(g_xfer.stream, g_xfer.tmp, 0));
-        if (trace) cudaEventRecord(tr[0], g_xfer.stream);
-        if (k > 0 && rc == FM_OK) rc = copy_h2d(da, ldda, a, lda, m, k, g_xfer.stream);
-        if (trace) cudaEventRecord(tr[1], g_xfer.stream);
+        chk(cudaEventRecord(xfer().tmp, ctx().stream));
+        chk(cudaStreamWaitEvent(xfer().stream, xfer().tmp, 0));
+        if (trace) cudaEventRecord(tr[0], xfer().stream);
+        if (k > 0 && rc == FM_OK && !a_dev) rc = copy_h2d(da, ldda, a, lda, m, k, xfer().stream);
+        if (trace) cudaEventRecord(tr[1], xfer().stream);
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
             const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
-            if (k > 0) rc = copy_h2d(db + (size_t)c0 * lddb, lddb, b + (size_t)c0 * ldb, ldb, k, w, g_xfer.stream);
-            if (beta != 0.0 && rc == FM_OK) rc = copy_h2d(dc + (size_t)c0 * lddc, lddc, c + (size_t)c0 * ldc, ldc, m, w, g_xfer.stream);
-            chk(cudaEventRecord(ev[2 * j], g_xfer.stream));
-            chk(cudaStreamWaitEvent(g_ctx.stream, ev[2 * j], 0));
+            if (k > 0) rc = copy_h2d(db + (size_t)c0 * lddb, lddb, b + (size_t)c0 * ldb, ldb, k, w, xfer().stream);
+            if (beta != 0.0 && rc == FM_OK) rc = copy_h2d(dc + (size_t)c0 * lddc, lddc, c + (size_t)c0 * ldc, ldc, m, w, xfer().stream);
+            chk(cudaEventRecord(ev[2 * j], xfer().stream));
+            chk(cudaStreamWaitEvent(ctx().stream, ev[2 * j], 0));
             if (rc != FM_OK) break;
-            if (trace) { cudaEventRecord(tr[2 + 4 * j], g_xfer.stream); cudaEventRecord(tr[3 + 4 * j], g_ctx.stream); }
+            if (trace) { cudaEventRecord(tr[2 + 4 * j], xfer().stream); cudaEventRecord(tr[3 + 4 * j], ctx().stream); }
             GemmEpilogue ep;
             ep.alpha = alpha;
             ep.beta = beta;
             if (k > 0) rc = k_dgemm(FM_NO_TRANS, FM_NO_TRANS, m, w, k, da, ldda, 0, db + (size_t)c0 * lddb, lddb, 0, dc + (size_t)c0 * lddc, lddc, 0, 1, ep);
             else if (beta == 0.0) rc = k_fill(dc + (size_t)c0 * lddc, lddc, m, w, 0.0);  // BLAS: k = 0 leaves C := beta*C (beta = 0: no read of C)
             else rc = k_scal2d(m, w, beta, dc + (size_t)c0 * lddc, lddc);
-            if (rc == FM_OK) chk(cudaEventRecord(ev[2 * j + 1], g_ctx.stream));
-            if (trace) cudaEventRecord(tr[4 + 4 * j], g_ctx.stream);
+            if (rc == FM_OK) chk(cudaEventRecord(ev[2 * j + 1], ctx().stream));
+            if (trace) cudaEventRecord(tr[4 + 4 * j], ctx().stream);
         }
         // downloads are queued after every upload: a copy to pageable memory blocks the host until it has run
         for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
             const int c0 = j * cw, w = (j == nchunks - 1) ? n - c0 : cw;
-            chk(cudaStreamWaitEvent(g_xfer.down, ev[2 * j + 1], 0));
-            if (rc == FM_OK) rc = copy_d2h(c + (size_t)c0 * ldc, ldc, dc + (size_t)c0 * lddc, lddc, m, w, g_xfer.down);
-            if (trace) cudaEventRecord(tr[5 + 4 * j], g_xfer.down);
+            chk(cudaStreamWaitEvent(xfer().down, ev[2 * j + 1], 0));
+            if (rc == FM_OK) rc = copy_d2h(c + (size_t)c0 * ldc, ldc, dc + (size_t)c0 * lddc, lddc, m, w, xfer().down);
+            if (trace) cudaEventRecord(tr[5 + 4 * j], xfer().down);
         }
         // whatever reuses the staging blocks (compute stream) comes after the last download
-        chk(cudaEventRecord(g_xfer.tmp, g_xfer.down));
-        chk(cudaStreamWaitEvent(g_ctx.stream, g_xfer.tmp, 0));
-        chk(cudaEventRecord(g_xfer.last, g_xfer.stream));
-        g_xfer.dirty = true;
+        chk(cudaEventRecord(xfer().tmp, xfer().down));
+        chk(cudaStreamWaitEvent(ctx().stream, xfer().tmp, 0));
+        chk(cudaEventRecord(xfer().last, xfer().stream));
+        xfer().dirty = true;
     }
     if (rc != FM_OK || !async) {
-        cudaStreamSynchronize(g_xfer.stream);
-        cudaStreamSynchronize(g_ctx.stream);
-        cudaStreamSynchronize(g_xfer.down);
+        cudaStreamSynchronize(xfer().stream);
+        cudaStreamSynchronize(ctx().stream);
+        cudaStreamSynchronize(xfer().down);
     }
     if (trace) {
         auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0], tr[i]); return ms; };
@@ -513,11 +556,13 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
             fprintf(stderr, "[fm_dgemm_host] %5d  %8.2f  %13.2f  %12.2f  %10.2f\n", j, at(2 + 4 * j), at(3 + 4 * j), at(4 + 4 * j), at(5 + 4 * j));
         for (auto &e : tr) cudaEventDestroy(e);
     }
-    if (da) fm_free(da);
+    if (da && !a_dev) fm_free(da);
     if (db) fm_free(db);
     if (dc) fm_free(dc);
     return rc;
 }
+}  // namespace fm
+extern "C" {
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta, double *c, int ldc,
                   double diag) {
     FM_TRY(ensure_init());
@@ -550,9 +595,9 @@ int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, do
 }
 // one device int32 to the host (syncs the library stream)
 static int read_i32(const int32_t *dev, int32_t *out) {
-    int32_t *h = reinterpret_cast<int32_t *>(g_ctx.h_scalar + 32);
-    FM_CUDA(cudaMemcpyAsync(h, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    int32_t *h = reinterpret_cast<int32_t *>(ctx().h_scalar + 32);
+    FM_CUDA(cudaMemcpyAsync(h, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
     *out = *h;
     return FM_OK;
 }
@@ -570,9 +615,9 @@ int fm_gesv(int n, int nrhs, double *a, int lda, int32_t *ipiv, double *b, int l
 int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
     FM_TRY(ensure_init());
     if (n < 0 || lda < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "fm_getri: bad dimensions");
-    int32_t *d_info = info ? info : reinterpret_cast<int32_t *>(g_ctx.d_scalar + 16);
+    int32_t *d_info = info ? info : reinterpret_cast<int32_t *>(ctx().d_scalar + 16);
     if (n == 0) {
-        if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), g_ctx.stream));
+        if (info) FM_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), ctx().stream));
         return FM_OK;
     }
     // LAPACK's dgetri (through dtrtri) returns info = i for an exactly zero U(i,i) before any work: A stays the LU factors, which
@@ -585,10 +630,10 @@ int fm_getri(int n, double *a, int lda, const int32_t *ipiv, int32_t *info) {
 }
 int fm_det(int n, const double *lu, int lda, const int32_t *ipiv, double *out) {
     FM_TRY(ensure_init());
-    FM_TRY(k_det_device(n, lu, lda, ipiv, g_ctx.d_scalar));
-    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
-    *out = g_ctx.h_scalar[0];
+    FM_TRY(k_det_device(n, lu, lda, ipiv, ctx().d_scalar));
+    FM_CUDA(cudaMemcpyAsync(ctx().h_scalar, ctx().d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = ctx().h_scalar[0];
     return FM_OK;
 }
 
@@ -618,28 +663,28 @@ int fm_gemv(int trans, int m, int n, double alpha, const double *a, int lda, con
     return k_gemv(trans == FM_TRANS, m, n, alpha, a, lda, x, incx, beta, y, incy);
 }
 static int scalar_back(double *out) {
-    FM_CUDA(cudaMemcpyAsync(g_ctx.h_scalar, g_ctx.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
-    FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
-    *out = g_ctx.h_scalar[0];
+    FM_CUDA(cudaMemcpyAsync(ctx().h_scalar, ctx().d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    FM_CUDA(cudaStreamSynchronize(ctx().stream));
+    *out = ctx().h_scalar[0];
     return FM_OK;
 }
 int fm_dot(int n, const double *x, int incx, const double *y, int incy, double *out) {
     FM_TRY(ensure_init());
     if (incx < 0 || incy < 0) return set_error(FM_ERR_ARG, "fm_dot: negative increments are not used by flomat and not supported");
-    FM_TRY(k_dot_device(n, x, incx, y, incy, g_ctx.d_scalar));
+    FM_TRY(k_dot_device(n, x, incx, y, incy, ctx().d_scalar));
     return scalar_back(out);
 }
 int fm_nrm2(int n, const double *x, int incx, double *out) {
     FM_TRY(ensure_init());
     if (incx <= 0) { *out = 0.0; return FM_OK; }
-    FM_TRY(k_nrm2_device(n, x, incx, g_ctx.d_scalar));
+    FM_TRY(k_nrm2_device(n, x, incx, ctx().d_scalar));
     return scalar_back(out);
 }
 int fm_iamax(int n, const double *x, int incx, int *out) {
     FM_TRY(ensure_init());
     *out = 0;
     if (n <= 0 || incx <= 0) return FM_OK;
-    FM_TRY(k_iamax_device(n, x, incx, reinterpret_cast<long long *>(g_ctx.d_scalar)));
+    FM_TRY(k_iamax_device(n, x, incx, reinterpret_cast<long long *>(ctx().d_scalar)));
     double raw;
     FM_TRY(scalar_back(&raw));
     long long idx;
@@ -769,7 +814,7 @@ void cblas_dgemm(int order, int transA, int transB, int M, int N, int K, double 
             rc = k_dgemm(transA, transB, M, N, K, a.dev, a.ld, 0, b.dev, b.ld, 0, c.dev, c.ld, 0, 1, ep);
         }
         if (rc == FM_OK) rc = c.out();
-        if (rc == FM_OK && c.owned && cudaStreamSynchronize(g_ctx.stream) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "cblas_dgemm: sync failed");
+        if (rc == FM_OK && c.owned && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "cblas_dgemm: sync failed");
     }
     report("cblas_dgemm", rc);
 }
@@ -794,9 +839,9 @@ struct StagedVec {
             const long long ainc = incp < 0 ? -(long long)incp : incp;
             const double *start = host;  // BLAS: negative inc walks backwards from (1-n)*inc
             if (ainc <= 1) {
-                FM_CUDA(cudaMemcpyAsync(dev, start, (size_t)len * 8, cudaMemcpyHostToDevice, g_ctx.stream));
+                FM_CUDA(cudaMemcpyAsync(dev, start, (size_t)len * 8, cudaMemcpyHostToDevice, ctx().stream));
             } else {
-                FM_CUDA(cudaMemcpy2DAsync(dev, 8, start, (size_t)ainc * 8, 8, len, cudaMemcpyHostToDevice, g_ctx.stream));
+                FM_CUDA(cudaMemcpy2DAsync(dev, 8, start, (size_t)ainc * 8, 8, len, cudaMemcpyHostToDevice, ctx().stream));
             }
         }
         return FM_OK;
@@ -805,12 +850,12 @@ struct StagedVec {
         if (!owned) return FM_OK;
         const long long ainc = inch < 0 ? -(long long)inch : inch;
         const int len = (inch == 0) ? 1 : n;  // as staged by in(): a stride-0 vector is one element
-        if (ainc <= 1) FM_CUDA(cudaMemcpyAsync(host, dev, (size_t)len * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-        else FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ainc * 8, dev, 8, 8, len, cudaMemcpyDeviceToHost, g_ctx.stream));
-        FM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        if (ainc <= 1) FM_CUDA(cudaMemcpyAsync(host, dev, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx().stream));
+        else FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ainc * 8, dev, 8, 8, len, cudaMemcpyDeviceToHost, ctx().stream));
+        FM_CUDA(cudaStreamSynchronize(ctx().stream));
         return FM_OK;
     }
-    ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(g_ctx.stream); fm_free(dev); } }
+    ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(ctx().stream); fm_free(dev); } }
 };
 
 void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY) {
@@ -1032,7 +1077,7 @@ void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *i
         if (rc == FM_OK) rc = A.out();
         if (rc == FM_OK && hinfo == 0) rc = B.out();
         if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)*n);
-        if (rc == FM_OK) { cudaStreamSynchronize(g_ctx.stream); *info = hinfo; }
+        if (rc == FM_OK) { cudaStreamSynchronize(ctx().stream); *info = hinfo; }
         if (ipiv_dev) { if (d_info) fm_free(d_info); } else if (d_ipiv) fm_free(d_ipiv);
     }
     report("dgesv_", rc);
@@ -1066,7 +1111,7 @@ void dgetri_(const int *n, double *a, const int *lda, const int32_t *ipiv, doubl
         if (rc == FM_OK) *info = hinfo;
         if (d_info) fm_free(d_info);
         if (rc == FM_OK && *info == 0) rc = A.out();
-        if (rc == FM_OK) cudaStreamSynchronize(g_ctx.stream);
+        if (rc == FM_OK) cudaStreamSynchronize(ctx().stream);
         if (!ipiv_dev && d_ipiv) fm_free(d_ipiv);
     }
     report("dgetri_", rc);

@@ -14,6 +14,11 @@
 
 namespace fm {
 
+constexpr int FM_MAX_DEVICES = 16;
+
+// One Context per CUDA device.  A host thread is bound to one device at a time (fm_init, or the default device on its first call);
+// ctx() is the bound device's context.  Calls that target the same device must be serialised by the caller (the reference
+// calls from one OS thread); the single-process multi-GPU entry points (fm_mg_*, mg.cu) drive every device from its own worker thread.
 struct Context {
     bool ready = false;
     int device = -1;
@@ -31,6 +36,22 @@ struct Context {
 Context &ctx();
 int set_error(int code, const char *fmt, ...);
 int ensure_init();
+int bind_device(int device);  // bind the calling thread to `device` (cudaSetDevice + context creation on first use)
+int bound_device();           // the calling thread's device, -1 if it has none yet
+unsigned long long launches_of_device(int d);
+const char *error_text();     // the calling thread's last error message
+bool is_device_pointer(const void *p, int *device_out);  // device (or managed) memory? and on which device
+int xfer_streams(cudaStream_t *up, cudaStream_t *down);  // the bound device's transfer streams (created on first use)
+int dgemm_host_pipeline(int m, int n, int k, double alpha, const double *a_host, int lda, const double *a_dev, int ldda, const double *b,
+                        int ldb, double beta, double *c, int ldc, int async);
+
+// state that exists once per device (kernel attributes, workspaces, event pools ...): `static PerDevice<T> x;  x()` is the slot of the
+// calling thread's device
+template <class T>
+struct PerDevice {
+    T v[FM_MAX_DEVICES]{};
+    T &operator()() { const int d = ctx().device; return v[d < 0 ? 0 : d]; }
+};
 void *scratch(size_t bytes);  // returns nullptr + sets error on failure
 
 inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }

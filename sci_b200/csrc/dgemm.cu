@@ -596,10 +596,10 @@ using CfgHalf = GemmCfg<64, 128, 16, 1, 4, 4, 2>;
 template <class Cfg>
 int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
                long long sc, int batch, const EpiParams &ep, int max_sms) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<bool> attr_set;  // function attributes are per device
+    if (!attr_set()) {
         FM_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set() = true;
     }
     CUtensorMap tmA, tmB;
     FM_TRY(make_map(&tmA, a, m, k, lda, sa, batch, 16, Cfg::BK));
@@ -698,15 +698,16 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
         if (epi.dynamic_tiles && g_dynamic_enabled && !epi.active_until) {
             // a ring of counters: this launch draws from slot i and clears slot i + 32 for a launch far in the future (at most a
             // couple of GEMMs are ever in flight at once)
-            static int *d_counters = nullptr;
-            static unsigned seq = 0;
-            if (!d_counters) {
-                FM_CUDA(cudaMalloc(&d_counters, 64 * sizeof(int)));
-                FM_CUDA(cudaMemsetAsync(d_counters, 0, 64 * sizeof(int), ctx().stream));
+            struct Counters { int *dev = nullptr; unsigned seq = 0; };
+            static PerDevice<Counters> counters;
+            Counters &cn = counters();
+            if (!cn.dev) {
+                FM_CUDA(cudaMalloc(&cn.dev, 64 * sizeof(int)));
+                FM_CUDA(cudaMemsetAsync(cn.dev, 0, 64 * sizeof(int), ctx().stream));
             }
-            ep.tile_counter = d_counters + (seq % 64);
-            ep.counter_to_clear = d_counters + ((seq + 32) % 64);
-            ++seq;
+            ep.tile_counter = cn.dev + (cn.seq % 64);
+            ep.counter_to_clear = cn.dev + ((cn.seq + 32) % 64);
+            ++cn.seq;
         }
         if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
         return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);

@@ -44,7 +44,7 @@ struct Pool {
         return buf[slot];
     }
 };
-Pool g_pool;
+PerDevice<Pool> g_pool_pd;
 
 // out_z := (s_z is odd ? b1_z : b0_z)   -- collects each item's result from the ping-pong buffer it ended in
 __global__ void __launch_bounds__(256) select_copy_kernel(int n, const double *b0, const double *b1, long long ldw, long long sw,
@@ -75,23 +75,24 @@ struct InfoBack {
     int cap = 0;
     cudaEvent_t ready = nullptr;
 };
-InfoBack g_info;
+PerDevice<InfoBack> g_info_pd;
 
 int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host,
                   bool host_out = false, bool honour_singular = false) {
     const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
     cudaStream_t st = ctx().stream;
+    InfoBack &g_info = g_info_pd();
     const int ldw = n + (n & 1);
     const long long sw = (long long)ldw * n;
     const size_t mat_bytes = (size_t)sw * batch * sizeof(double);
     double *B[6];
     for (int i = 0; i < 6; ++i) {
-        B[i] = static_cast<double *>(g_pool.get(i, mat_bytes));
+        B[i] = static_cast<double *>(g_pool_pd().get(i, mat_bytes));
         if (!B[i]) return FM_ERR_NOMEM;
     }
     // small arrays: norms | scales (doubles), rounds | ipiv | info (int32)
     const size_t small_bytes = (size_t)batch * (2 * sizeof(double) + 2 * sizeof(int32_t)) + (size_t)batch * n * sizeof(int32_t) + 64;
-    char *small = static_cast<char *>(g_pool.get(6, small_bytes));
+    char *small = static_cast<char *>(g_pool_pd().get(6, small_bytes));
     if (!small) return FM_ERR_NOMEM;
     double *d_norm = reinterpret_cast<double *>(small);
     double *d_scale = d_norm + batch;
@@ -263,6 +264,7 @@ namespace {
 int expm_checked(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out,
                  bool host_out, int32_t *info_host) {
     FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false));
+    InfoBack &g_info = g_info_pd();
     FM_CUDA(cudaEventSynchronize(g_info.ready));
     int32_t first = 0;
     for (int z = 0; z < batch && first == 0; ++z) first = g_info.h[z];

@@ -1509,7 +1509,7 @@ struct MapPool {
         return buf;
     }
 };
-MapPool g_maps_getrf, g_maps_getrs;
+PerDevice<MapPool> g_maps_getrf, g_maps_getrs;
 
 struct Maps {
     int2 *base;
@@ -1522,7 +1522,8 @@ constexpr int panel_dyn_smem() { return (2 * LEAF * UP + (MINB == 1 ? NT * RPT *
 
 template <int NT, int RPT, int MINB = 1>
 int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize) {
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    bool &attr = attr_pd();
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_dyn_smem<NT, RPT, MINB>()));
@@ -1628,7 +1629,8 @@ int permute_rows(const Mat &A, int c0, int ncols, const Maps &maps, int p0, int 
 
 template <bool UPPER, int CPT, bool RSIDE = false>
 int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    bool &attr = attr_pd();
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel<UPPER, CPT, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<CPT>()));
         attr = true;
@@ -1646,7 +1648,8 @@ int trsm_leaf_launch(int nb, int ncols, const double *T, int ldt, long long st, 
 
 template <bool UPPER, bool RSIDE>
 int trsm_leaf_dmma_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    bool &attr = attr_pd();
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(trsm_leaf_dmma_kernel<UPPER, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM));
         attr = true;
@@ -1662,7 +1665,8 @@ int trsm_leaf_dmma_launch(int nb, int ncols, const double *T, int ldt, long long
 
 template <bool UPPER, bool RSIDE>
 int trsm_leaf_cols_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    bool &attr = attr_pd();
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(trsm_leaf_cols_kernel<UPPER, RSIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         attr = true;
@@ -1722,18 +1726,19 @@ int trsm_wave(int w, int ncols, const double *T, int ldt, double *B, int ldb, bo
     static const bool no_pair = getenv("FLOMAT_TRSM_WAVE_NO_PAIR") != nullptr;  // developer switch: four unpaired warps
     const bool narrow = !wide_only && (long long)nblk * ceil_div(ncols, 32) <= ctx().sm_count;
     const int cchunks = ceil_div(ncols, narrow ? 32 : 64);
-    static int *d_flags = nullptr;
-    static int epoch = 0;
+    struct Flags { int *dev = nullptr; int epoch = 0; };
+    static PerDevice<Flags> flags_pd;
+    int *&d_flags = flags_pd().dev;
+    int &epoch = flags_pd().epoch;
     const int nflags = 4096;
     if ((long long)nblk * cchunks > ctx().sm_count || nblk * cchunks > nflags) return FM_OK;
-    static int flags_device = -1;
-    if (!d_flags || flags_device != ctx().device) {  // (the flags of a previously used device are left to that context)
+    if (!d_flags) {
         FM_CUDA(cudaMalloc(&d_flags, nflags * sizeof(int)));
         FM_CUDA(cudaMemsetAsync(d_flags, 0, nflags * sizeof(int), ctx().stream));
-        flags_device = ctx().device;
         epoch = 0;
     }
-    static bool attr = false;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    bool &attr = attr_pd();
     if (!attr) {
         FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
         FM_CUDA(cudaFuncSetAttribute(trsm_wave_kernel<UPPER, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
@@ -2060,7 +2065,7 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     const int npanels = ceil_div(mn, NB);
     Maps maps;
     maps.item_stride = (long long)npanels * MAPN;
-    maps.base = g_maps_getrf.get((size_t)maps.item_stride * batch);
+    maps.base = g_maps_getrf().get((size_t)maps.item_stride * batch);
     if (!maps.base) return FM_ERR_NOMEM;
     static const bool recursive = getenv("FLOMAT_LU_RECURSIVE") != nullptr;  // developer switch: DGETRF2-style recursion
     if (!recursive) return getrf_lookahead(A, m, n, ipiv, sp, info, maps);
@@ -2080,7 +2085,7 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
     const int nblocks = ceil_div(n, NB);
     Maps maps;
     maps.item_stride = (long long)nblocks * MAPN;
-    maps.base = g_maps_getrs.get((size_t)maps.item_stride * batch);
+    maps.base = g_maps_getrs().get((size_t)maps.item_stride * batch);
     if (!maps.base) return FM_ERR_NOMEM;
     ipiv_to_maps_kernel<<<dim3(nblocks, batch), 32, 0, ctx().stream>>>(n, ipiv, sp, maps.base, maps.item_stride, 0, 0);
     FM_LAUNCH_CHECK();
@@ -2104,7 +2109,8 @@ int k_getri(int n, double *a, int lda, const int32_t *ipiv) {
     if (rc == FM_OK) rc = rtrsm<true>(n, n, a, lda, 0, x, ldx, 0, 1);
     if (rc == FM_OK) {
         if ((size_t)n * 8 <= (size_t)ctx().max_smem_optin) {
-            static bool attr = false;
+            static PerDevice<bool> attr_pd;
+            bool &attr = attr_pd();
             if (!attr) {
                 cudaFuncSetAttribute(perm_forward_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx().max_smem_optin);
                 attr = true;

@@ -41,6 +41,7 @@ class CopyPool {
             for (int p = 0; p < parts; ++p) f(p);
             return;
         }
+        std::lock_guard<std::mutex> one_job(run_mu_);  // one job slot: callers on different devices (fm_mg_* worker threads) take turns
         {
             std::lock_guard<std::mutex> lk(mu_);
             job_ = &f;
@@ -93,6 +94,7 @@ class CopyPool {
         }
     }
     const int n_;
+    std::mutex run_mu_;
     std::mutex mu_;
     std::condition_variable cv_, done_;
     const std::function<void(int)> *job_ = nullptr;
@@ -114,23 +116,24 @@ CopyPool &pool() {
     return *p;
 }
 
-struct Bounce {
+struct Bounce {  // one ring per device: its events belong to that device and its buffers may be in flight on that device's streams
     double *buf[MAX_BOUNCE] = {};
     cudaEvent_t ev[MAX_BOUNCE] = {};
     bool busy[MAX_BOUNCE] = {};
-    int device = -1;
+    int next = 0;  // keeps rotating across calls: back-to-back uploads of small blocks do not all wait on buffer 0
+    bool ready = false;
 };
-Bounce g_b;
+PerDevice<Bounce> g_bounce;
 
 int bounce_init() {
-    if (g_b.buf[0] && g_b.device == ctx().device) return FM_OK;
+    Bounce &g_b = g_bounce();
+    if (g_b.ready) return FM_OK;
     for (int i = 0; i < NBOUNCE; ++i) {
         if (!g_b.buf[i]) FM_CUDA(cudaMallocHost(&g_b.buf[i], BOUNCE_BYTES));
-        if (g_b.ev[i]) cudaEventDestroy(g_b.ev[i]);  // events belong to the device they were created on
-        FM_CUDA(cudaEventCreateWithFlags(&g_b.ev[i], cudaEventDisableTiming));
+        if (!g_b.ev[i]) FM_CUDA(cudaEventCreateWithFlags(&g_b.ev[i], cudaEventDisableTiming));
         g_b.busy[i] = false;
     }
-    g_b.device = ctx().device;
+    g_b.ready = true;
     return FM_OK;
 }
 
@@ -182,10 +185,10 @@ int copy_h2d(double *dev, size_t ldd, const double *host, size_t ldh, size_t m, 
         return FM_OK;
     }
     FM_TRY(bounce_init());
+    Bounce &g_b = g_bounce();
     const size_t per = BOUNCE_BYTES / (m * sizeof(double));
-    static int next_buffer = 0;  // keeps rotating across calls: back-to-back uploads of small blocks do not all wait on buffer 0
-    int b = next_buffer;
-    for (size_t c0 = 0; c0 < n; c0 += per, b = (b + 1) % NBOUNCE, next_buffer = b) {
+    int b = g_b.next;
+    for (size_t c0 = 0; c0 < n; c0 += per, b = (b + 1) % NBOUNCE, g_b.next = b) {
         const size_t nc = n - c0 < per ? n - c0 : per;
         if (g_b.busy[b]) FM_CUDA(cudaEventSynchronize(g_b.ev[b]));
         host_pack(g_b.buf[b], host, ldh, m, c0, nc, true);
@@ -205,6 +208,7 @@ int copy_d2h(double *host, size_t ldh, const double *dev, size_t ldd, size_t m, 
         return FM_OK;
     }
     FM_TRY(bounce_init());
+    Bounce &g_b = g_bounce();
     const size_t per = BOUNCE_BYTES / (m * sizeof(double));
     const size_t nchunks = (n + per - 1) / per;
     auto issue = [&](size_t i) -> int {

@@ -786,3 +786,53 @@ def sync() -> None:
 def transfer_sync() -> None:
     """Wait for the asynchronous uploads / downloads issued so far (Flomat.upload_async / download_async)."""
     check(_L().fm_transfer_sync(), "fm_transfer_sync")
+
+
+# --------------------------------------------------------------------------------------------------
+# all devices of the box from ONE process and ONE calling thread (include/flomat_cuda.h, tier 3b): the form `flomat*` can use
+# --------------------------------------------------------------------------------------------------
+def mg_init(ndev: int = 0) -> int:
+    """Start the device group (one worker thread per device, peer access between all pairs); returns the number of devices."""
+    check(_L().fm_mg_init(int(ndev)), "fm_mg_init")
+    return _L().fm_mg_device_count()
+
+
+def mg_sync() -> None:
+    check(_L().fm_mg_sync(), "fm_mg_sync")
+
+
+def times_mg(a: Flomat, b: Flomat, c: Flomat | None = None, alpha: float = 1.0, beta: float = 1.0) -> Flomat:
+    """flomat* (flomat.rkt:905) on device-resident matrices, sharded over every device of the group by column blocks of B and C:
+    the other devices fetch A and their block of B over NVLink and write their tiles of C straight into this device's C."""
+    if a.n != b.m:
+        raise ValueError(f"flomat*: expected two matrices with compatible dimensions, got {a.m}x{a.n} and {b.m}x{b.n}")
+    if c is None:
+        c, beta = Flomat.alloc(a.m, b.n), 0.0
+    elif c.m != a.m or c.n != b.n:
+        raise ValueError("flomat*!: result matrix has the wrong dimensions")
+    check(_L().fm_mg_dgemm(NO_TRANS, NO_TRANS, a.m, b.n, a.n, float(alpha), a.a, a.lda, b.a, b.lda, float(beta), c.a, c.lda), "fm_mg_dgemm")
+    return c
+
+
+def times_host_mg(a: np.ndarray, b: np.ndarray, c: np.ndarray | None = None, alpha: float = 1.0, beta: float = 1.0) -> np.ndarray:
+    """flomat* on HOST matrices (what the unmodified reference hands to cblas_dgemm, flomat.rkt:888) over every device of the group:
+    each device uploads its slice of A and its column block of B over its own PCIe link, A is all-gathered over NVLink."""
+    for x in (a, b) + ((c,) if c is not None else ()):
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 2 and x.flags.f_contiguous):
+            raise ValueError("times_host_mg: expected column-major float64 matrices")
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"flomat*: expected two matrices with compatible dimensions, got {a.shape[0]}x{a.shape[1]} and {b.shape[0]}x{b.shape[1]}")
+    m, k, n = a.shape[0], a.shape[1], b.shape[1]
+    if c is None:
+        c, beta = np.empty((m, n), order="F"), 0.0
+    elif c.shape != (m, n):
+        raise ValueError("flomat*!: result matrix has the wrong dimensions")
+    check(_L().fm_mg_dgemm(NO_TRANS, NO_TRANS, m, n, k, float(alpha), a.ctypes.data, max(1, m), b.ctypes.data, max(1, k), float(beta),
+                           c.ctypes.data, max(1, m)), "fm_mg_dgemm")
+    return c
+
+
+def expm_batched_mg(a_ptr: int, n: int, batch: int, out_ptr: int, mode: int = EXPM_REFERENCE_ORDER, s_out: np.ndarray | None = None):
+    """`batch` dense n x n matrices stored back to back at a_ptr (host or this device's memory), one contiguous block per device."""
+    sp = s_out.ctypes.data if s_out is not None else None
+    check(_L().fm_mg_expm_batched(n, a_ptr, n, n * n, out_ptr, n, n * n, batch, int(mode), sp), "fm_mg_expm_batched")

@@ -267,13 +267,33 @@ class ShardedJob:
         h = self._host_buffers()
         if nloc:
             self.check(lib.fm_upload_async(cs.A.data_ptr() + 8 * j0 * n, n, h["a"].data_ptr(), n, n, nloc), "fm_upload_async")
-            self.check(lib.fm_upload_async(cs.B.data_ptr(), n, h["b"].data_ptr(), n, n, nloc), "fm_upload_async")
         if self.world > 1:
             allgather_columns(cs.A, n, n, self.world, self.rank, self.dist)  # A over NVLink instead of `world` times over PCIe
-        cs.step_fused()
+        # the rank's block of B / C in sub-blocks of >= 1024 columns (whole waves of the persistent GEMM): sub-block i+1 goes up and
+        # sub-block i-1 comes down while sub-block i is multiplied
+        nsub = min(4, max(1, nloc // 1024))
+        cuts = [(nloc * i // nsub) // 128 * 128 for i in range(nsub)] + [nloc]
+        subs = [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(nsub) if cuts[i + 1] > cuts[i]]
+        stage = {}
+
+        def up(i):
+            c0, w = subs[i]
+            stage[i] = self.F.Flomat.alloc(n, w)  # a recycled block: the allocator orders the upload behind its last readers
+            self.check(lib.fm_upload_async(stage[i].a, n, h["b"].data_ptr() + 8 * c0 * n, n, n, w), "fm_upload_async")
+
+        if subs:
+            up(0)
+        for i, (c0, w) in enumerate(subs):
+            if i + 1 < len(subs):
+                up(i + 1)
+            self.check(lib.fm_dgemm_colshard(n, w, n, cs.A.data_ptr(), n, stage[i].a, n, cs.c_ptr, n, j0 + c0, cs.peer_array, len(cs.peers)),
+                       "fm_dgemm_colshard")
+            self.check(lib.fm_download_async(h["c"].data_ptr() + 8 * c0 * n, n, cs.c_ptr + 8 * (j0 + c0) * n, n, n, w), "fm_download_async")
+        # (the staging blocks are given back when the step returns: fm_free orders the compute stream behind the transfers in flight,
+        #  which would serialise the next product with this sub-block's download)
+        if self.world > 1:
+            self.dist.all_reduce(cs._sync_token)  # stream-ordered barrier: every peer's stores have landed
         per = self.n_item * self.n_item
-        if nloc:
-            self.check(lib.fm_download_async(h["c"].data_ptr(), n, cs.c_ptr + 8 * j0 * n, n, n, nloc), "fm_download_async")
         if self.nitems:
             x = self.F.Flomat.alloc(per, self.nitems)  # a recycled block: the allocator orders the upload behind its last readers
             self.check(lib.fm_upload_async(x.a, per, h["x"].data_ptr(), per, per, self.nitems), "fm_upload_async")
