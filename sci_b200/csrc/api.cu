@@ -173,7 +173,7 @@ namespace {
 struct Xfer {
     cudaStream_t stream = nullptr;
     cudaStream_t down = nullptr;  // device->host chunks of fm_dgemm_host: a second copy engine beside the uploads on `stream`
-    cudaEvent_t last = nullptr, tmp = nullptr;
+    cudaEvent_t last = nullptr, last_down = nullptr, tmp = nullptr;  // last upload / last download issued; scratch
     bool dirty = false;  // transfers issued since the last fm_transfer_sync
 };
 PerDevice<Xfer> g_xfer_pd;
@@ -221,6 +221,7 @@ int xfer_init() {
     FM_CUDA(cudaStreamCreateWithFlags(&xfer().stream, cudaStreamNonBlocking));
     FM_CUDA(cudaStreamCreateWithFlags(&xfer().down, cudaStreamNonBlocking));
     FM_CUDA(cudaEventCreateWithFlags(&xfer().last, cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&xfer().last_down, cudaEventDisableTiming));
     FM_CUDA(cudaEventCreateWithFlags(&xfer().tmp, cudaEventDisableTiming));
     return FM_OK;
 }
@@ -279,7 +280,10 @@ int fm_free(void *dev) {
     cache().live.erase(it);
     if (xfer().stream) {
         // a transfer may still be reading or writing the block: whatever reuses it on the compute stream comes after the transfers
-        if (xfer().dirty) FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().last, 0));
+        if (xfer().dirty) {
+            FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().last, 0));
+            FM_CUDA(cudaStreamWaitEvent(ctx().stream, xfer().last_down, 0));
+        }
         // and a later asynchronous upload into the recycled block must wait for the kernels queued up to now
         if (!blk.freed) FM_CUDA(cudaEventCreateWithFlags(&blk.freed, cudaEventDisableTiming));
         FM_CUDA(cudaEventRecord(blk.freed, ctx().stream));
@@ -340,10 +344,11 @@ int fm_download_async(double *host, int ldh, const double *dev, int ldd, int m, 
     if (m < 0 || n < 0 || ldd < m || ldh < m) return set_error(FM_ERR_ARG, "fm_download_async: bad dimensions");
     if (m == 0 || n == 0) return FM_OK;
     FM_TRY(xfer_init());
+    // on the DOWNLOAD stream: a download that waits for a kernel must not hold back the uploads queued after it (second copy engine)
     FM_CUDA(cudaEventRecord(xfer().tmp, ctx().stream));
-    FM_CUDA(cudaStreamWaitEvent(xfer().stream, xfer().tmp, 0));
-    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, xfer().stream));
-    FM_CUDA(cudaEventRecord(xfer().last, xfer().stream));
+    FM_CUDA(cudaStreamWaitEvent(xfer().down, xfer().tmp, 0));
+    FM_CUDA(cudaMemcpy2DAsync(host, (size_t)ldh * 8, dev, (size_t)ldd * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, xfer().down));
+    FM_CUDA(cudaEventRecord(xfer().last_down, xfer().down));
     xfer().dirty = true;
     return FM_OK;
 }

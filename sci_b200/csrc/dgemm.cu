@@ -77,6 +77,7 @@ struct EpiParams {
     int *tile_counter;  // non-null: tiles are handed out dynamically (atomic counter) instead of round-robin; see the producer loop
     int *counter_to_clear;  // a counter slot no kernel in flight uses: zeroed for a later launch
     int stagger_ns;  // two CTAs per SM: the second wave of CTAs starts this much later, so that one CTA's epilogue overlaps the other's main loop
+    int copier;      // npeers > 0: the three spare warps of the producer warpgroup forward every finished tile to the peers (see below)
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -112,11 +113,12 @@ struct GemmCfg {
     static constexpr int B_BOX_BYTES = BN * 128;      // one box: BN rows (n) x 16 doubles (k)
     static constexpr int B_STAGE = (BK / 16) * B_BOX_BYTES;
     static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ids*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ids*/ +
+                                      64 /*copier: 4 mbarriers, 2 tile ids (padded)*/;
     static_assert(BK % 16 == 0 && WTM % 16 == 0 && WTN % 8 == 0 && R >= 1 && R <= 4, "tile shape");
 };
 
-template <class Cfg>
+template <class Cfg, bool COPIER = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double *__restrict__ C,
                  long long ldc, long long sc, int M, int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams ep,
@@ -130,10 +132,20 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     const uint32_t tile_slot = bar_base + 16u * STAGES;  // dynamic scheduling: the tile whose FIRST k-step sits in stage s
     const bool dynamic = ep.tile_counter != nullptr;
+    // Fused all-gather (column-sharded multi-GPU product): the consumers store a finished tile to the LOCAL C only and post its id in
+    // a two-slot mailbox; the three spare warps of the producer warpgroup read the tile back (L2 hits) and store it to every peer's
+    // C over NVLink while the consumers are already in the next tile's main loop.  (With the consumers issuing the 7 x 32 remote
+    // stores themselves the DMMA pipe idled while the stores drained: 33.5 instead of 35.9 TFLOP/s per GPU at 8 GPUs.)
+    const uint32_t copy_bar = (tile_slot + 4u * STAGES + 7u) & ~7u;  // full[0], full[1], empty[0], empty[1]
+    const uint32_t copy_tile = copy_bar + 32u;
+    auto copy_full = [&](int s) { return copy_bar + 8u * s; };
+    auto copy_empty = [&](int s) { return copy_bar + 16u + 8u * s; };
+    constexpr bool copier = COPIER;  // a separate instantiation: the plain product keeps its register allocation (168, no spills)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(copy_full(s), NW); mbar_init(copy_empty(s), 3); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -184,6 +196,50 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 tile = dynamic ? atomicAdd(ep.tile_counter, 1) : next;
             }
+        } else if (COPIER && warp > NW) {
+            // ===================== tile forwarding to the peer GPUs =====================
+            const int ct = threadIdx.x - (NW + 1) * 32;  // 0..95
+            constexpr int CH = BM / 2;                    // 16-byte chunks per tile column
+            int slot = 0;
+            uint32_t cph = 0;
+            for (;;) {
+                mbar_wait(copy_full(slot), cph);
+                int tile;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(copy_tile + 4u * slot) : "memory");
+                if (tile < 0) break;
+                int tm, tn, z;
+                decode_tile(tile, tiles_m, tiles_n, tm, tn, z);
+                const long long zoff = z * sc;
+                const int m0 = tm * BM, n0 = tn * BN;
+                if (vec_ok && (M & 1) == 0) {
+#pragma unroll 2
+                    for (int idx = ct; idx < BN * CH; idx += 96) {
+                        const int n = n0 + idx / CH, m = m0 + 2 * (idx % CH);
+                        if (n < N && m < M) {
+                            const long long off = zoff + (long long)n * ldc + m;
+                            const double2 v = __ldcg(reinterpret_cast<const double2 *>(C + off));
+#pragma unroll
+                            for (int r = 0; r < 7; ++r)
+                                if (r < ep.npeers) *reinterpret_cast<double2 *>(ep.peer[r] + off) = v;
+                        }
+                    }
+                } else {
+                    for (int idx = ct; idx < BN * BM; idx += 96) {
+                        const int n = n0 + idx / BM, m = m0 + idx % BM;
+                        if (n < N && m < M) {
+                            const long long off = zoff + (long long)n * ldc + m;
+                            const double v = __ldcg(C + off);
+#pragma unroll
+                            for (int r = 0; r < 7; ++r)
+                                if (r < ep.npeers) ep.peer[r][off] = v;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(copy_empty(slot));
+                slot ^= 1;
+                if (slot == 0) cph ^= 1u;
+            }
         }
         return;
     }
@@ -212,6 +268,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int permg = ((g & 1) << 2) | (g >> 1);
     const uint32_t b_off = (wn0 + permg) * 128 + ((t ^ permg) << 4);
 
+    // what the consumers themselves store to: with the copier warps on duty, the local C only
+    const int npeers_cons = copier ? 0 : ep.npeers;
+    unsigned nposts = 0;  // mailbox slot of the next post = nposts & 1, its phase = (nposts >> 1) & 1
+    auto post = [&](int id) {  // all of this warp's stores of tile `id` are issued: release them to the copier warps
+        __syncwarp();
+        if (lane == 0) {
+            const int cslot = nposts & 1u;
+            mbar_wait(copy_empty(cslot), ((nposts >> 1) & 1u) ^ 1u);  // the copier is done with the tile that used this slot two posts ago
+            if (warp == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(copy_tile + 4u * cslot), "r"(id) : "memory");
+            mbar_arrive(copy_full(cslot));
+        }
+        ++nposts;
+    };
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x;; tile += gridDim.x) {
@@ -288,7 +357,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n_base = tn * BN + wn0;
         double *Cz = C + z * sc + ks * ep.kstride;
         const long long zoff = z * sc;
-        if (vec_ok && ep.npeers == 0 && tm * BM + BM <= M && tn * BN + BN <= N) {
+        if (vec_ok && npeers_cons == 0 && tm * BM + BM <= M && tn * BN + BN <= N) {
             // interior tile, the common case: no bounds, peer or per-element diagonal tests -- ~6 instructions per 16-byte store
             // instead of ~45 (ncu source view, batched 256^3 products: the generic epilogue was 1/3 of the DMMA count in
             // issued instructions and 12% of the consumer warps' time, which two CTAs per SM only partly hide).
@@ -304,6 +373,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int c = 0; c < R; ++c)
                             *reinterpret_cast<double2 *>(q + 2 * c * GPB) = make_double2(ep.alpha * acc[2 * c][ni][x], ep.alpha * acc[2 * c + 1][ni][x]);
                     }
+                if (copier) post(tile);
                 continue;
             }
             const int dm = m_base - (n_base + t);  // element (c, ni, x) sits on the diagonal iff dm + 2*c*GPB == 8*ni + 4*x
@@ -338,6 +408,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 *reinterpret_cast<double2 *>(q + (long long)(8 * d + 4 * x) * ldc + 2 * c * GPB) = make_double2(v0, v1);
                             }
                 }
+                if (copier) post(tile);
                 continue;
             }
             double *q = p0;
@@ -352,6 +423,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const double v1 = fma(ep.alpha, acc[2 * c + 1][ni][x], dm + 1 == off ? dgv : 0.0);
                         *reinterpret_cast<double2 *>(q + (long long)(4 * x) * ldc + 2 * c * GPB) = make_double2(v0, v1);
                     }
+            if (copier) post(tile);
             continue;
         }
         if (vec_ok && (M & 1) == 0) {
@@ -394,10 +466,11 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             *reinterpret_cast<double2 *>(Cz + (long long)n * ldc + m) = make_double2(v0, v1);
 #pragma unroll
                             for (int r = 0; r < 7; ++r)
-                                if (r < ep.npeers)
+                                if (r < npeers_cons)
                                     *reinterpret_cast<double2 *>(ep.peer[r] + zoff + (long long)n * ldc + m) = make_double2(v0, v1);
                         }
             }
+            if (copier) post(tile);
             continue;
         }
 #pragma unroll
@@ -432,14 +505,14 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
 #pragma unroll
                         for (int r = 0; r < 7; ++r)
-                            if (r < ep.npeers)
+                            if (r < npeers_cons)
                                 *reinterpret_cast<double2 *>(ep.peer[r] + zoff + (long long)n * ldc + m) = make_double2(v0, v1);
                     } else {
                         p[0] = v0;
                         if (m + 1 < M) p[1] = v1;
 #pragma unroll
                         for (int r = 0; r < 7; ++r)
-                            if (r < ep.npeers) {
+                            if (r < npeers_cons) {
                                 double *q = ep.peer[r] + zoff + (long long)n * ldc + m;
                                 q[0] = v0;
                                 if (m + 1 < M) q[1] = v1;
@@ -448,7 +521,9 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
+        if (copier) post(tile);
     }
+    if (copier) post(-1);  // end of this CTA's tiles
     // Look-ahead LU launches this kernel as a programmatic dependent of the panel kernel so that both run concurrently.
     // Nothing here reads the panel's output, but kernels launched after this one rely on stream order for BOTH: by waiting
     // for the primary grid before exiting, this grid's completion implies the panel's.
@@ -593,12 +668,12 @@ using CfgBig = GemmCfg<128, 128, 16, 2, 4, 6>;
 // -- the case of the rank-128/256 updates inside LU and the triangular solves.
 using CfgHalf = GemmCfg<64, 128, 16, 1, 4, 4, 2>;
 
-template <class Cfg>
+template <class Cfg, bool COPIER = false>
 int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
                long long sc, int batch, const EpiParams &ep, int max_sms) {
     static PerDevice<bool> attr_set;  // function attributes are per device
     if (!attr_set()) {
-        FM_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        FM_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<Cfg, COPIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set() = true;
     }
     CUtensorMap tmA, tmB;
@@ -627,7 +702,7 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = ep.pdl_wait ? 1 : 0;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, epl, vec_all));
+    FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg, COPIER>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, epl, vec_all));
     count_launch();
     return FM_OK;
 }
@@ -636,6 +711,7 @@ bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer sw
 bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
 bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
 bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
+bool g_copier_enabled = getenv("FLOMAT_GEMM_NO_COPIER") == nullptr;  // off: the consumer warps store to the peers themselves (round-1 epilogue)
 int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
 
 }  // namespace
@@ -667,6 +743,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.ksplit = 1;
     ep.kstride = 0;
     ep.stagger_ns = ((epi.beta != 0.0 || g_stagger_all) && k <= 512) ? g_stagger_ns : 0;
+    ep.copier = (epi.npeers > 0 && g_copier_enabled) ? 1 : 0;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
@@ -708,6 +785,10 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
             ep.tile_counter = cn.dev + (cn.seq % 64);
             ep.counter_to_clear = cn.dev + ((cn.seq + 32) % 64);
             ++cn.seq;
+        }
+        if (ep.copier) {  // the fused all-gather: the instantiation whose spare producer-group warps forward the tiles to the peers
+            if (half) return launch_tma<CfgHalf, true>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
+            return launch_tma<CfgBig, true>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
         }
         if (half) return launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);
         return launch_tma<CfgBig>(m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch, ep, epi.max_sms);

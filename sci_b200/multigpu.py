@@ -297,8 +297,13 @@ class ShardedJob:
         if self.nitems:
             x = self.F.Flomat.alloc(per, self.nitems)  # a recycled block: the allocator orders the upload behind its last readers
             self.check(lib.fm_upload_async(x.a, per, h["x"].data_ptr(), per, per, self.nitems), "fm_upload_async")
-            self.F.expm_batched(x.a, self.n_item, self.nitems, self.dst.data_ptr(), self.mode, None)
-            self.check(lib.fm_download_async(h["e"].data_ptr(), per, self.dst.data_ptr(), per, per, self.nitems), "fm_download_async")
+            # two halves: the results of the first half travel to the host while the second half is computed
+            half = self.nitems // 2 if self.nitems >= 128 else self.nitems
+            for z0, cnt in ((0, half), (half, self.nitems - half)):
+                if cnt:
+                    self.F.expm_batched(x.a + 8 * per * z0, self.n_item, cnt, self.dst.data_ptr() + 8 * per * z0, self.mode, None)
+                    self.check(lib.fm_download_async(h["e"].data_ptr() + 8 * per * z0, per, self.dst.data_ptr() + 8 * per * z0, per, per, cnt),
+                               "fm_download_async")
         self.check(lib.fm_transfer_sync(), "fm_transfer_sync")
 
     # ---- verification (asserted by bench.py) -----------------------------------------------------------------------------------
