@@ -114,7 +114,7 @@ struct GemmCfg {
     static constexpr int B_STAGE = (BK / 16) * B_BOX_BYTES;
     static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8 + STAGES * 4 /*tile ids*/ +
-                                      64 /*copier: 4 mbarriers, 2 tile ids (padded)*/;
+                                      96 /*copier: 4 mbarriers, 2 tile ids, a post counter per consumer warp (padded)*/;
     static_assert(BK % 16 == 0 && WTM % 16 == 0 && WTN % 8 == 0 && R >= 1 && R <= 4, "tile shape");
 };
 
@@ -136,8 +136,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // a two-slot mailbox; the three spare warps of the producer warpgroup read the tile back (L2 hits) and store it to every peer's
     // C over NVLink while the consumers are already in the next tile's main loop.  (With the consumers issuing the 7 x 32 remote
     // stores themselves the DMMA pipe idled while the stores drained: 33.5 instead of 35.9 TFLOP/s per GPU at 8 GPUs.)
-    const uint32_t copy_bar = (tile_slot + 4u * STAGES + 7u) & ~7u;  // full[0], full[1], empty[0], empty[1]
-    const uint32_t copy_tile = copy_bar + 32u;
+    // (constant offsets from smem_base, so the addresses cost no registers across the main loop)
+    constexpr uint32_t COPY_BAR_OFF = (uint32_t)((STAGES * Cfg::STAGE_BYTES + 16 * STAGES + 4 * STAGES + 7) & ~7);
+    const uint32_t copy_bar = smem_base + COPY_BAR_OFF;  // full[0], full[1], empty[0], empty[1]
+    const uint32_t copy_tile = smem_base + COPY_BAR_OFF + 32u;
     auto copy_full = [&](int s) { return copy_bar + 8u * s; };
     auto copy_empty = [&](int s) { return copy_bar + 16u + 8u * s; };
     constexpr bool copier = COPIER;  // a separate instantiation: the plain product keeps its register allocation (168, no spills)
@@ -270,16 +272,21 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     // what the consumers themselves store to: with the copier warps on duty, the local C only
     const int npeers_cons = copier ? 0 : ep.npeers;
-    unsigned nposts = 0;  // mailbox slot of the next post = nposts & 1, its phase = (nposts >> 1) & 1
+    // every consumer warp keeps its post count in shared memory (touched once per tile; a register would be live across the main
+    // loop, which has none to spare): mailbox slot of the next post = count & 1, its phase = (count >> 1) & 1
+    const uint32_t post_cnt = copy_tile + 8u + 4u * warp;
+    if (copier && lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(post_cnt), "r"(0u) : "memory");
     auto post = [&](int id) {  // all of this warp's stores of tile `id` are issued: release them to the copier warps
         __syncwarp();
         if (lane == 0) {
+            unsigned nposts;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nposts) : "r"(post_cnt) : "memory");
             const int cslot = nposts & 1u;
             mbar_wait(copy_empty(cslot), ((nposts >> 1) & 1u) ^ 1u);  // the copier is done with the tile that used this slot two posts ago
             if (warp == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(copy_tile + 4u * cslot), "r"(id) : "memory");
             mbar_arrive(copy_full(cslot));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(post_cnt), "r"(nposts + 1u) : "memory");
         }
-        ++nposts;
     };
     int stage = 0;
     uint32_t phase = 0;
@@ -712,6 +719,7 @@ bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
 bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
 bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
 bool g_copier_enabled = getenv("FLOMAT_GEMM_NO_COPIER") == nullptr;  // off: the consumer warps store to the peers themselves (round-1 epilogue)
+int g_copier_min_peers = getenv("FLOMAT_GEMM_COPIER_MIN_PEERS") ? atoi(getenv("FLOMAT_GEMM_COPIER_MIN_PEERS")) : 3;
 int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
 
 }  // namespace
@@ -743,7 +751,9 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.ksplit = 1;
     ep.kstride = 0;
     ep.stagger_ns = ((epi.beta != 0.0 || g_stagger_all) && k <= 512) ? g_stagger_ns : 0;
-    ep.copier = (epi.npeers > 0 && g_copier_enabled) ? 1 : 0;
+    // forwarding by the spare warps pays from three peers on (measured, n = 16384: 8 GPUs 33.3 -> 34.9 TFLOP/s per GPU; with ONE peer the
+    // consumers' own stores are 0.4 % faster: profiles/r02_colshard_copier_ab.jsonl)
+    ep.copier = (epi.npeers >= g_copier_min_peers && g_copier_enabled) ? 1 : 0;
 
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&

@@ -113,3 +113,47 @@ def test_second_device_context(fm, ref):
     finally:
         fm.init(0)
     assert normwise_rel_err(fm.times(fm.matrix(a), fm.matrix(b)).to_numpy(), want) <= tol(700)
+
+
+@pytest.mark.parametrize("npeers", [2, 7])
+def test_peer_store_epilogue_under_lsu_pressure_single_gpu(fm, npeers):
+    """Regression guard for the stage-release hazard of the GEMM main loop (dgemm.cu: the mbarrier arrive that frees a pipeline stage
+    must not overtake the stage's last LDS; seen in round 1 only with NVLink stores in flight on 2 GPUs).  One GPU is enough to
+    exercise it: the "peers" are other buffers of the same device, so the peer-store epilogue runs (consumer-side stores for 2 peers,
+    the forwarding warps for 7), while a second stream saturates the memory pipes with elementwise traffic.  120 products per
+    configuration must equal a quiet run bit for bit, in the local C and in every "peer"."""
+    import ctypes
+
+    import torch
+
+    lib = fm.load()
+    n, nloc = 2048, 1024
+    A = fm.randn(n, n, iseed=np.array([7, 7, 7, 7], dtype=np.int32))
+    B = fm.randn(n, nloc, iseed=np.array([9, 9, 9, 9], dtype=np.int32))
+    quiet = fm.Flomat.alloc(n, n)
+    fm._lib.check(lib.fm_fill(quiet.a, n, n, n, 0.0), "fm_fill")
+    fm._lib.check(lib.fm_dgemm_colshard(n, nloc, n, A.a, n, B.a, n, quiet.a, n, 512, None, 0), "fm_dgemm_colshard")
+    want = quiet.to_numpy()
+    C = fm.Flomat.alloc(n, n)
+    peers = [fm.Flomat.alloc(n, n) for _ in range(npeers)]
+    arr = (ctypes.c_void_p * npeers)(*[p.a for p in peers])
+    side = torch.cuda.Stream()
+    x = torch.randn(1 << 26, dtype=torch.float64, device="cuda")
+    y = torch.randn(1 << 26, dtype=torch.float64, device="cuda")
+    bad = 0
+    for rep in range(120):
+        for buf in [C] + peers:
+            fm._lib.check(lib.fm_fill(buf.a, n, n, n, 0.0), "fm_fill")
+        fm.sync()
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                x.add_(y)  # 1.6 GB of traffic per pass beside the product
+        fm._lib.check(lib.fm_dgemm_colshard(n, nloc, n, A.a, n, B.a, n, C.a, n, 512, arr, npeers), "fm_dgemm_colshard")
+        torch.cuda.synchronize()
+        if rep % 8 == 0 or rep == 119:  # full comparison of every copy on a sample of the repetitions, checksums on the rest
+            for buf in [C] + peers:
+                bad += int(not np.array_equal(buf.to_numpy(), want))
+        else:
+            for buf in [C] + peers:
+                bad += int(fm.norm(fm.minus(buf, quiet), "max") != 0.0)
+    assert bad == 0
