@@ -89,16 +89,29 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const double *src, bool 
 // argmax over (key, then lowest position) of one candidate per lane; lanes without a candidate pass valid = false
 // (and key = 0).  Returns true in exactly one lane (the winner), or in none when no lane has a candidate.  The common
 // case (a unique maximum of the high word) costs one REDUX and one vote.
-__device__ __forceinline__ bool warp_argmax(unsigned long long key, int pos, bool valid = true) {
+// (returns the vote itself -- one bit set, or none -- so that a caller that needs the winner's LANE does not vote a second time)
+__device__ __forceinline__ unsigned warp_argmax_mask(unsigned long long key, int pos, bool valid = true) {
     const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
     const unsigned mh = __reduce_max_sync(FULL, hi);
     const unsigned tie = __ballot_sync(FULL, valid && hi == mh);
-    if (__popc(tie) == 1) return valid && hi == mh;
-    if (tie == 0) return false;
+    if (__popc(tie) <= 1) return tie;
     const unsigned ml = __reduce_max_sync(FULL, (valid && hi == mh) ? lo : 0u);
     const bool top = valid && hi == mh && lo == ml;
     const int mp = __reduce_min_sync(FULL, top ? pos : NOROW);
-    return top && pos == mp;
+    return __ballot_sync(FULL, top && pos == mp);
+}
+__device__ __forceinline__ bool warp_argmax(unsigned long long key, int pos, bool valid = true) {
+    return (warp_argmax_mask(key, pos, valid) >> (threadIdx.x & 31)) & 1u;
+}
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,7 +250,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             // every warp finds the CTA's candidate (redundantly) and pushes it to its destination CTAs
             const int p2 = lane < NWARP ? s_wpos[wb][lane] : NOROW;
             const unsigned long long k2 = p2 != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_wdata[wb][lane < NWARP ? lane : 0][2])) : 0ull;
-            const unsigned who = __ballot_sync(FULL, warp_argmax(k2, p2, p2 != NOROW));
+            const unsigned who = warp_argmax_mask(k2, p2, p2 != NOROW);
             if (solo) {
                 solo_src = who ? __ffs(who) - 1 : 0;
                 return;
@@ -270,19 +283,20 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             if (!solo) bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
             PROF_T(tc1);
             PROF_ADD(0, tc0, tc1);
-            // global winner: same decision in every warp (lane d looks at CTA d's candidate)
-            const double *prow;
+            // global winner: same decision in every warp (lane d looks at CTA d's candidate).  The winner's row is read through an
+            // explicit shared-space address: a generic pointer that may point into either array costs a window-base computation
+            // (S2UR SR_CgaCtaId + LEA) on the critical chain of every step.
+            uint32_t prow;
             if (!solo) {
                 const long long c0 = lane < (int)csize ? __double_as_longlong(s_cand[buf][lane][0]) : ((long long)NOROW << 32);
                 const int cp = (int)(c0 >> 32);
                 const unsigned long long ck = cp != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_cand[buf][lane < (int)csize ? lane : 0][2])) : 0ull;
-                const unsigned who = __ballot_sync(FULL, warp_argmax(ck, cp, cp != NOROW));
-                prow = &s_cand[buf][who ? __ffs(who) - 1 : 0][0];
+                const unsigned who = warp_argmax_mask(ck, cp, cp != NOROW);
+                prow = lsmem(&s_cand[0][0][0]) + (uint32_t)((buf * MAXC + (who ? __ffs(who) - 1 : 0)) * PAY * 8);
             } else {
-                prow = &s_wdata[q & 1][solo_src][0];
+                prow = lsmem(&s_wdata[0][0][0]) + (uint32_t)(((q & 1) * NWARP + solo_src) * PAY * 8);
             }
-            const double2 *pr2 = reinterpret_cast<const double2 *>(prow);
-            const double2 head = pr2[0];
+            const double2 head = lds_v2(prow);
             const long long hd = __double_as_longlong(head.x);
             const int p = (int)(hd >> 32);           // LAPACK position of the pivot row (ipiv)
             const int pphys = (int)(unsigned)hd;     // where it physically lives
@@ -290,13 +304,13 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             double pm[W];
 #pragma unroll
             for (int c = 0; c < W; c += 2) {
-                const double2 t = pr2[1 + c / 2];
+                const double2 t = lds_v2(prow + 16u + 8u * c);
                 pm[c] = t.x;
                 pm[c + 1] = t.y;
             }
             const double pval = pm[0];
             if (warp == 0) {
-                if (lane < j) s_L[j][lane] = prow[2 + W - j + lane];  // multipliers of pivot row j for the leaf's earlier steps
+                if (lane < j) s_L[j][lane] = lds_f64(prow + 8u * (2 + W - j + lane));  // multipliers of pivot row j for the leaf's earlier steps
                 if (lane == 0) {
                     s_pphys[q] = pphys;
                     if (crank == 0) {
