@@ -863,10 +863,42 @@ struct StagedVec {
     ~StagedVec() { if (owned && dev) { cudaStreamSynchronize(ctx().stream); fm_free(dev); } }
 };
 
+// The reference's `plus` / `minus` arrive as ONE cblas_daxpy PER COLUMN with unit strides and host pointers (flomat.rkt:805-813): an
+// n = 8192 matrix sum is 8192 calls of 64 KB each, 90 112 calls per expm.  For that shape the generic staging (two allocations, two
+// pageable uploads, each with its own driver-side staging and synchronisation) costs ~55 us per call; here X and Y are packed into one
+// pinned buffer, travel up in one copy, and Y comes back through the same buffer.  Per device: 2 x 512 KB pinned + 2 x 512 KB of HBM.
+struct SmallVecStage {
+    static constexpr size_t CAP = 65536;  // doubles per vector
+    double *pin = nullptr, *dev = nullptr;
+};
+static PerDevice<SmallVecStage> g_small;
+static int daxpy_small_host(int n, double alpha, const double *X, double *Y) {
+    SmallVecStage &sv = g_small();
+    if (!sv.pin) {
+        FM_CUDA(cudaMallocHost(&sv.pin, 2 * SmallVecStage::CAP * sizeof(double)));
+        FM_CUDA(cudaMalloc(&sv.dev, 2 * SmallVecStage::CAP * sizeof(double)));
+    }
+    const size_t bytes = (size_t)n * sizeof(double);
+    memcpy(sv.pin, X, bytes);
+    memcpy(sv.pin + n, Y, bytes);
+    cudaStream_t st = ctx().stream;
+    FM_CUDA(cudaMemcpyAsync(sv.dev, sv.pin, 2 * bytes, cudaMemcpyHostToDevice, st));
+    FM_TRY(k_axpy_strided(n, alpha, sv.dev, 1, sv.dev + n, 1));
+    FM_CUDA(cudaMemcpyAsync(sv.pin + n, sv.dev + n, bytes, cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaStreamSynchronize(st));
+    memcpy(Y, sv.pin + n, bytes);
+    return FM_OK;
+}
+
 void cblas_daxpy(int n, double alpha, const double *X, int incX, double *Y, int incY) {
     if (n <= 0) return;
     int rc = ensure_init();
     if (rc == FM_OK && (incX < 0 || incY <= 0)) rc = set_error(FM_ERR_ARG, "cblas_daxpy: negative increments (and incY = 0) are not used by flomat and not supported");
+    if (rc == FM_OK && incX == 1 && incY == 1 && (size_t)n <= SmallVecStage::CAP && !is_device_ptr(X) && !is_device_ptr(Y)) {
+        rc = daxpy_small_host(n, alpha, X, Y);
+        report("cblas_daxpy", rc);
+        return;
+    }
     if (rc == FM_OK) {
         StagedVec x, y;
         rc = x.in(X, incX, n, true);
