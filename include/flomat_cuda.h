@@ -255,6 +255,9 @@ int fm_mg_dgemm(int transA, int transB, int m, int n, int k, double alpha, const
 int fm_mg_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,
                        int batch, int mode, double *s_out);
 int fm_mg_sync(void);                     /* wait for every device of the group */
+/* the partitions the two calls above use: columns in whole 128-column tile columns, items in contiguous blocks (host arithmetic only) */
+int fm_mg_column_block(int n, int world, int r, int *first, int *count);
+int fm_mg_item_block(int batch, int world, int r, int *first, int *count);
 
 #ifdef __cplusplus
 }

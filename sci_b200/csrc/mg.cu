@@ -210,6 +210,18 @@ int fm_mg_init(int ndev) {
 
 int fm_mg_device_count(void) { return g_group ? g_group->ndev : 0; }
 
+// the partition fm_mg_dgemm / fm_mg_expm_batched use (pure host arithmetic, callable without a GPU): block of rank r of `world`
+int fm_mg_column_block(int n, int world, int r, int *first, int *count) {
+    if (n < 0 || world <= 0 || r < 0 || r >= world || !first || !count) return set_error(FM_ERR_ARG, "fm_mg_column_block: bad arguments");
+    column_block(n, world, r, first, count);
+    return FM_OK;
+}
+int fm_mg_item_block(int batch, int world, int r, int *first, int *count) {
+    if (batch < 0 || world <= 0 || r < 0 || r >= world || !first || !count) return set_error(FM_ERR_ARG, "fm_mg_item_block: bad arguments");
+    item_block(batch, world, r, first, count);
+    return FM_OK;
+}
+
 int fm_mg_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
                 double *c, int ldc) {
     if (!g_group) FM_TRY(fm_mg_init(0));

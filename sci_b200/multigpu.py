@@ -38,6 +38,15 @@ def item_block(batch: int, world: int, rank: int) -> tuple[int, int]:
     return z0, base + (1 if rank < extra else 0)
 
 
+def sub_blocks(nloc: int, max_blocks: int = 4, min_cols: int = 1024) -> list[tuple[int, int]]:
+    """The sub-blocks (first column, width) a rank's column block is cut into for the end-to-end pipeline (upload i+1 | product i |
+    download i-1): at most `max_blocks`, each a whole number of 128-column tile columns and at least `min_cols` wide, so that every
+    product still fills whole waves of the persistent GEMM."""
+    nsub = min(max_blocks, max(1, nloc // min_cols))
+    cuts = [(nloc * i // nsub) // 128 * 128 for i in range(nsub)] + [nloc]
+    return [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(nsub) if cuts[i + 1] > cuts[i]]
+
+
 def allgather_columns(c_full, n_rows: int, n_cols: int, world: int, rank: int, dist):
     """Reassemble a column-major (n_rows x n_cols) matrix stored in the flat torch tensor `c_full` whose own column block
     is already in place.  Works for any backend (NCCL on GPUs, gloo on CPU tensors).  Equal blocks use one in-place
@@ -271,9 +280,7 @@ class ShardedJob:
             allgather_columns(cs.A, n, n, self.world, self.rank, self.dist)  # A over NVLink instead of `world` times over PCIe
         # the rank's block of B / C in sub-blocks of >= 1024 columns (whole waves of the persistent GEMM): sub-block i+1 goes up and
         # sub-block i-1 comes down while sub-block i is multiplied
-        nsub = min(4, max(1, nloc // 1024))
-        cuts = [(nloc * i // nsub) // 128 * 128 for i in range(nsub)] + [nloc]
-        subs = [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(nsub) if cuts[i + 1] > cuts[i]]
+        subs = sub_blocks(nloc)
         stage = {}
 
         def up(i):

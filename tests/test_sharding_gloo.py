@@ -31,6 +31,42 @@ def test_partitions_cover_exactly_once():
     assert [item_block(4096, 8, r)[1] for r in range(8)] == [512] * 8  # BASELINE config 5
 
 
+def test_single_process_partitions_match_the_launcher_ones():
+    """fm_mg_dgemm / fm_mg_expm_batched (one process, all devices; csrc/mg.cu) cut B / C and the batch exactly like the
+    one-process-per-GPU path does (sci_b200/multigpu.py): host arithmetic, no GPU needed."""
+    from ctypes import byref, c_int
+
+    from sci_b200 import _lib
+    from sci_b200.multigpu import column_block, item_block
+
+    lib = _lib.load()
+    a, b = c_int(), c_int()
+    for n in (1, 100, 128, 129, 1000, 2500, 8192, 16384, 16400):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                assert lib.fm_mg_column_block(n, world, r, byref(a), byref(b)) == 0
+                assert (a.value, b.value) == column_block(n, world, r), (n, world, r)
+                assert lib.fm_mg_item_block(n, world, r, byref(a), byref(b)) == 0
+                assert (a.value, b.value) == item_block(n, world, r), (n, world, r)
+    assert lib.fm_mg_column_block(100, 4, 4, byref(a), byref(b)) == -1002 and lib.fm_mg_item_block(-1, 2, 0, byref(a), byref(b)) == -1002
+    assert lib.fm_mg_device_count() == 0  # no group without fm_mg_init (and no GPU is touched by asking)
+
+
+def test_e2e_sub_blocks_cover_the_column_block():
+    from sci_b200.multigpu import sub_blocks
+
+    for nloc in (0, 1, 127, 128, 1000, 1024, 2048, 2176, 4096, 8192, 16384):
+        subs = sub_blocks(nloc)
+        assert sum(w for _, w in subs) == nloc and len(subs) <= 4
+        pos = 0
+        for c0, w in subs:
+            assert c0 == pos and c0 % 128 == 0 and w > 0
+            pos += w
+        if nloc >= 2048:
+            assert min(w for _, w in subs) >= 1024  # whole waves of 128 x 128 tiles at m = 16384
+    assert sub_blocks(2048) == [(0, 1024), (1024, 1024)] and sub_blocks(8192) == [(0, 2048), (2048, 2048), (4096, 2048), (6144, 2048)]
+
+
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, {root!r})
