@@ -168,6 +168,11 @@ int fm_dgemm_batched(int m, int n, int k, double alpha, const double *a, int lda
 
 /* LU family, device pointers (a, b, ipiv, info all in HBM; info is one int32 per matrix) */
 int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info);
+/* LU WITHOUT interchanges, verified (the solve inside expm uses it: its Pade denominator is column diagonally dominant, so dgetrf
+ * performs no interchange on it): a := L\U, ipiv := 1..n, info := 0, and *violated (device int32) := 1 if some multiplier exceeds
+ * 0.999 in magnitude or a pivot is zero / not finite -- i.e. if partial pivoting WOULD have interchanged -- in which case the result
+ * must be discarded and fm_getrf used on the original matrix.  When *violated == 0 the factors are dgetrf's (same pivots: none). */
+int fm_getrf_nopiv(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int32_t *violated);
 int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb);
 /* dgesv semantics (flomat.rkt:2112): with info > 0 (exactly singular U) the solve is skipped and B is left untouched, which is
  * what flomat-solve-many! (:2135-2142, info ignored) then returns.  Reads info back once (4 bytes, syncs). */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "fm_dgemm_batched": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_double, _DP, c_int,
                                  c_longlong, c_double, c_int]),
     "fm_getrf": (c_int, [c_int, c_int, _DP, c_int, _IP, _IP]),
+    "fm_getrf_nopiv": (c_int, [c_int, _DP, c_int, _IP, _IP, _IP]),
     "fm_getrs": (c_int, [c_int, c_int, _DP, c_int, _IP, _DP, c_int]),
     "fm_gesv": (c_int, [c_int, c_int, _DP, c_int, _IP, _DP, c_int, _IP]),
     "fm_getri": (c_int, [c_int, _DP, c_int, _IP, _IP]),

@@ -594,6 +594,12 @@ int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info) {
     FM_TRY(ensure_init());
     return k_getrf(m, n, a, lda, 0, ipiv, 0, info, 1);
 }
+int fm_getrf_nopiv(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int32_t *violated) {
+    FM_TRY(ensure_init());
+    if (!ipiv || !info || !violated) return set_error(FM_ERR_ARG, "fm_getrf_nopiv: ipiv, info and violated must be device pointers");
+    FM_CUDA(cudaMemsetAsync(violated, 0, sizeof(int32_t), ctx().stream));
+    return k_getrf_nopiv(n, a, lda, 0, ipiv, 0, info, violated, 1);
+}
 int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb) {
     FM_TRY(ensure_init());
     return k_getrs(n, nrhs, lu, lda, 0, ipiv, 0, b, ldb, 0, 1);

@@ -125,6 +125,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
             double *c, int ldc, long long sc, int batch, const GemmEpilogue &ep);
 // lu.cu
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
+int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int32_t *viol, int batch);
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);
 int k_getri(int n, double *a, int lda, const int32_t *ipiv);

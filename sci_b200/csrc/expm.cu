@@ -11,6 +11,7 @@
 // Non-finite norm: the reference's `repeated-squaring` never terminates (F5-iii); we return FM_ERR_NONFINITE.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace fm {
@@ -77,8 +78,12 @@ struct InfoBack {
 };
 PerDevice<InfoBack> g_info_pd;
 
+// `pivot`: factor the denominator with the pivoting LU.  The default first pass uses the verified no-interchange LU (lu.cu,
+// k_getrf_nopiv): the Pade denominator is column diagonally dominant (||den - I||_1 <= 0.282 for the reference's scaling), so dgesv
+// performs no interchange on it and the pivot search -- the latency chain that dominated expm at small n -- is skipped; the violation
+// flag of that factorization travels with the info words, and the caller repeats the pipeline with pivot = true if it is raised.
 int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_host,
-                  bool host_out = false, bool honour_singular = false) {
+                  bool host_out = false, bool honour_singular = false, bool pivot = true) {
     const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
     cudaStream_t st = ctx().stream;
     InfoBack &g_info = g_info_pd();
@@ -91,14 +96,15 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
         if (!B[i]) return FM_ERR_NOMEM;
     }
     // small arrays: norms | scales (doubles), rounds | ipiv | info (int32)
-    const size_t small_bytes = (size_t)batch * (2 * sizeof(double) + 2 * sizeof(int32_t)) + (size_t)batch * n * sizeof(int32_t) + 64;
+    const size_t small_bytes = (size_t)batch * (2 * sizeof(double) + 2 * sizeof(int32_t)) + (size_t)batch * n * sizeof(int32_t) + 128;
     char *small = static_cast<char *>(g_pool_pd().get(6, small_bytes));
     if (!small) return FM_ERR_NOMEM;
     double *d_norm = reinterpret_cast<double *>(small);
     double *d_scale = d_norm + batch;
     int32_t *d_rounds = reinterpret_cast<int32_t *>(d_scale + batch);
-    int32_t *d_info = d_rounds + batch;
-    int32_t *d_ipiv = d_info + batch;
+    int32_t *d_info = d_rounds + batch;  // batch info words, then ONE violation word of the no-interchange LU
+    int32_t *d_viol = d_info + batch;
+    int32_t *d_ipiv = d_viol + 1;
 
     // ---- scaling exponents (expm.rkt:212-215) ----
     FM_TRY(k_norm1_batched(n, a, lda, sa, batch, d_norm));
@@ -177,16 +183,18 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     // num = even + odd, den = even - odd, R = den \ num   (expm.rkt:197-199 -> flomat.rkt:2145-2152)
     // the workspaces of a batch are contiguous (item stride = ldw*n), i.e. one ldw x (n*batch) matrix: one launch
     FM_TRY(k_addsub(n, n * batch, E, ldw, O, ldw, num, ldw, den, ldw));
-    FM_TRY(k_getrf(n, n, den, ldw, sw, d_ipiv, n, d_info, batch));
-    if (g_info.cap < batch) {
+    FM_CUDA(cudaMemsetAsync(d_viol, 0, sizeof(int32_t), st));
+    if (pivot) FM_TRY(k_getrf(n, n, den, ldw, sw, d_ipiv, n, d_info, batch));
+    else FM_TRY(k_getrf_nopiv(n, den, ldw, sw, d_ipiv, n, d_info, d_viol, batch));
+    if (g_info.cap < batch + 1) {
         if (g_info.h) cudaFreeHost(g_info.h);
         g_info.h = nullptr;
         g_info.cap = 0;
-        FM_CUDA(cudaMallocHost(&g_info.h, (size_t)(batch < 64 ? 64 : batch) * sizeof(int32_t)));
-        g_info.cap = batch < 64 ? 64 : batch;
+        FM_CUDA(cudaMallocHost(&g_info.h, (size_t)(batch < 63 ? 64 : batch + 1) * sizeof(int32_t)));
+        g_info.cap = batch < 63 ? 64 : batch + 1;
     }
     if (!g_info.ready) FM_CUDA(cudaEventCreateWithFlags(&g_info.ready, cudaEventDisableTiming));
-    FM_CUDA(cudaMemcpyAsync(g_info.h, d_info, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FM_CUDA(cudaMemcpyAsync(g_info.h, d_info, (size_t)(batch + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));  // info words + violation word
     FM_CUDA(cudaEventRecord(g_info.ready, st));
     if (!honour_singular) {
         FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
@@ -263,14 +271,26 @@ namespace {
 // sends the call through the pipeline a second time with dgesv's "B untouched" rule applied.  Returns the first nonzero info.
 int expm_checked(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out,
                  bool host_out, int32_t *info_host) {
-    FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false));
+    static const bool always_pivot = getenv("FLOMAT_EXPM_PIVOT") != nullptr;  // developer switch: the pivoting LU from the start (A/B timing)
+    // the no-interchange LU has no look-ahead (diagonal block, two leaf solves and the trailing product run one after the other), which
+    // the pivoting LU's panel || product overlap makes up for at large n: measured equal at n = 8192, 9-27 % faster for n <= 2048
+    static const int nopiv_max_n = getenv("FLOMAT_EXPM_NOPIV_MAX_N") ? atoi(getenv("FLOMAT_EXPM_NOPIV_MAX_N")) : 4096;
+    bool pivot = always_pivot || n > nopiv_max_n;
+    FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false, pivot));
     InfoBack &g_info = g_info_pd();
     FM_CUDA(cudaEventSynchronize(g_info.ready));
+    if (!pivot && g_info.h[batch] != 0) {
+        // the no-interchange factorization was not what partial pivoting computes (never for a finite, nonzero input: see lu.cu): the
+        // whole pipeline again with the pivoting LU -- the queued rest of the first pass only wrote workspaces and `out`
+        pivot = true;
+        FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false, true));
+        FM_CUDA(cudaEventSynchronize(g_info.ready));
+    }
     int32_t first = 0;
     for (int z = 0; z < batch && first == 0; ++z) first = g_info.h[z];
     if (info_host) *info_host = first;
     if (first == 0) return FM_OK;
-    return expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, true);
+    return expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, true, true);
 }
 }  // namespace
 

@@ -2000,6 +2000,167 @@ __global__ void __launch_bounds__(256) tri_copy_kernel(int n, const double *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LU WITHOUT interchanges, verified: the fast path of the solve inside expm (expm.rkt:199, `(mldivide den num)`).
+// The Pade denominator den = sum_k c_k (-X)^k with ||X||_1 in (1/4, 1/2] (the reference's own scaling, expm.rkt:212-215) satisfies
+// ||den - I||_1 <= 0.282: it is strictly diagonally dominant by columns, and for such matrices partial pivoting never interchanges
+// (the Schur complements stay column diagonally dominant), i.e. dgetrf's answer IS the no-pivot factorization with ipiv = 1..n.
+// Without the pivot search the panel is plain arithmetic -- no argmax chain of ~2300 cycles per column.  The claim is CHECKED, not
+// assumed: every multiplier must satisfy |l_ij| <= 0.999 (|l_ij| <= 1 for all i > j is exactly "IDAMAX picks the diagonal at step j")
+// and every pivot must be finite and nonzero; otherwise a violation flag is raised and the caller repeats the factorization with the
+// pivoting kernels (expm.cu).  Blocked right-looking, NB = 128:
+//   getf2_nopiv_kernel  the 128 x 128 diagonal block in the shared memory of one CTA, eliminated in block steps of 16 columns
+//                       (DGETF2's arithmetic: multiplier = entry times the pivot's reciprocal); also writes U11^T (lower, non-unit)
+//                       to a scratch block for the right-side solve below
+//   L21 = A21 U11^-1    the leaf TRSM in its right-side mode on T = U11^T (as Cholesky uses it)
+//   U12 = L11^-1 A12    the leaf TRSM (unit lower);   A22 -= L21 U12   the DMMA GEMM
+// ---------------------------------------------------------------------------------------------
+constexpr int NP_LD = NB + 2;                                                      // column stride of the block in shared memory
+constexpr int NP_SMEM = (NB * NP_LD + 16 * NB) * (int)sizeof(double);              // the block + a row-major copy of the current U block row
+__global__ void __launch_bounds__(256, 1) getf2_nopiv_kernel(int nb, double *a, long long lda, long long sa, double *ut, long long sut, int32_t *viol) {
+    // The 128 x 128 block lives in shared memory: S(i, c) = S[c * NP_LD + i], padded with the identity beyond nb.  Eight block steps of
+    // 16 columns: (1) unblocked elimination of the 16-wide block column over all rows below (thread = row, one barrier per column: the
+    // sequential part; measured ~330 ns per column); (2) the U block row right of it by forward
+    // substitution with the unit-lower 16 x 16 block (thread = column); (3) rank-16 update of the trailing square from registers
+    // (thread (ty, tx) of a 16 x 16 grid owns the elements (ty + 16 a, tx + 16 b): 14 shared-memory loads per 49 FMAs).
+    extern __shared__ double sm[];
+    double *S = sm;
+    double *Us = sm + NB * NP_LD;  // Us[t * NB + c] = U(c0 + t, c)
+    a += blockIdx.x * sa;
+    ut += blockIdx.x * sut;
+    const int tid = threadIdx.x;
+    {
+        const int i = tid & (NB - 1), ch = tid >> 7;  // two columns per pass; 8 passes of loads in flight at a time
+#pragma unroll 1
+        for (int cb = 0; cb < NB; cb += 16) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = cb + 2 * q + ch;
+                v[q] = (i < nb && c < nb) ? a[c * lda + i] : (i == c ? 1.0 : 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) S[(cb + 2 * q + ch) * NP_LD + i] = v[q];
+        }
+    }
+    __syncthreads();
+    bool bad = false;
+    const int ty = tid & 15, tx = tid >> 4;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        const int c0 = 16 * kb;
+        if (c0 >= nb) break;  // (uniform)
+        // ---- (1) the block column, unblocked: thread = row, one barrier per column ----
+#pragma unroll 1
+        for (int jt = 0; jt < 16; ++jt) {
+            const int j = c0 + jt;
+            if (j >= nb) break;  // (uniform)
+            const double d = S[j * NP_LD + j];
+            if (!(fabs(d) > 0.0) || !(fabs(d) < DBL_MAX)) bad = true;  // a zero / non-finite pivot is not a dominant one
+            const bool use_rcp = fabs(d) >= DBL_MIN;                  // DGETF2: scale by the reciprocal unless the pivot is tiny
+            const double rcp = 1.0 / d;
+            if (tid < NB && tid > j) {
+                const int row = tid;
+                // all loads first (the compiler cannot reorder them across the stores into the same array), then the arithmetic
+                double own[15], piv[15];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) {
+                    const int c = j + q < c0 + 16 ? j + q : j;  // (clamped: the value is not used beyond the block column)
+                    own[q - 1] = S[c * NP_LD + row];
+                    piv[q - 1] = S[c * NP_LD + j];
+                }
+                const double x = S[j * NP_LD + row];
+                const double l = use_rcp ? x * rcp : x / d;
+                if (!(fabs(l) <= 0.999)) bad = true;  // |l| <= 1 everywhere is "IDAMAX picks the diagonal" (NaN fails the test too)
+#pragma unroll
+                for (int q = 1; q < 16; ++q)
+                    if (j + q < c0 + 16) S[(j + q) * NP_LD + row] = own[q - 1] - l * piv[q - 1];
+                S[j * NP_LD + row] = l;
+            }
+            __syncthreads();
+        }
+        const int r0 = c0 + 16;  // first row / column of the trailing square
+        if (r0 >= NB) break;
+        // ---- (2) U(c0 .. c0+15, c) for the columns right of the block: L11 u = a, unit lower ----
+        if (tid < NB - r0) {
+            const int c = r0 + tid;
+            double u[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                double acc = S[c * NP_LD + c0 + t];
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (q < t) acc -= S[(c0 + q) * NP_LD + c0 + t] * u[q];
+                u[t] = acc;
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                S[c * NP_LD + c0 + t] = u[t];
+                Us[t * NB + c] = u[t];
+            }
+        }
+        __syncthreads();
+        // ---- (3) trailing square: S(i, c) -= sum_t L(i, c0 + t) U(c0 + t, c) ----
+        constexpr int NA_MAX = 7;
+        const int na = 7 - kb;  // 16-wide strips of the trailing square (compile time after unrolling)
+        double acc[NA_MAX][NA_MAX];
+#pragma unroll
+        for (int x = 0; x < NA_MAX; ++x)
+#pragma unroll
+            for (int y = 0; y < NA_MAX; ++y)
+                if (x < na && y < na) acc[x][y] = S[(r0 + tx + 16 * y) * NP_LD + r0 + ty + 16 * x];
+#pragma unroll 4
+        for (int t = 0; t < 16; ++t) {
+            double lf[NA_MAX], uf[NA_MAX];
+#pragma unroll
+            for (int x = 0; x < NA_MAX; ++x)
+                if (x < na) {
+                    lf[x] = S[(c0 + t) * NP_LD + r0 + ty + 16 * x];
+                    uf[x] = Us[t * NB + r0 + tx + 16 * x];
+                }
+#pragma unroll
+            for (int x = 0; x < NA_MAX; ++x)
+#pragma unroll
+                for (int y = 0; y < NA_MAX; ++y)
+                    if (x < na && y < na) acc[x][y] -= lf[x] * uf[y];
+        }
+#pragma unroll
+        for (int x = 0; x < NA_MAX; ++x)
+#pragma unroll
+            for (int y = 0; y < NA_MAX; ++y)
+                if (x < na && y < na) S[(r0 + tx + 16 * y) * NP_LD + r0 + ty + 16 * x] = acc[x][y];
+        __syncthreads();
+    }
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx & (NB - 1), c = idx >> 7;
+        if (i < nb && c < nb) a[c * lda + i] = S[c * NP_LD + i];
+    }
+    // T = U11^T (lower, non-unit) for the right-side solve: T(r, k) = U(k, r), column-major with leading dimension NB; consecutive
+    // threads walk a column of T, i.e. a ROW of U
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx & (NB - 1), k = idx >> 7;
+        if (r < nb && k <= r) ut[(long long)k * NB + r] = S[r * NP_LD + k];
+    }
+    if (__syncthreads_or(bad) && tid == 0) atomicOr(viol, 1);
+}
+
+// ipiv := 1..n (no interchanges) for every item; info := 0
+__global__ void iota_pivots_kernel(int n, int32_t *ipiv, long long sp, int32_t *info) {
+    int32_t *p = ipiv + blockIdx.y * sp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) info[blockIdx.y] = 0;
+}
+
+// raises *viol when some multiplier below the diagonal of rows [r0, m) x columns [c0, c0 + w) exceeds 0.999 in magnitude (or is NaN)
+__global__ void __launch_bounds__(256) multiplier_check_kernel(int r0, int m, int c0, int w, const double *a, long long lda, long long sa, int32_t *viol) {
+    const double *p = a + blockIdx.z * sa;
+    bool bad = false;
+    for (int c = c0 + blockIdx.y; c < c0 + w; c += gridDim.y)
+        for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+            if (!(fabs(p[c * lda + i]) <= 0.999)) bad = true;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(viol, 1);
+}
+
 // idx[i] = original row that LAPACK's interchange sequence leaves at position i (sequential: one thread)
 __global__ void perm_forward_kernel(int n, const int32_t *ipiv, int32_t *idx) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -2089,6 +2250,45 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
         FM_TRY(rtrsm<false>(mn, n - mn, a, lda, sa, A.at(0, mn), lda, sa, batch));
     }
     return FM_OK;
+}
+
+// a := L\\U of a without interchanges (square, batched), ipiv := 1..n, info := 0; *viol (device int32, zeroed by the caller) is raised
+// when the factorization is NOT what partial pivoting would have produced (see getf2_nopiv_kernel) -- the caller must then discard it.
+int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int32_t *viol, int batch) {
+    if (n < 0 || lda < (n > 1 ? n : 1) || batch < 0) return set_error(FM_ERR_ARG, "getrf_nopiv: bad dimensions");
+    if (batch == 0) return FM_OK;
+    if (batch > 65535) return set_error(FM_ERR_ARG, "getrf_nopiv: at most 65535 items per call");
+    iota_pivots_kernel<<<dim3(n > 0 ? std::min(ceil_div(n, 256), 64) : 1, batch), 256, 0, ctx().stream>>>(n, ipiv, sp, info);
+    FM_LAUNCH_CHECK();
+    if (n == 0) return FM_OK;
+    static PerDevice<bool> attr_pd;  // function attributes are per device
+    if (!attr_pd()) {
+        FM_CUDA(cudaFuncSetAttribute(getf2_nopiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SMEM));
+        attr_pd() = true;
+    }
+    double *ut = static_cast<double *>(fm_alloc_bytes((size_t)NB * NB * batch * sizeof(double)));  // U11^T of the current step, per item
+    if (!ut) return FM_ERR_NOMEM;
+    int rc = FM_OK;
+    for (int j0 = 0; j0 < n && rc == FM_OK; j0 += NB) {
+        const int jb = std::min(NB, n - j0), j1 = j0 + jb, rest = n - j1;
+        double *akk = a + (size_t)j0 * lda + j0;
+        getf2_nopiv_kernel<<<batch, 256, NP_SMEM, ctx().stream>>>(jb, akk, lda, sa, ut, (long long)NB * NB, viol);
+        rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "getf2_nopiv launch failed");
+        count_launch();
+        if (rest <= 0 || rc != FM_OK) break;
+        rc = trsm_leaf_cols_launch<false, true>(jb, rest, ut, NB, (long long)NB * NB, akk + jb, lda, sa, batch);  // L21 = A21 U11^-1
+        if (rc == FM_OK) {
+            dim3 grid(std::min(ceil_div(rest, 256), 8), std::min(jb, 64), batch);
+            multiplier_check_kernel<<<grid, 256, 0, ctx().stream>>>(j1, n, j0, jb, a, lda, sa, viol);
+            rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "multiplier_check launch failed");
+            count_launch();
+        }
+        if (rc == FM_OK) rc = trsm_leaf<false>(jb, rest, akk, lda, sa, a + (size_t)j1 * lda + j0, lda, sa, batch);  // U12 = L11^-1 A12
+        if (rc == FM_OK)
+            rc = gemm_minus(rest, rest, jb, akk + jb, lda, sa, a + (size_t)j1 * lda + j0, lda, sa, a + (size_t)j1 * lda + j1, lda, sa, batch);
+    }
+    fm_free(ut);
+    return rc;
 }
 
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb,

@@ -447,6 +447,20 @@ def flomat_lu_bang(a: Flomat):
     return piv, piv.info()
 
 
+def flomat_lu_nopivot_bang(a: Flomat):
+    """LU without interchanges, verified (fm_getrf_nopiv): returns (pivots = 1..n, info, violated).  `violated` is True when partial
+    pivoting would have interchanged rows; the factors are then NOT dgetrf's and flomat_lu_bang must be used on the original matrix.
+    No reference counterpart: it is the fast path of the solve inside `expm`, whose denominator is column diagonally dominant."""
+    _check_square(a, "flomat-lu (no pivoting)")
+    piv = Pivots(a.m + 4)  # (the violation word sits behind the pivots)
+    viol_ptr = piv.ptr + 4 * a.m
+    check(_L().fm_getrf_nopiv(a.m, a.a, a.lda, piv.ptr, piv.info_ptr, viol_ptr), "fm_getrf_nopiv")
+    h = np.zeros(1, dtype=np.int32)
+    check(_L().fm_download_i32(h.ctypes.data, viol_ptr, 1), "fm_download_i32")
+    piv.n = a.m
+    return piv, piv.info(), bool(h[0])
+
+
 def mldivide(a: Flomat, b: Flomat) -> Flomat:
     """`mldivide` (flomat.rkt:3289) -> flomat-solve-many :2145: copies A and B, dgesv, info ignored; returns X."""
     _check_square(a, "mldivide")

@@ -410,6 +410,38 @@ def test_inverse_general_matrix_with_interchanges(fm, ref, n):
         gate_inverse(f"inv (general) n={n}", a, Ai.to_numpy(), ref.inv(a), n)
 
 
+@pytest.mark.parametrize("n", [1, 7, 16, 33, 128, 130, 257, 512, 1000, 2304])
+def test_lu_without_interchanges_is_dgetrf_on_dominant_matrices(fm, ref, n):
+    """fm_getrf_nopiv (the solve inside expm): on a strictly column diagonally dominant matrix partial pivoting never interchanges, so
+    the verified no-interchange LU must reproduce the oracle's dgetrf -- ipiv = 1..n, same factors within 64 n eps -- and report no
+    violation; on a general matrix it must raise the violation flag instead of returning wrong factors."""
+    a = rnd(500 + n, n, n)
+    a = np.asfortranarray(a / (np.abs(a).sum(axis=0) * 1.5) + np.eye(n))  # off-diagonal column sums <= 2/3 < diagonal
+    lu = up(fm, a)
+    piv, info, violated = fm.flomat_lu_nopivot_bang(lu)
+    want_lu, want_piv, want_info = ref.lu(a)
+    assert not violated and info == want_info == 0
+    assert np.array_equal(piv.to_numpy(), np.arange(1, n + 1)) and np.array_equal(want_piv[:n], np.arange(1, n + 1))
+    gate(f"getrf_nopiv n={n}", lu.to_numpy(), want_lu, n)
+    b = rnd(600 + n, n, n)  # a general matrix: pivoting needed
+    if n > 1:
+        _piv, _info, violated = fm.flomat_lu_nopivot_bang(up(fm, b))
+        assert violated
+    z = np.asfortranarray(np.eye(n)); z[n // 2, n // 2] = 0.0  # exact zero pivot
+    _piv, _info, violated = fm.flomat_lu_nopivot_bang(up(fm, z))
+    assert violated
+
+
+def test_expm_falls_back_to_pivoting_when_the_check_fails(fm, ref):
+    """The expm pipeline tries the no-interchange LU first and repeats itself with the pivoting LU when the check fails.  A finite
+    nonzero input can never fail it (the Pade denominator is dominant), so the fallback is exercised through the NaN case the
+    reference produces for the zero matrix (expm.rkt:205: A / 2^-inf), and both paths must agree on ordinary inputs."""
+    assert np.isnan(fm.expm(fm.zeros(5, 5)).to_numpy()).all()
+    a = rnd(77, 300, 300, 1.0 / math.sqrt(300))
+    E = fm.expm(up(fm, a), fm.EXPM_MIN_PRODUCTS).to_numpy()
+    assert normwise_rel_err(E, ref.expm(a)) <= tol(300)
+
+
 # ---------------------------------------------------------------- expm
 @pytest.mark.parametrize("mode", [0, 1])
 def test_expm_closed_forms_and_quirks(fm, mode):

@@ -31,4 +31,7 @@ X = randn(512, 512, 2001, 1 / math.sqrt(512)); ms = best(lambda: fm.expm(X, 1), 
 g = torch.Generator(device=dev); g.manual_seed(5001)
 src = torch.randn(256 * 256 * 512, dtype=torch.float64, device=dev, generator=g) / 16.0; dst = torch.empty_like(src)
 ms = best(lambda: fm.expm_batched(src.data_ptr(), 256, 512, dst.data_ptr(), 1, None)); out["expm_batched_512x256"] = {"ms": round(ms, 4)}
+del src, dst
+for n in (1024, 2048, 4096, 8192):
+    X = randn(n, n, 6003, 1 / math.sqrt(n)); ms = best(lambda: fm.expm(X, 1), 3); out[f"expm_{n}"] = {"ms": round(ms, 3)}; del X
 print(json.dumps(out))
