@@ -2062,19 +2062,25 @@ __global__ void __launch_bounds__(256, 1) getf2_nopiv_kernel(int nb, double *a, 
             if (tid < NB && tid > j) {
                 const int row = tid;
                 // all loads first (the compiler cannot reorder them across the stores into the same array), then the arithmetic
+                // (only the columns still inside the block column: the step is bound by the shared-memory pipe -- 250 ns of its 330 ns
+                //  per column were these loads and stores when all 15 were issued regardless)
                 double own[15], piv[15];
+                const int nq = 16 - jt;  // columns j+1 .. c0+15 are q = 1 .. nq-1
 #pragma unroll
                 for (int q = 1; q < 16; ++q) {
-                    const int c = j + q < c0 + 16 ? j + q : j;  // (clamped: the value is not used beyond the block column)
-                    own[q - 1] = S[c * NP_LD + row];
-                    piv[q - 1] = S[c * NP_LD + j];
+                    own[q - 1] = 0.0;
+                    piv[q - 1] = 0.0;
+                    if (q < nq) {
+                        own[q - 1] = S[(j + q) * NP_LD + row];
+                        piv[q - 1] = S[(j + q) * NP_LD + j];
+                    }
                 }
                 const double x = S[j * NP_LD + row];
                 const double l = use_rcp ? x * rcp : x / d;
                 if (!(fabs(l) <= 0.999)) bad = true;  // |l| <= 1 everywhere is "IDAMAX picks the diagonal" (NaN fails the test too)
 #pragma unroll
                 for (int q = 1; q < 16; ++q)
-                    if (j + q < c0 + 16) S[(j + q) * NP_LD + row] = own[q - 1] - l * piv[q - 1];
+                    if (q < nq) S[(j + q) * NP_LD + row] = own[q - 1] - l * piv[q - 1];
                 S[j * NP_LD + row] = l;
             }
             __syncthreads();
