@@ -1013,7 +1013,7 @@ constexpr int TC_BLK = 16 * TC_LP;
 constexpr int TC_SMEM = 36 * TC_BLK * (int)sizeof(double);
 template <bool UPPER, bool RSIDE>
 __global__ void __launch_bounds__(256, 2) trsm_leaf_cols_kernel(int nb, int ncols, const double *__restrict__ T, long long ldt, long long st, double *B,
-                                                                long long ldb, long long sb, int vec_ok) {
+                                                                long long ldb, long long sb, int vec_ok, int32_t *viol) {
     constexpr bool UNIT = !UPPER && !RSIDE;
     extern __shared__ double sm[];
     double *Ts = sm;  // block (bi, bk): Ts[blk * TC_BLK + i * TC_LP + k] = T(16 bi + i, 16 bk + k); diagonal blocks hold their inverse
@@ -1141,6 +1141,15 @@ __global__ void __launch_bounds__(256, 2) trsm_leaf_cols_kernel(int nb, int ncol
                         for (int nt2 = 0; nt2 < 2; ++nt2) dmma884(wc[2 * bi + nt2][0], wc[2 * bi + nt2][1], ng[sl], bf2[j][nt2][sl]);
                     }
             }
+        }
+        if (RSIDE && viol != nullptr) {
+            // the no-interchange LU (k_getrf_nopiv): these are its multipliers L21; any |l| > 0.999 (or NaN) means partial pivoting
+            // would have interchanged and the factorization must be discarded
+            bool bad = false;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt)
+                if (col < ncols && nt < 2 * nblk) bad = bad || !(fabs(wc[nt][0]) <= 0.999) || !(fabs(wc[nt][1]) <= 0.999);
+            if (__any_sync(FULL, bad) && lane == 0) atomicOr(viol, 1);
         }
 #pragma unroll
         for (int nt = 0; nt < 16; ++nt) {
@@ -1678,7 +1687,8 @@ int trsm_leaf_dmma_launch(int nb, int ncols, const double *T, int ldt, long long
 }
 
 template <bool UPPER, bool RSIDE>
-int trsm_leaf_cols_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch) {
+int trsm_leaf_cols_launch(int nb, int ncols, const double *T, int ldt, long long st, double *B, int ldb, long long sb, int batch,
+                          int32_t *viol = nullptr) {
     static PerDevice<bool> attr_pd;  // function attributes are per device
     bool &attr = attr_pd();
     if (!attr) {
@@ -1690,7 +1700,7 @@ int trsm_leaf_cols_launch(int nb, int ncols, const double *T, int ldt, long long
     if (gx > chunks) gx = chunks;
     if (gx < 1) gx = 1;
     const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15u) == 0 && (ldb % 2) == 0 && (sb % 2) == 0) ? 1 : 0;
-    trsm_leaf_cols_kernel<UPPER, RSIDE><<<dim3(gx, batch), 256, TC_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb, vec_ok);
+    trsm_leaf_cols_kernel<UPPER, RSIDE><<<dim3(gx, batch), 256, TC_SMEM, ctx().stream>>>(nb, ncols, T, ldt, st, B, ldb, sb, vec_ok, viol);
     FM_LAUNCH_CHECK();
     return FM_OK;
 }
@@ -2157,16 +2167,6 @@ __global__ void iota_pivots_kernel(int n, int32_t *ipiv, long long sp, int32_t *
     if (blockIdx.x == 0 && threadIdx.x == 0) info[blockIdx.y] = 0;
 }
 
-// raises *viol when some multiplier below the diagonal of rows [r0, m) x columns [c0, c0 + w) exceeds 0.999 in magnitude (or is NaN)
-__global__ void __launch_bounds__(256) multiplier_check_kernel(int r0, int m, int c0, int w, const double *a, long long lda, long long sa, int32_t *viol) {
-    const double *p = a + blockIdx.z * sa;
-    bool bad = false;
-    for (int c = c0 + blockIdx.y; c < c0 + w; c += gridDim.y)
-        for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
-            if (!(fabs(p[c * lda + i]) <= 0.999)) bad = true;
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(viol, 1);
-}
-
 // idx[i] = original row that LAPACK's interchange sequence leaves at position i (sequential: one thread)
 __global__ void perm_forward_kernel(int n, const int32_t *ipiv, int32_t *idx) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -2282,13 +2282,8 @@ int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long l
         rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "getf2_nopiv launch failed");
         count_launch();
         if (rest <= 0 || rc != FM_OK) break;
-        rc = trsm_leaf_cols_launch<false, true>(jb, rest, ut, NB, (long long)NB * NB, akk + jb, lda, sa, batch);  // L21 = A21 U11^-1
-        if (rc == FM_OK) {
-            dim3 grid(std::min(ceil_div(rest, 256), 8), std::min(jb, 64), batch);
-            multiplier_check_kernel<<<grid, 256, 0, ctx().stream>>>(j1, n, j0, jb, a, lda, sa, viol);
-            rc = cudaGetLastError() == cudaSuccess ? FM_OK : set_error(FM_ERR_CUDA, "multiplier_check launch failed");
-            count_launch();
-        }
+        // L21 = A21 U11^-1; the kernel checks the multipliers it produces (|l| <= 0.999) and raises *viol otherwise
+        rc = trsm_leaf_cols_launch<false, true>(jb, rest, ut, NB, (long long)NB * NB, akk + jb, lda, sa, batch, viol);
         if (rc == FM_OK) rc = trsm_leaf<false>(jb, rest, akk, lda, sa, a + (size_t)j1 * lda + j0, lda, sa, batch);  // U12 = L11^-1 A12
         if (rc == FM_OK)
             rc = gemm_minus(rest, rest, jb, akk + jb, lda, sa, a + (size_t)j1 * lda + j0, lda, sa, a + (size_t)j1 * lda + j1, lda, sa, batch);
