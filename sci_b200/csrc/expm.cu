@@ -272,9 +272,8 @@ namespace {
 int expm_checked(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out,
                  bool host_out, int32_t *info_host) {
     static const bool always_pivot = getenv("FLOMAT_EXPM_PIVOT") != nullptr;  // developer switch: the pivoting LU from the start (A/B timing)
-    // the no-interchange LU has no look-ahead (diagonal block, two leaf solves and the trailing product run one after the other), which
-    // the pivoting LU's panel || product overlap makes up for at large n: measured equal at n = 8192, 9-27 % faster for n <= 2048
-    static const int nopiv_max_n = getenv("FLOMAT_EXPM_NOPIV_MAX_N") ? atoi(getenv("FLOMAT_EXPM_NOPIV_MAX_N")) : 4096;
+    // (no-interchange cluster panels with look-ahead exist up to 16384 rows; beyond that the pivoting LU)
+    static const int nopiv_max_n = getenv("FLOMAT_EXPM_NOPIV_MAX_N") ? atoi(getenv("FLOMAT_EXPM_NOPIV_MAX_N")) : 16384;
     bool pivot = always_pivot || n > nopiv_max_n;
     FM_TRY(expm_pipeline(n, a, lda, sa, out, ldo, so, batch, mode, s_out, host_out, false, pivot));
     InfoBack &g_info = g_info_pd();

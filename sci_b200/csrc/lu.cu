@@ -127,10 +127,14 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // U12 is written back to the pivot rows one leaf later (after the cluster barrier that proves every CTA has read the old
 // values).  ipiv gets LAPACK's interchange sequence, map[] the panel's net permutation.
 // ---------------------------------------------------------------------------------------------
-template <int NT, int RPT, int MINB = 1>
+// NOPIV (round 2): the no-interchange variant for matrices on which partial pivoting provably never interchanges (the Pade denominator
+// inside expm, see k_getrf_nopiv below).  The pivot of step q is panel row q, known in advance: its owner thread publishes the row and
+// its warp pushes it to every CTA -- no thread/warp/CTA/cluster argmax, no __syncthreads in the column step of a cluster.  Every
+// multiplier is checked (|l| <= 0.999, finite nonzero pivot: exactly "IDAMAX would have picked the diagonal") and *viol raised otherwise.
+template <int NT, int RPT, int MINB = 1, bool NOPIV = false>
 __global__ void __launch_bounds__(NT, MINB)
 lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, int32_t *ipiv, long long sp, int32_t *info, int2 *map,
-                long long smap) {
+                long long smap, int32_t *viol) {
     constexpr int W = LEAF, NWARP = NT / 32, ROWS = NT * RPT;
     uint32_t crank, csize;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -146,16 +150,20 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     // dynamic smem: the U12 blocks, double buffered, U(i, c) at sU[buf][i * UP + c]; then (MINB == 1) the multiplier tile
     // sLm[local row * LP + k] of the DMMA rank-16 update
     extern __shared__ double dyn[];
-    __shared__ __align__(8) unsigned long long s_bar[3];
+    // NOPIV: a ring of 32 (two leaves) -- only the owner of a pivot row sends, so nothing holds a fast CTA back within a leaf (the
+    // cluster barrier of step 4 does between leaves); with an all-to-all exchange per step (pivoting) three buffers are enough
+    constexpr int NBAR = NOPIV ? 32 : 3;
+    __shared__ __align__(8) unsigned long long s_bar[NBAR];
     __shared__ int s_wpos[2][NWARP];                         // position of each warp's candidate (NOROW: none)
     __shared__ __align__(16) double s_wdata[2][NWARP][PAY];  // each warp's candidate: head | 1/pivot | 16 row values
-    __shared__ __align__(16) double s_cand[3][MAXC][PAY];    // every CTA's candidate; step q uses buffer q % 3
+    __shared__ __align__(16) double s_cand[3][MAXC][PAY];    // every CTA's candidate; step q uses buffer q % 3 (NOPIV: a flat ring of 32 rows)
+    static_assert(3 * MAXC >= 32, "the NOPIV ring of 32 pivot rows lives in s_cand");
     __shared__ double s_L[W][W + 1];                         // L11 of the current leaf (row j: multipliers of pivot row j)
     __shared__ int s_pphys[NB];                              // physical panel row of every pivot
 
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[b])) : "memory");
+        for (int b = 0; b < NBAR; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsmem(&s_bar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 2 * NWARP) (&s_wpos[0][0])[tid] = NOROW;
@@ -163,7 +171,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     cluster_arrive();
     cluster_wait();
-    const uint32_t tx_bytes = csize * PAY * 8;
+    const uint32_t tx_bytes = (NOPIV ? 1u : csize) * PAY * 8;  // NOPIV: one sender per step (the owner of the pivot row)
     // the lean batched configuration (MINB > 1) is only ever launched as a single CTA: the exchange code is compiled out
     const bool solo = (MINB > 1) || (csize == 1);
     // this warp pushes the CTA's candidate to CTAs warp, warp + NWARP, ...: remote addresses of s_cand[0][crank][lane] and
@@ -184,6 +192,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
     for (int k = 0; k < RPT; ++k) pos[k] = (rbase + k * NT < m) ? rbase + k * NT : ~0x3fffffff;
 
     int pend_lc0 = -1;  // leaf whose U12 still has to be written to the pivot rows
+    bool nopiv_bad = false;
 
     for (int lc0 = 0; lc0 < pw; lc0 += W) {
         const int w = min(W, pw - lc0);
@@ -211,9 +220,16 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         PROF_ADD(8, tl0, tl1);
         // thread-level candidate among this thread's rows in play: largest |x| (x = slot 0), lowest position on ties (IDAMAX).
         // key = bits(|x|); rows out of play carry position NOROW and never win.
-        auto thread_best = [&](unsigned long long &bkey, int &bpos, int &kb, double &brcp) {
+        auto thread_best = [&](const int qn, unsigned long long &bkey, int &bpos, int &kb, double &brcp) {
             bkey = 0ull; bpos = NOROW; kb = 0;
             double bval = 1.0;
+            if (NOPIV) {  // the candidate is row qn itself: this thread has it or has nothing
+#pragma unroll
+                for (int k = 0; k < RPT; ++k)
+                    if (rbase + k * NT == qn && pos[k] >= 0) { bpos = qn; kb = k; bval = v[k][0]; bkey = 1ull; }
+                brcp = 1.0 / bval;
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
                 const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v[k][0]));
@@ -227,7 +243,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
         // read where the winning warp published it (solo_src = that warp).
         int solo_src = 0;
         auto publish_and_push = [&](const int q, const bool iwin, const int bpos, const int kb, const double brcp) {
-            const int buf = q % 3, wb = q & 1;
+            const int buf = NOPIV ? q % 32 : q % 3, wb = q & 1;
             PROF_T(tp0);
             if (tid == 0 && !solo)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsmem(&s_bar[buf])), "r"(tx_bytes) : "memory");
@@ -244,6 +260,24 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             }
             PROF_T(tp1);
             PROF_ADD(4, tp0, tp1);
+            if (NOPIV) {
+                // the owner of row q is one thread of one CTA: its warp pushes the row to every CTA (itself included); everybody else
+                // goes straight to the mbarrier.  A single CTA reads the row where it was published, behind one barrier.
+                if (solo) {
+                    __syncthreads();
+                    solo_src = ((q % ROWS) % NT) >> 5;
+                    return;
+                }
+                if (__any_sync(FULL, iwin)) {
+                    __syncwarp();
+                    const double payload = s_wdata[wb][warp][lane < PAY ? lane : 0];
+                    if (lane < PAY) {
+                        const uint32_t la = lsmem(&s_cand[0][0][0]) + (uint32_t)((buf * PAY + lane) * 8), lb = lsmem(&s_bar[buf]);
+                        for (uint32_t d = 0; d < csize; ++d) st_async(mapa(la, d), payload, mapa(lb, d));
+                    }
+                }
+                return;
+            }
             __syncthreads();
             PROF_T(tp2);
             PROF_ADD(5, tp1, tp2);
@@ -270,24 +304,26 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
 
         {
             unsigned long long bkey; int bpos, kb; double brcp;
-            thread_best(bkey, bpos, kb, brcp);
-            const bool iwin = warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW);
+            thread_best(lc0, bkey, bpos, kb, brcp);
+            const bool iwin = NOPIV ? bpos != NOROW : warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW);
             publish_and_push(lc0, iwin, bpos, kb, brcp);
         }
 #pragma unroll 1
         for (int j = 0; j < w; ++j) {
             const int q = lc0 + j;  // pivot index inside the panel
-            const int buf = q % 3;
+            const int buf = NOPIV ? q % 32 : q % 3;
             if (lane == 0) s_wpos[(q + 1) & 1][warp] = NOROW;  // reset for the next publish (last read before the previous barrier)
             PROF_T(tc0);
-            if (!solo) bar_wait(lsmem(&s_bar[buf]), (q / 3) & 1);
+            if (!solo) bar_wait(lsmem(&s_bar[buf]), NOPIV ? (q / 32) & 1 : (q / 3) & 1);
             PROF_T(tc1);
             PROF_ADD(0, tc0, tc1);
             // global winner: same decision in every warp (lane d looks at CTA d's candidate).  The winner's row is read through an
             // explicit shared-space address: a generic pointer that may point into either array costs a window-base computation
             // (S2UR SR_CgaCtaId + LEA) on the critical chain of every step.
             uint32_t prow;
-            if (!solo) {
+            if (NOPIV && !solo) {
+                prow = lsmem(&s_cand[0][0][0]) + (uint32_t)(buf * PAY * 8);  // ring slot of this step
+            } else if (!solo) {
                 const long long c0 = lane < (int)csize ? __double_as_longlong(s_cand[buf][lane][0]) : ((long long)NOROW << 32);
                 const int cp = (int)(c0 >> 32);
                 const unsigned long long ck = cp != NOROW ? (unsigned long long)__double_as_longlong(fabs(s_cand[buf][lane < (int)csize ? lane : 0][2])) : 0ull;
@@ -323,6 +359,7 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             PROF_ADD(1, tc1, tc2);
             const bool use_rcp = fabs(pval) >= DBL_MIN;  // DGETF2: scale by the reciprocal unless the pivot is tiny
             const int last = W - 1 - j;                   // slots 1..last hold trailing columns; beyond them earlier multipliers
+            if (NOPIV && (!(fabs(pval) > 0.0) || !(fabs(pval) < DBL_MAX))) nopiv_bad = true;  // a zero / non-finite pivot is not a dominant one
             double l[RPT], app[RPT];
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
@@ -331,16 +368,17 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
                 if (mine) pos[k] = ~q;
                 const bool active = (pos[k] >= 0 && pval != 0.0);
                 l[k] = active ? (use_rcp ? v[k][0] * rcp : v[k][0] / pval) : 0.0;
+                if (NOPIV && !(fabs(l[k]) <= 0.999)) nopiv_bad = true;  // |l| <= 1 everywhere is "IDAMAX picks the diagonal"
                 app[k] = active ? l[k] : v[k][0];
                 v[k][0] = v[k][1] - l[k] * (last >= 1 ? pm[1] : 0.0);  // next column first
             }
             // reduction for pivot q+1 on the freshly updated next column, issued before the rest of the update
             unsigned long long bkey; int bpos, kb; double brcp;
-            thread_best(bkey, bpos, kb, brcp);
+            thread_best(q + 1, bkey, bpos, kb, brcp);
             const bool more = j + 1 < w;
             PROF_T(tc3);
             PROF_ADD(2, tc2, tc3);
-            const bool iwin = more ? warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW) : false;
+            const bool iwin = !more ? false : (NOPIV ? bpos != NOROW : warp_argmax(bpos != NOROW ? bkey : 0ull, bpos, bpos != NOROW));
 #pragma unroll
             for (int c = 2; c < W; ++c) {
                 const double pc = (c <= last) ? pm[c] : 0.0;
@@ -528,6 +566,9 @@ lu_panel_kernel(double *a, long long lda, long long sa, int m, int pw, int j0, i
             const int q = ~pos[k];
             if (q < pw) map[q] = make_int2(j0 + q, j0 + r);  // final row q comes from physical row r
         }
+    }
+    if (NOPIV) {
+        if (__syncthreads_or(nopiv_bad) && tid == 0 && viol != nullptr) atomicOr(viol, 1);
     }
     if (crank == 0) {
         // a top row (physical row < 128: thread r % NT, slot r / NT of CTA 0) that never became a pivot ends where the
@@ -1543,13 +1584,14 @@ struct Maps {
 template <int NT, int RPT, int MINB>
 constexpr int panel_dyn_smem() { return (2 * LEAF * UP + (MINB == 1 ? NT * RPT * LP : 0)) * (int)sizeof(double); }
 
-template <int NT, int RPT, int MINB = 1>
-int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize) {
+template <int NT, int RPT, int MINB = 1, bool NOPIV = false>
+int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int csize,
+                 int32_t *viol = nullptr) {
     static PerDevice<bool> attr_pd;  // function attributes are per device
     bool &attr = attr_pd();
     if (!attr) {
-        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_dyn_smem<NT, RPT, MINB>()));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB, NOPIV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        FM_CUDA(cudaFuncSetAttribute(lu_panel_kernel<NT, RPT, MINB, NOPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_dyn_smem<NT, RPT, MINB>()));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1564,8 +1606,8 @@ int launch_panel(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long s
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT, MINB>, A.at(j0, j0), (long long)A.lda, A.stride, m, pw, j0, ipiv, sp, info,
-                               maps.panel(j0), maps.item_stride));
+    FM_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<NT, RPT, MINB, NOPIV>, A.at(j0, j0), (long long)A.lda, A.stride, m, pw, j0, ipiv, sp, info,
+                               maps.panel(j0), maps.item_stride, viol));
     count_launch();
     return FM_OK;
 }
@@ -1575,7 +1617,18 @@ int panel_tall_entry(const Mat &A, int j0, int m, int pw, int32_t *ipiv, int32_t
 
 // factor the m x pw panel whose top-left element is A(j0, j0): one cluster launch.  One row per thread whenever the cluster
 // (<= 16 CTAs) can cover the panel: the column step is latency bound, so fewer rows per thread is faster.
-int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int *csize_out = nullptr) {
+// viol != nullptr: the no-interchange variant of the cluster kernel (single matrices, m <= 16384; see lu_panel_kernel<.., NOPIV>)
+int panel_factor(const Mat &A, int j0, int m, int pw, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int *csize_out = nullptr,
+                 int32_t *viol = nullptr) {
+    if (viol) {
+        auto pow2 = [](int rows, int per_cta) { int cs = 1; while (cs * per_cta < rows) cs *= 2; return cs; };
+        if (A.batch != 1 || m > 16384) return set_error(FM_ERR_ARG, "getrf_nopiv: no-interchange cluster panels are for single matrices of <= 16384 rows");
+        if (csize_out) *csize_out = m <= 2048 ? pow2(m, 128) : (m <= 4096 ? pow2(m, 256) : 16);
+        if (m <= 2048) return launch_panel<128, 1, 1, true>(A, j0, m, pw, ipiv, sp, info, maps, pow2(m, 128), viol);
+        if (m <= 4096) return launch_panel<256, 1, 1, true>(A, j0, m, pw, ipiv, sp, info, maps, pow2(m, 256), viol);
+        if (m <= 8192) return launch_panel<256, 2, 1, true>(A, j0, m, pw, ipiv, sp, info, maps, 16, viol);
+        return launch_panel<256, 4, 1, true>(A, j0, m, pw, ipiv, sp, info, maps, 16, viol);
+    }
     if (const char *tm = getenv("FLOMAT_LU_TALL_MIN"))  // test hook: send panels of more than this many rows to the tall fallback
         if (m > atoi(tm) && A.batch == 1) return panel_tall_entry(A, j0, m, pw, ipiv, info, maps, csize_out);
     auto pow2_ctas = [](int rows, int per_cta) {
@@ -1865,17 +1918,19 @@ int rgetrf(const Mat &A, int m, int j0, int w, int32_t *ipiv, long long sp, int3
 // is launched as a programmatic dependent of the panel kernel (the panel's CTAs are resident before the GEMM's first CTA
 // is placed, so the two never fight over the 16 SMs of the cluster) and waits for the panel before it exits, which keeps
 // plain stream order valid for everything queued afterwards.
-int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps) {
+int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int32_t *viol = nullptr) {
+    // viol != nullptr: no-interchange panels (k_getrf_nopiv for large single matrices): same schedule, and no row permutations at all
     const int mn = m < n ? m : n;
     const bool overlap = A.batch == 1 && getenv("FLOMAT_LU_NO_LOOKAHEAD") == nullptr;
     int csize = 1;
-    FM_TRY(panel_factor(A, 0, m, mn < NB ? mn : NB, ipiv, sp, info, maps, &csize));
+    FM_TRY(panel_factor(A, 0, m, mn < NB ? mn : NB, ipiv, sp, info, maps, &csize, viol));
     for (int j0 = 0; j0 < mn; j0 += NB) {
         const int jb = std::min(NB, mn - j0), j1 = j0 + jb;
         // panel j0 is complete: its interchanges go to its own and to the trailing columns now; the columns to its left (L)
         // are off the critical chain and get all their interchanges in one pass at the end.  (csize == 0: the tall fallback
         // has already interchanged the panel's own columns.)
-        if (csize == 0) FM_TRY(permute_rows(A, j1, n - j1, maps, j0, j1));
+        if (viol) { /* identity */ }
+        else if (csize == 0) FM_TRY(permute_rows(A, j1, n - j1, maps, j0, j1));
         else FM_TRY(permute_rows(A, j0, n - j0, maps, j0, j1));
         const int nr = n - j1;
         if (nr <= 0) break;
@@ -1885,7 +1940,7 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
         const int jb2 = j1 < mn ? std::min(NB, mn - j1) : 0;
         if (jb2 > 0) {  // next panel's columns first, then its factorization runs beside the rest of the update
             FM_TRY(gemm_minus(mrest, jb2, jb, A.at(j1, j0), A.lda, A.stride, A.at(j0, j1), A.lda, A.stride, A.at(j1, j1), A.lda, A.stride, A.batch));
-            FM_TRY(panel_factor(A, j1, mrest, jb2, ipiv, sp, info, maps, &csize));
+            FM_TRY(panel_factor(A, j1, mrest, jb2, ipiv, sp, info, maps, &csize, viol));
         }
         const int nb_cols = nr - jb2;
         if (nb_cols > 0) {
@@ -1894,6 +1949,7 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
                               A.stride, A.batch, (dep && csize > 0) ? ctx().sm_count - csize : 0, dep && csize > 0));
         }
     }
+    if (viol) return FM_OK;
     return permute_rows(A, 0, mn, maps, 0, mn, true);  // L part: column c receives the interchanges of every panel right of it
 }
 
@@ -2267,6 +2323,19 @@ int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long l
     iota_pivots_kernel<<<dim3(n > 0 ? std::min(ceil_div(n, 256), 64) : 1, batch), 256, 0, ctx().stream>>>(n, ipiv, sp, info);
     FM_LAUNCH_CHECK();
     if (n == 0) return FM_OK;
+    // Large single matrices: the look-ahead schedule of the pivoting LU (panel k+1 beside the trailing update of panel k) with the
+    // no-interchange variant of the cluster panel kernel.  Small and batched ones: one CTA per diagonal block, below.
+    // (measured, ms: n = 2048 2.24 cluster / 1.85 diagonal block; 4096 4.99 / 4.96; 8192 17.2 / 19.0; the pivoting LU: 3.15, 7.1, 21.5)
+    static const int cluster_min_n = getenv("FLOMAT_NOPIV_CLUSTER_MIN_N") ? atoi(getenv("FLOMAT_NOPIV_CLUSTER_MIN_N")) : 6144;
+    if (batch == 1 && n >= cluster_min_n && n <= 16384) {
+        Mat A{a, lda, sa, 1};
+        const int npanels = ceil_div(n, NB);
+        Maps maps;
+        maps.item_stride = (long long)npanels * MAPN;
+        maps.base = g_maps_getrf().get((size_t)maps.item_stride);
+        if (!maps.base) return FM_ERR_NOMEM;
+        return getrf_lookahead(A, n, n, ipiv, sp, info, maps, viol);
+    }
     static PerDevice<bool> attr_pd;  // function attributes are per device
     if (!attr_pd()) {
         FM_CUDA(cudaFuncSetAttribute(getf2_nopiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SMEM));

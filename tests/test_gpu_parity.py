@@ -410,7 +410,7 @@ def test_inverse_general_matrix_with_interchanges(fm, ref, n):
         gate_inverse(f"inv (general) n={n}", a, Ai.to_numpy(), ref.inv(a), n)
 
 
-@pytest.mark.parametrize("n", [1, 7, 16, 33, 128, 130, 257, 512, 1000, 2304])
+@pytest.mark.parametrize("n", [1, 7, 16, 33, 128, 130, 257, 512, 1000, 2304, 6144, 6401])
 def test_lu_without_interchanges_is_dgetrf_on_dominant_matrices(fm, ref, n):
     """fm_getrf_nopiv (the solve inside expm): on a strictly column diagonally dominant matrix partial pivoting never interchanges, so
     the verified no-interchange LU must reproduce the oracle's dgetrf -- ipiv = 1..n, same factors within 64 n eps -- and report no
