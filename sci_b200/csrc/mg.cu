@@ -33,7 +33,6 @@ constexpr int MG_MAX = 8;  // the peer-store epilogue addresses at most 7 peers;
 // nobody waits at a later barrier for a worker that has bailed out.
 class Workers {
   public:
-    int size() const { return n_; }
     int start(int n, const int *devices) {
         n_ = n;
         fail_.assign(n, 0);
