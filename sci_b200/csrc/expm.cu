@@ -197,7 +197,7 @@ int expm_pipeline(int n, const double *a, int lda, long long sa, double *out, in
     FM_CUDA(cudaMemcpyAsync(g_info.h, d_info, (size_t)(batch + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));  // info words + violation word
     FM_CUDA(cudaEventRecord(g_info.ready, st));
     if (!honour_singular) {
-        FM_TRY(k_getrs(n, n, den, ldw, sw, d_ipiv, n, num, ldw, sw, batch));
+        FM_TRY(k_getrs(n, n, den, ldw, sw, pivot ? d_ipiv : nullptr, n, num, ldw, sw, batch));  // (no interchanges: no row permutation of num)
     } else {
         // second pass after a singular denominator was seen: items with info > 0 keep num (dgesv leaves B untouched)
         FM_CUDA(cudaEventSynchronize(g_info.ready));

@@ -2365,6 +2365,10 @@ int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int3
             int batch) {
     if (n < 0 || nrhs < 0 || lda < (n > 1 ? n : 1) || ldb < (n > 1 ? n : 1) || batch < 0) return set_error(FM_ERR_ARG, "getrs: bad dimensions");
     if (n == 0 || nrhs == 0 || batch == 0) return FM_OK;
+    if (ipiv == nullptr) {  // the factorization had no interchanges (k_getrf_nopiv): P = I, just the two triangular sweeps
+        FM_TRY(rtrsm<false>(n, nrhs, lu, lda, sa, b, ldb, sb, batch));
+        return rtrsm<true>(n, nrhs, lu, lda, sa, b, ldb, sb, batch);
+    }
     Mat B{b, ldb, sb, batch};
     const int nblocks = ceil_div(n, NB);
     Maps maps;
