@@ -173,6 +173,10 @@ int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info);
  * 0.999 in magnitude or a pivot is zero / not finite -- i.e. if partial pivoting WOULD have interchanged -- in which case the result
  * must be discarded and fm_getrf used on the original matrix.  When *violated == 0 the factors are dgetrf's (same pivots: none). */
 int fm_getrf_nopiv(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int32_t *violated);
+/* The factorisation dgesv_ / dgetrf_ run on a HOST matrix of n >= 6144 (columns arrive in chunks of `chunk` columns, a multiple of
+ * 128, while earlier chunks are factored; left-looking over the chunks), here on a matrix already in HBM: for tests and timing.
+ * Same result as fm_getrf up to the summation order of the Schur updates. */
+int fm_getrf_chunked(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int chunk);
 int fm_getrs(int n, int nrhs, const double *lu, int lda, const int32_t *ipiv, double *b, int ldb);
 /* dgesv semantics (flomat.rkt:2112): with info > 0 (exactly singular U) the solve is skipped and B is left untouched, which is
  * what flomat-solve-many! (:2135-2142, info ignored) then returns.  Reads info back once (4 bytes, syncs). */

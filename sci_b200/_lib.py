@@ -90,6 +90,7 @@ SIGNATURES = {
                                  c_longlong, c_double, c_int]),
     "fm_getrf": (c_int, [c_int, c_int, _DP, c_int, _IP, _IP]),
     "fm_getrf_nopiv": (c_int, [c_int, _DP, c_int, _IP, _IP, _IP]),
+    "fm_getrf_chunked": (c_int, [c_int, _DP, c_int, _IP, _IP, c_int]),
     "fm_getrs": (c_int, [c_int, c_int, _DP, c_int, _IP, _DP, c_int]),
     "fm_gesv": (c_int, [c_int, c_int, _DP, c_int, _IP, _DP, c_int, _IP]),
     "fm_getri": (c_int, [c_int, _DP, c_int, _IP, _IP]),

@@ -566,6 +566,132 @@ int dgemm_host_pipeline(int m, int n, int k, double alpha, const double *a, int 
     if (dc) fm_free(dc);
     return rc;
 }
+
+// dgesv_ / dgetrf_ on a HOST matrix (the reference's call: flomat.rkt:2140 / :1510 hand over GC memory).  Upload, factorisation and
+// download used to run one after the other (n = 8192: 20 + 21.5 + 11 ms); here A goes up in column chunks on the transfer stream
+// while k_getrf_streamed factors the chunks that have arrived, and every part of L\U comes down on the download stream as soon as
+// no later step can touch it.  nrhs > 0: also solves for b (host or device) when the factorisation succeeded.  *hinfo = LAPACK info.
+int lu_pipeline_min_n() {  // read at every call (tests lower it): below it upload, factorisation and download run one after the other
+    if (getenv("FLOMAT_CUDA_NO_LU_PIPELINE")) return 0x7fffffff;
+    const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_MIN_N");
+    return e && atoi(e) >= 256 ? atoi(e) : 6144;
+}
+// chunk bounds of the pipeline: the first chunk is small (nothing overlaps its upload), the widths then double (wide chunks factor
+// closer to the rate of the plain LU) up to `cap` (nothing overlaps the download of the last chunk's rows either)
+std::vector<int> lu_chunk_bounds(int n, int first, int cap) {
+    std::vector<int> b{0};
+    for (int k = 0; b.back() < n; ++k) {
+        long long w = (long long)first << (k > 1 ? k - 1 : 0);  // first, first, 2 first, 4 first, ...
+        if (w > cap) w = cap;
+        long long next = b.back() + w;
+        if (next >= n || n - next < 128) next = n;
+        b.push_back((int)next);
+    }
+    return b;
+}
+int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, double *b, int ldb, int32_t *hinfo) {
+    FM_TRY(xfer_init());
+    const int ldd = n + (n & 1);
+    int first = 1024, cap = (n / 4 / 128) * 128;
+    if (cap < first) cap = first;
+    if (const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_CHUNK")) { const int v = atoi(e); if (v >= 128 && v % 128 == 0) first = cap = v; }  // developer switch: uniform chunks
+    const std::vector<int> bounds = lu_chunk_bounds(n, first, cap);
+    const int nchunks = (int)bounds.size() - 1;
+    auto chunk_of = [&](int c0) { int j = 0; while (bounds[j] != c0) ++j; return j; };
+    int rc = FM_OK;
+    double *da = static_cast<double *>(fm_alloc_bytes((size_t)ldd * n * 8));
+    const bool ipiv_dev = is_device_ptr(ipiv);
+    int32_t *d_ipiv = ipiv_dev ? ipiv : static_cast<int32_t *>(fm_alloc_bytes((size_t)n * 4 + 16));
+    int32_t *d_info = ipiv_dev ? static_cast<int32_t *>(fm_alloc_bytes(16)) : (d_ipiv ? d_ipiv + n : nullptr);
+    if (!da || !d_ipiv || !d_info) rc = set_error(FM_ERR_NOMEM, "dgesv_/dgetrf_: staging allocation failed (n=%d)", n);
+    static PerDevice<std::vector<cudaEvent_t>> ev_pd;  // [3j] chunk j uploaded, [3j+1] its U rows final, [3j+2] its own rows final
+    std::vector<cudaEvent_t> &ev = ev_pd();
+    while (rc == FM_OK && (int)ev.size() < 3 * nchunks) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "getrf_host_pipeline: event creation failed");
+        else ev.push_back(e);
+    }
+    auto chk = [&](cudaError_t e) { if (e != cudaSuccess && rc == FM_OK) rc = set_error(FM_ERR_CUDA, "dgesv_/dgetrf_ (host pipeline): %s", cudaGetErrorString(e)); };
+    // developer switch: per chunk, when its upload / factorisation / download finished (ms after the call started)
+    static const bool trace = getenv("FLOMAT_HOST_LU_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr;
+    if (trace) {
+        tr.resize(1 + 4 * (size_t)nchunks);
+        for (auto &e : tr) cudaEventCreate(&e);
+        cudaEventRecord(tr[0], ctx().stream);
+        for (int j = 0; j < nchunks; ++j) cudaEventRecord(tr[2 + 4 * j], ctx().stream);  // chunk 0 has no U rows: keep the event valid
+    }
+    {
+        Staged B;  // released (after a sync of the compute stream) before da is
+        if (rc == FM_OK && nrhs > 0) rc = B.in(b, ldb, n, nrhs, true);
+        if (rc == FM_OK) {
+            chk(cudaEventRecord(xfer().tmp, ctx().stream));  // the staging blocks may be recycled ones that queued kernels still use
+            chk(cudaStreamWaitEvent(xfer().stream, xfer().tmp, 0));
+        }
+        auto arrive = [&](int c0, int c1) -> int {
+            const int j = chunk_of(c0);
+            FM_TRY(copy_h2d(da + (size_t)c0 * ldd, ldd, a + (size_t)c0 * lda, lda, n, c1 - c0, xfer().stream));
+            FM_CUDA(cudaEventRecord(ev[3 * j], xfer().stream));
+            FM_CUDA(cudaStreamWaitEvent(ctx().stream, ev[3 * j], 0));
+            if (trace) cudaEventRecord(tr[1 + 4 * j], xfer().stream);
+            return FM_OK;
+        };
+        auto upper_done = [&](int c0, int) -> int {
+            const int j = chunk_of(c0);
+            FM_CUDA(cudaEventRecord(ev[3 * j + 1], ctx().stream));
+            if (trace) cudaEventRecord(tr[2 + 4 * j], ctx().stream);
+            return FM_OK;
+        };
+        auto done = [&](int c0, int) -> int {
+            const int j = chunk_of(c0);
+            FM_CUDA(cudaEventRecord(ev[3 * j + 2], ctx().stream));
+            if (trace) cudaEventRecord(tr[3 + 4 * j], ctx().stream);
+            return FM_OK;
+        };
+        if (rc == FM_OK) rc = k_getrf_streamed(n, da, ldd, d_ipiv, d_info, bounds, arrive, upper_done, done);
+        // The solve is queued before the factors' way back so that it runs beside the downloads.  With the right-hand sides in a staging
+        // block that is safe when A turns out singular (LAPACK: b untouched): the block is simply not copied back.
+        bool solved = false;
+        if (rc == FM_OK && nrhs > 0 && B.owned) {
+            rc = k_getrs(n, nrhs, da, ldd, 0, d_ipiv, 0, B.dev, B.ld, 0, 1);
+            solved = true;
+        }
+        // downloads come after every upload is queued: a copy to pageable memory blocks this thread until it has run
+        for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
+            const int c0 = bounds[j], c1 = bounds[j + 1];
+            const int r1 = j == nchunks - 1 ? n : c1;
+            if (c0 > 0) {  // U above the chunk: final once the triangular solve of the chunk has run
+                chk(cudaStreamWaitEvent(xfer().down, ev[3 * j + 1], 0));
+                if (rc == FM_OK) rc = copy_d2h(a + (size_t)c0 * lda, lda, da + (size_t)c0 * ldd, ldd, c0, c1 - c0, xfer().down);
+            }
+            chk(cudaStreamWaitEvent(xfer().down, ev[3 * j + 2], 0));
+            if (rc == FM_OK) rc = copy_d2h(a + c0, lda, da + c0, ldd, r1 - c0, c1, xfer().down);  // rows of the chunk, columns up to it
+            if (trace) cudaEventRecord(tr[4 + 4 * j], xfer().down);
+        }
+        int32_t info = 0;
+        if (rc == FM_OK) rc = fm_download_i32(&info, d_info, 1);  // synchronises the compute stream
+        if (rc == FM_OK && nrhs > 0 && !solved && info == 0) rc = k_getrs(n, nrhs, da, ldd, 0, d_ipiv, 0, B.dev, B.ld, 0, 1);  // b in HBM: only now
+        if (rc == FM_OK && nrhs > 0 && info == 0) rc = B.out();
+        if (rc == FM_OK && !ipiv_dev) rc = fm_download_i32(ipiv, d_ipiv, (size_t)n);
+        if (rc == FM_OK) *hinfo = info;
+        chk(cudaEventRecord(xfer().last, xfer().stream));
+        chk(cudaEventRecord(xfer().last_down, xfer().down));
+        xfer().dirty = true;
+        cudaStreamSynchronize(xfer().stream);
+        cudaStreamSynchronize(xfer().down);  // pinned host memory: the copies above were asynchronous
+        cudaStreamSynchronize(ctx().stream);
+    }
+    if (trace) {
+        auto at = [&](size_t i) { float ms = 0.f; return cudaEventElapsedTime(&ms, tr[0], tr[i]) == cudaSuccess ? ms : -1.f; };
+        fprintf(stderr, "[host LU pipeline] n=%d nrhs=%d: %d chunks\n[host LU pipeline] chunk  columns  uploaded  U rows final  factored  downloaded (ms)\n", n, nrhs, nchunks);
+        for (int j = 0; j < nchunks; ++j)
+            fprintf(stderr, "[host LU pipeline] %5d  %7d  %8.2f  %12.2f  %8.2f  %10.2f\n", j, bounds[j + 1] - bounds[j], at(1 + 4 * j), at(2 + 4 * j), at(3 + 4 * j), at(4 + 4 * j));
+        for (auto &e : tr) cudaEventDestroy(e);
+    }
+    if (da) fm_free(da);
+    if (ipiv_dev) { if (d_info) fm_free(d_info); } else if (d_ipiv) fm_free(d_ipiv);
+    return rc;
+}
 }  // namespace fm
 extern "C" {
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta, double *c, int ldc,
@@ -593,6 +719,13 @@ int fm_dgemm_batched(int m, int n, int k, double alpha, const double *a, int lda
 int fm_getrf(int m, int n, double *a, int lda, int32_t *ipiv, int32_t *info) {
     FM_TRY(ensure_init());
     return k_getrf(m, n, a, lda, 0, ipiv, 0, info, 1);
+}
+int fm_getrf_chunked(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int chunk) {
+    FM_TRY(ensure_init());
+    if (!ipiv || !info) return set_error(FM_ERR_ARG, "fm_getrf_chunked: ipiv and info must be device pointers");
+    if (chunk < 128 || chunk % 128 != 0) return set_error(FM_ERR_ARG, "fm_getrf_chunked: chunk must be a positive multiple of 128");
+    auto nothing = [](int, int) { return FM_OK; };
+    return k_getrf_streamed(n, a, lda, ipiv, info, lu_chunk_bounds(n, chunk, chunk), nothing, nothing, nothing);
 }
 int fm_getrf_nopiv(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int32_t *violated) {
     FM_TRY(ensure_init());
@@ -1068,7 +1201,11 @@ void dgetrf_(const int *m, const int *n, double *a, const int *lda, int32_t *ipi
     *info = lapack_arg_check_getrf(*m, *n, *lda);
     if (*info != 0 || *m == 0 || *n == 0) return;
     int rc = ensure_init();
-    if (rc == FM_OK) {
+    if (rc == FM_OK && *m == *n && *n >= lu_pipeline_min_n() && !is_device_ptr(a)) {
+        int32_t hinfo = 0;
+        rc = getrf_host_pipeline(*n, a, *lda, ipiv, 0, nullptr, 1, &hinfo);
+        if (rc == FM_OK) *info = hinfo;
+    } else if (rc == FM_OK) {
         const int mn = *m < *n ? *m : *n;
         Staged A;
         rc = A.in(a, *lda, *m, *n, true);
@@ -1100,7 +1237,11 @@ void dgesv_(const int *n, const int *nrhs, double *a, const int *lda, int32_t *i
     else if (*ldb < (*n > 1 ? *n : 1)) *info = -7;
     if (*info != 0 || *n == 0) return;
     int rc = ensure_init();
-    if (rc == FM_OK) {
+    if (rc == FM_OK && *n >= lu_pipeline_min_n() && !is_device_ptr(a)) {
+        int32_t hinfo = 0;
+        rc = getrf_host_pipeline(*n, a, *lda, ipiv, *nrhs, b, *ldb, &hinfo);
+        if (rc == FM_OK) *info = hinfo;
+    } else if (rc == FM_OK) {
         Staged A, B;
         rc = A.in(a, *lda, *n, *n, true);
         if (rc == FM_OK) rc = B.in(b, *ldb, *n, *nrhs, true);

@@ -1,6 +1,8 @@
 // common.cuh -- shared context, error plumbing and small device helpers for libflomat_cuda (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
+#include <vector>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -125,6 +127,10 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
             double *c, int ldc, long long sc, int batch, const GemmEpilogue &ep);
 // lu.cu
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
+int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, const std::vector<int> &bounds,
+                     const std::function<int(int, int)> &arrive, const std::function<int(int, int)> &upper_done,
+                     const std::function<int(int, int)> &done);
+std::vector<int> lu_chunk_bounds(int n, int first, int cap);
 int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int32_t *viol, int batch);
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);

@@ -718,6 +718,8 @@ bool g_half_enabled = getenv("FLOMAT_GEMM_NO_HALF") == nullptr;  // developer sw
 bool g_splitk_enabled = getenv("FLOMAT_GEMM_NO_SPLITK") == nullptr;
 bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
 bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
+// shortest k slice of a split-K product.  64 against 128 (round 1): 256^3 19.1 -> 14.8 us, 384^3 19.3 -> 15.1, 512^3 20.2 -> 19.6 (tools/small_gemm_time.py)
+int g_splitk_min_k = getenv("FLOMAT_GEMM_SPLITK_MIN_K") && atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) >= 16 ? atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) : 64;
 bool g_copier_enabled = getenv("FLOMAT_GEMM_NO_COPIER") == nullptr;  // off: the consumer warps store to the peers themselves (round-1 epilogue)
 int g_copier_min_peers = getenv("FLOMAT_GEMM_COPIER_MIN_PEERS") ? atoi(getenv("FLOMAT_GEMM_COPIER_MIN_PEERS")) : 3;
 int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
@@ -766,7 +768,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
         const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
         if (half && g_splitk_enabled && half_tiles <= ctx().sm_count && k >= 256 && epi.npeers == 0 && !epi.active_until) {
             int ksplit = (int)((2LL * ctx().sm_count) / half_tiles);
-            if (ksplit > k / 128) ksplit = k / 128;
+            if (ksplit > k / g_splitk_min_k) ksplit = k / g_splitk_min_k;
             if (ksplit > 16) ksplit = 16;
             if (ksplit >= 2) {
                 const long long ldw = m + (m & 1), wz = ldw * n, kstride = wz * batch;

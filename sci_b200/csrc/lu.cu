@@ -1918,13 +1918,17 @@ int rgetrf(const Mat &A, int m, int j0, int w, int32_t *ipiv, long long sp, int3
 // is launched as a programmatic dependent of the panel kernel (the panel's CTAs are resident before the GEMM's first CTA
 // is placed, so the two never fight over the 16 SMs of the cluster) and waits for the panel before it exits, which keeps
 // plain stream order valid for everything queued afterwards.
-int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int32_t *viol = nullptr) {
+// jbeg > 0 (a multiple of NB; k_getrf_streamed): factor the columns [jbeg, n) only -- the updates of the columns left of jbeg have been
+// applied to them already, and the interchanges found here go to [jbeg, n) and to nothing else.
+int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int32_t *viol = nullptr,
+                    int jbeg = 0) {
     // viol != nullptr: no-interchange panels (k_getrf_nopiv for large single matrices): same schedule, and no row permutations at all
     const int mn = m < n ? m : n;
+    if (jbeg >= mn) return FM_OK;
     const bool overlap = A.batch == 1 && getenv("FLOMAT_LU_NO_LOOKAHEAD") == nullptr;
     int csize = 1;
-    FM_TRY(panel_factor(A, 0, m, mn < NB ? mn : NB, ipiv, sp, info, maps, &csize, viol));
-    for (int j0 = 0; j0 < mn; j0 += NB) {
+    FM_TRY(panel_factor(A, jbeg, m - jbeg, mn - jbeg < NB ? mn - jbeg : NB, ipiv, sp, info, maps, &csize, viol));
+    for (int j0 = jbeg; j0 < mn; j0 += NB) {
         const int jb = std::min(NB, mn - j0), j1 = j0 + jb;
         // panel j0 is complete: its interchanges go to its own and to the trailing columns now; the columns to its left (L)
         // are off the critical chain and get all their interchanges in one pass at the end.  (csize == 0: the tall fallback
@@ -1950,7 +1954,7 @@ int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int
         }
     }
     if (viol) return FM_OK;
-    return permute_rows(A, 0, mn, maps, 0, mn, true);  // L part: column c receives the interchanges of every panel right of it
+    return permute_rows(A, jbeg, mn - jbeg, maps, jbeg, mn, true);  // L part: column c receives the interchanges of every panel right of it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2310,6 +2314,50 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     if (n > mn) {  // wide matrix: U12 = L11^-1 (P A12)
         FM_TRY(permute_rows(A, mn, n - mn, maps, 0, mn));
         FM_TRY(rtrsm<false>(mn, n - mn, a, lda, sa, A.at(0, mn), lda, sa, batch));
+    }
+    return FM_OK;
+}
+
+// LU of a square matrix whose columns ARRIVE in chunks (the host-operand dgesv_ / dgetrf_: the upload of chunk c+1 runs beside the
+// arithmetic of chunk c) and whose finished parts LEAVE early.  Left-looking over the chunks [bounds[c], bounds[c+1]) (multiples of
+// 128 except the last bound, n), the look-ahead schedule inside one:
+//     arrive(c0, c1)      -- the caller makes columns [c0, c1) valid on the compute stream
+//     P, L11^-1           -- the interchanges of every panel left of c0, then U(0:c0, chunk) = L(0:c0, 0:c0)^-1 A(0:c0, chunk)
+//     upper_done(c0, c1)  -- rows [0, c0) of columns [c0, c1) are FINAL (the caller may start to download them)
+//     Schur, getrf        -- A(c0:, chunk) -= L(c0:, 0:c0) U, then columns [c0, c1) of rows [c0, n) with getrf_lookahead
+//     interchanges of [c0, c1) to the columns left of c0
+//     done(c0, c1)        -- rows [c0, c1) of columns [0, c1) are FINAL (later interchanges move rows >= c1 only); after the last
+//                            chunk: rows [c0, n)
+// The same arithmetic as k_getrf up to the summation order of the Schur updates (one k = c0 product per chunk instead of c0/128
+// rank-128 updates), so a pivot can differ from k_getrf's only where two candidates agree to rounding.  What it costs: the panel
+// chain of a chunk is no longer hidden behind the update of the whole trailing matrix (device-resident n = 8192: 21.5 ms k_getrf,
+// 24.5 / 28.6 / 32.5 ms with chunks of 4096 / 2048 / 1024 columns: tools/chunked_lu_time.py) -- less than the transfers it hides.
+int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, const std::vector<int> &bounds,
+                     const std::function<int(int, int)> &arrive, const std::function<int(int, int)> &upper_done,
+                     const std::function<int(int, int)> &done) {
+    if (n < 0 || lda < (n > 1 ? n : 1) || bounds.size() < 2 || bounds.front() != 0 || bounds.back() != n)
+        return set_error(FM_ERR_ARG, "getrf_streamed: bad dimensions");
+    for (size_t c = 0; c + 1 < bounds.size(); ++c)
+        if (bounds[c + 1] <= bounds[c] || bounds[c] % NB != 0) return set_error(FM_ERR_ARG, "getrf_streamed: chunk bounds must increase in multiples of %d", NB);
+    zero_info_kernel<<<1, 256, 0, ctx().stream>>>(info, 1);
+    FM_LAUNCH_CHECK();
+    Mat A{a, lda, 0, 1};
+    Maps maps;
+    maps.item_stride = (long long)ceil_div(n, NB) * MAPN;
+    maps.base = g_maps_getrf().get((size_t)maps.item_stride);
+    if (!maps.base) return FM_ERR_NOMEM;
+    for (size_t c = 0; c + 1 < bounds.size(); ++c) {
+        const int c0 = bounds[c], c1 = bounds[c + 1], w = c1 - c0;
+        FM_TRY(arrive(c0, c1));
+        if (c0 > 0) {
+            FM_TRY(permute_rows(A, c0, w, maps, 0, c0));
+            FM_TRY(rtrsm<false>(c0, w, a, lda, 0, A.at(0, c0), lda, 0, 1));
+            FM_TRY(upper_done(c0, c1));
+            FM_TRY(gemm_minus(n - c0, w, c0, A.at(c0, 0), lda, 0, A.at(0, c0), lda, 0, A.at(c0, c0), lda, 0, 1));
+        }
+        FM_TRY(getrf_lookahead(A, n, c1, ipiv, 0, info, maps, nullptr, c0));
+        if (c0 > 0) FM_TRY(permute_rows(A, 0, c0, maps, c0, c1));
+        FM_TRY(done(c0, c1));
     }
     return FM_OK;
 }
