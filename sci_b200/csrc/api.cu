@@ -592,8 +592,9 @@ std::vector<int> lu_chunk_bounds(int n, int first, int cap) {
 int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, double *b, int ldb, int32_t *hinfo) {
     FM_TRY(xfer_init());
     const int ldd = n + (n & 1);
-    int first = 1024, cap = (n / 4 / 128) * 128;
+    int first = 1024, cap = (n / 4 / 128) * 128;  // two chunks (a window) arrive before the first panel can start; 512 .. 2048 measured alike
     if (cap < first) cap = first;
+    if (const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_FIRST")) { const int v = atoi(e); if (v >= 128 && v % 128 == 0) { first = v; if (cap < first) cap = first; } }
     if (const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_CHUNK")) { const int v = atoi(e); if (v >= 128 && v % 128 == 0) first = cap = v; }  // developer switch: uniform chunks
     const std::vector<int> bounds = lu_chunk_bounds(n, first, cap);
     const int nchunks = (int)bounds.size() - 1;
@@ -604,7 +605,8 @@ int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, doub
     int32_t *d_ipiv = ipiv_dev ? ipiv : static_cast<int32_t *>(fm_alloc_bytes((size_t)n * 4 + 16));
     int32_t *d_info = ipiv_dev ? static_cast<int32_t *>(fm_alloc_bytes(16)) : (d_ipiv ? d_ipiv + n : nullptr);
     if (!da || !d_ipiv || !d_info) rc = set_error(FM_ERR_NOMEM, "dgesv_/dgetrf_: staging allocation failed (n=%d)", n);
-    static PerDevice<std::vector<cudaEvent_t>> ev_pd;  // [3j] chunk j uploaded, [3j+1] its U rows final, [3j+2] its own rows final
+    static PerDevice<std::vector<cudaEvent_t>> ev_pd;  // [3j] chunk j uploaded, [3j+1] its rows above the window final, [3j+2] its own rows final
+    std::vector<int> upper_rows((size_t)nchunks, 0), done_cols((size_t)nchunks, 0);  // what the two events of chunk j cover
     std::vector<cudaEvent_t> &ev = ev_pd();
     while (rc == FM_OK && (int)ev.size() < 3 * nchunks) {
         cudaEvent_t e;
@@ -636,14 +638,16 @@ int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, doub
             if (trace) cudaEventRecord(tr[1 + 4 * j], xfer().stream);
             return FM_OK;
         };
-        auto upper_done = [&](int c0, int) -> int {
+        auto upper_done = [&](int c0, int, int rows) -> int {
             const int j = chunk_of(c0);
+            upper_rows[j] = rows;
             FM_CUDA(cudaEventRecord(ev[3 * j + 1], ctx().stream));
             if (trace) cudaEventRecord(tr[2 + 4 * j], ctx().stream);
             return FM_OK;
         };
-        auto done = [&](int c0, int) -> int {
+        auto done = [&](int c0, int, int lim) -> int {
             const int j = chunk_of(c0);
+            done_cols[j] = lim;
             FM_CUDA(cudaEventRecord(ev[3 * j + 2], ctx().stream));
             if (trace) cudaEventRecord(tr[3 + 4 * j], ctx().stream);
             return FM_OK;
@@ -657,16 +661,19 @@ int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, doub
             solved = true;
         }
         // downloads come after every upload is queued: a copy to pageable memory blocks this thread until it has run
-        for (int j = 0; j < nchunks && rc == FM_OK; ++j) {
-            const int c0 = bounds[j], c1 = bounds[j + 1];
-            const int r1 = j == nchunks - 1 ? n : c1;
-            if (c0 > 0) {  // U above the chunk: final once the triangular solve of the chunk has run
+        // in the order the events fire: step j - 1 releases the upper rows of chunk j, then (its panels done) the rows of chunk j - 1
+        for (int j = 0; j <= nchunks && rc == FM_OK; ++j) {
+            if (j < nchunks && upper_rows[j] > 0) {  // rows [0, upper_rows) of chunk j's columns
+                const int c0 = bounds[j], c1 = bounds[j + 1];
                 chk(cudaStreamWaitEvent(xfer().down, ev[3 * j + 1], 0));
-                if (rc == FM_OK) rc = copy_d2h(a + (size_t)c0 * lda, lda, da + (size_t)c0 * ldd, ldd, c0, c1 - c0, xfer().down);
+                if (rc == FM_OK) rc = copy_d2h(a + (size_t)c0 * lda, lda, da + (size_t)c0 * ldd, ldd, upper_rows[j], c1 - c0, xfer().down);
             }
-            chk(cudaStreamWaitEvent(xfer().down, ev[3 * j + 2], 0));
-            if (rc == FM_OK) rc = copy_d2h(a + c0, lda, da + c0, ldd, r1 - c0, c1, xfer().down);  // rows of the chunk, columns up to it
-            if (trace) cudaEventRecord(tr[4 + 4 * j], xfer().down);
+            if (j > 0) {  // rows of chunk j - 1 (the last chunk: down to row n) of the columns [0, done_cols)
+                const int i = j - 1, r0 = bounds[i], r1 = i == nchunks - 1 ? n : bounds[i + 1];
+                chk(cudaStreamWaitEvent(xfer().down, ev[3 * i + 2], 0));
+                if (rc == FM_OK) rc = copy_d2h(a + r0, lda, da + r0, ldd, r1 - r0, done_cols[i], xfer().down);
+                if (trace) cudaEventRecord(tr[4 + 4 * i], xfer().down);
+            }
         }
         int32_t info = 0;
         if (rc == FM_OK) rc = fm_download_i32(&info, d_info, 1);  // synchronises the compute stream
@@ -725,7 +732,8 @@ int fm_getrf_chunked(int n, double *a, int lda, int32_t *ipiv, int32_t *info, in
     if (!ipiv || !info) return set_error(FM_ERR_ARG, "fm_getrf_chunked: ipiv and info must be device pointers");
     if (chunk < 128 || chunk % 128 != 0) return set_error(FM_ERR_ARG, "fm_getrf_chunked: chunk must be a positive multiple of 128");
     auto nothing = [](int, int) { return FM_OK; };
-    return k_getrf_streamed(n, a, lda, ipiv, info, lu_chunk_bounds(n, chunk, chunk), nothing, nothing, nothing);
+    auto nothing3 = [](int, int, int) { return FM_OK; };
+    return k_getrf_streamed(n, a, lda, ipiv, info, lu_chunk_bounds(n, chunk, chunk), nothing, nothing3, nothing3);
 }
 int fm_getrf_nopiv(int n, double *a, int lda, int32_t *ipiv, int32_t *info, int32_t *violated) {
     FM_TRY(ensure_init());

@@ -128,8 +128,8 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
 // lu.cu
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
 int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, const std::vector<int> &bounds,
-                     const std::function<int(int, int)> &arrive, const std::function<int(int, int)> &upper_done,
-                     const std::function<int(int, int)> &done);
+                     const std::function<int(int, int)> &arrive, const std::function<int(int, int, int)> &upper_done,
+                     const std::function<int(int, int, int)> &done);
 std::vector<int> lu_chunk_bounds(int n, int first, int cap);
 int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int32_t *viol, int batch);
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);

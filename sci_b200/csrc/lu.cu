@@ -1918,12 +1918,13 @@ int rgetrf(const Mat &A, int m, int j0, int w, int32_t *ipiv, long long sp, int3
 // is launched as a programmatic dependent of the panel kernel (the panel's CTAs are resident before the GEMM's first CTA
 // is placed, so the two never fight over the 16 SMs of the cluster) and waits for the panel before it exits, which keeps
 // plain stream order valid for everything queued afterwards.
-// jbeg > 0 (a multiple of NB; k_getrf_streamed): factor the columns [jbeg, n) only -- the updates of the columns left of jbeg have been
-// applied to them already, and the interchanges found here go to [jbeg, n) and to nothing else.
+// jbeg > 0 / jend >= 0 (multiples of NB; k_getrf_streamed): factor the panels [jbeg, jend) only -- the updates of the columns left of
+// jbeg have been applied to [jbeg, n) already; the interchanges and updates of these panels go to the columns [jbeg, n) and to
+// nothing else, and the panel at jend is left unfactored.
 int getrf_lookahead(const Mat &A, int m, int n, int32_t *ipiv, long long sp, int32_t *info, const Maps &maps, int32_t *viol = nullptr,
-                    int jbeg = 0) {
+                    int jbeg = 0, int jend = -1) {
     // viol != nullptr: no-interchange panels (k_getrf_nopiv for large single matrices): same schedule, and no row permutations at all
-    const int mn = m < n ? m : n;
+    const int mn = (jend >= 0 && jend < (m < n ? m : n)) ? jend : (m < n ? m : n);  // one past the last pivot factored here
     if (jbeg >= mn) return FM_OK;
     const bool overlap = A.batch == 1 && getenv("FLOMAT_LU_NO_LOOKAHEAD") == nullptr;
     int csize = 1;
@@ -2318,23 +2319,25 @@ int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long 
     return FM_OK;
 }
 
-// LU of a square matrix whose columns ARRIVE in chunks (the host-operand dgesv_ / dgetrf_: the upload of chunk c+1 runs beside the
-// arithmetic of chunk c) and whose finished parts LEAVE early.  Left-looking over the chunks [bounds[c], bounds[c+1]) (multiples of
-// 128 except the last bound, n), the look-ahead schedule inside one:
-//     arrive(c0, c1)      -- the caller makes columns [c0, c1) valid on the compute stream
-//     P, L11^-1           -- the interchanges of every panel left of c0, then U(0:c0, chunk) = L(0:c0, 0:c0)^-1 A(0:c0, chunk)
-//     upper_done(c0, c1)  -- rows [0, c0) of columns [c0, c1) are FINAL (the caller may start to download them)
-//     Schur, getrf        -- A(c0:, chunk) -= L(c0:, 0:c0) U, then columns [c0, c1) of rows [c0, n) with getrf_lookahead
-//     interchanges of [c0, c1) to the columns left of c0
-//     done(c0, c1)        -- rows [c0, c1) of columns [0, c1) are FINAL (later interchanges move rows >= c1 only); after the last
-//                            chunk: rows [c0, n)
+// LU of a square matrix whose columns ARRIVE in chunks (the host-operand dgesv_ / dgetrf_: the upload of a chunk runs beside the
+// arithmetic of the chunks before it) and whose finished parts LEAVE early.  Chunks are [bounds[c], bounds[c+1]) (multiples of 128
+// except the last bound, n).  Step c works on a window of two chunks, c (to be factored) and c+1 (just arrived):
+//     arrive(n0, n1)           -- the caller makes the columns of chunk c+1 valid on the compute stream
+//     catch-up of chunk c+1    -- against the chunks LEFT of c, in one piece: the interchanges of their panels, U(0:c0, chunk c+1) =
+//                                 L(0:c0, 0:c0)^-1 A(0:c0, chunk c+1), A(c0:, chunk c+1) -= L(c0:, 0:c0) U
+//     upper_done(n0, n1, c0)   -- rows [0, c0) of columns [n0, n1) are FINAL (the caller may start to download them)
+//     getrf_lookahead          -- the panels of chunk c, right-looking over the window [c0, n1): the update of chunk c+1 by chunk c's
+//                                 panels sits in the look-ahead slots, beside the next panel's factorisation
+//     the interchanges of chunk c to the columns left of c0
+//     done(c0, c1, lim)        -- rows [c0, c1) of columns [0, lim = n1) are FINAL (later interchanges move rows >= c1 only); after the
+//                                 last chunk: rows [c0, n)
 // The same arithmetic as k_getrf up to the summation order of the Schur updates (one k = c0 product per chunk instead of c0/128
 // rank-128 updates), so a pivot can differ from k_getrf's only where two candidates agree to rounding.  What it costs: the panel
-// chain of a chunk is no longer hidden behind the update of the whole trailing matrix (device-resident n = 8192: 21.5 ms k_getrf,
-// 24.5 / 28.6 / 32.5 ms with chunks of 4096 / 2048 / 1024 columns: tools/chunked_lu_time.py) -- less than the transfers it hides.
+// chain is hidden behind the update of a two-chunk window instead of the whole trailing matrix, and the catch-ups are not hidden at
+// all (device-resident n = 8192: tools/chunked_lu_time.py) -- less than the transfers it hides.
 int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, const std::vector<int> &bounds,
-                     const std::function<int(int, int)> &arrive, const std::function<int(int, int)> &upper_done,
-                     const std::function<int(int, int)> &done) {
+                     const std::function<int(int, int)> &arrive, const std::function<int(int, int, int)> &upper_done,
+                     const std::function<int(int, int, int)> &done) {
     if (n < 0 || lda < (n > 1 ? n : 1) || bounds.size() < 2 || bounds.front() != 0 || bounds.back() != n)
         return set_error(FM_ERR_ARG, "getrf_streamed: bad dimensions");
     for (size_t c = 0; c + 1 < bounds.size(); ++c)
@@ -2346,18 +2349,25 @@ int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, co
     maps.item_stride = (long long)ceil_div(n, NB) * MAPN;
     maps.base = g_maps_getrf().get((size_t)maps.item_stride);
     if (!maps.base) return FM_ERR_NOMEM;
-    for (size_t c = 0; c + 1 < bounds.size(); ++c) {
-        const int c0 = bounds[c], c1 = bounds[c + 1], w = c1 - c0;
-        FM_TRY(arrive(c0, c1));
-        if (c0 > 0) {
-            FM_TRY(permute_rows(A, c0, w, maps, 0, c0));
-            FM_TRY(rtrsm<false>(c0, w, a, lda, 0, A.at(0, c0), lda, 0, 1));
-            FM_TRY(upper_done(c0, c1));
-            FM_TRY(gemm_minus(n - c0, w, c0, A.at(c0, 0), lda, 0, A.at(0, c0), lda, 0, A.at(c0, c0), lda, 0, 1));
+    const size_t nchunks = bounds.size() - 1;
+    FM_TRY(arrive(bounds[0], bounds[1]));
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int c0 = bounds[c], c1 = bounds[c + 1];
+        int lim = c1;
+        if (c + 1 < nchunks) {
+            const int n0 = c1, n1 = bounds[c + 2], w = n1 - n0;
+            lim = n1;
+            FM_TRY(arrive(n0, n1));
+            if (c0 > 0) {
+                FM_TRY(permute_rows(A, n0, w, maps, 0, c0));
+                FM_TRY(rtrsm<false>(c0, w, a, lda, 0, A.at(0, n0), lda, 0, 1));
+                FM_TRY(upper_done(n0, n1, c0));
+                FM_TRY(gemm_minus(n - c0, w, c0, A.at(c0, 0), lda, 0, A.at(0, n0), lda, 0, A.at(c0, n0), lda, 0, 1));
+            }
         }
-        FM_TRY(getrf_lookahead(A, n, c1, ipiv, 0, info, maps, nullptr, c0));
+        FM_TRY(getrf_lookahead(A, n, lim, ipiv, 0, info, maps, nullptr, c0, c1));
         if (c0 > 0) FM_TRY(permute_rows(A, 0, c0, maps, c0, c1));
-        FM_TRY(done(c0, c1));
+        FM_TRY(done(c0, c1, lim));
     }
     return FM_OK;
 }

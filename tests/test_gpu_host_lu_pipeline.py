@@ -146,7 +146,7 @@ np.save(sys.argv[1], A); np.save(sys.argv[2], ipiv)
 
 def test_dgesv_host_pipeline_at_config_3_size(fm, ref):
     """BASELINE config 3 through the reference's own call: n = 8192, 64 right-hand sides, pageable host memory, default chunking
-    (1024, 1024, 2048, 2048, 2048 columns), against the oracle at 1x the gate."""
+    (1024, 1024, 2048, 2048, 2048 columns, a window of two chunks), against the oracle at 1x the gate."""
     lib = fm.load()
     n, nrhs = 8192, 64
     a, b = rnd(7500, n, n), rnd(7501, n, nrhs)
