@@ -255,6 +255,12 @@ int fm_dgemm_colshard(int m, int nloc, int k, const double *a, int lda, const do
  * Only the untransposed product is sharded; trans flags other than 111/111 are rejected (use fm_dgemm).
  * fm_mg_expm_batched: as fm_expm_batched with the items split into one contiguous block per device (no exchange); host operands
  *   or device operands on the caller's device.  s_out (host, `batch` doubles, may be NULL).
+ * fm_mg_expm: ONE matrix exponential (`expm`, expm.rkt:203) over the whole group (SURVEY 8e "single large expm ... via its dgemms"):
+ *   every device holds full copies of the operands; each of the 5+s / 11+s products is sharded by column blocks and its tiles are
+ *   stored into every peer's copy by the GEMM epilogue (fused all-gather); the Pade denominator's LU is replicated, the triangular
+ *   solves are sharded by right-hand-side columns; elementwise steps are replicated.  a and out: both host memory (each device moves
+ *   its column block over its own PCIe link) or both on the calling thread's device.  Blocks until `out` is complete.  Same results
+ *   as fm_expm up to the tile shapes of the products (<= 64 n eps, tested); n < 128 * devices runs on one device.
  * LU / solve / inv / det are single-GPU (north_star).
  * ---------------------------------------------------------------------------------------------- */
 int fm_mg_init(int ndev);                 /* <= 0: all visible devices (at most 8); idempotent for the same count */
@@ -263,6 +269,7 @@ int fm_mg_dgemm(int transA, int transB, int m, int n, int k, double alpha, const
                 int ldb, double beta, double *c, int ldc);
 int fm_mg_expm_batched(int n, const double *a, int lda, long long stride_a, double *out, int ldo, long long stride_o,
                        int batch, int mode, double *s_out);
+int fm_mg_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info);
 int fm_mg_sync(void);                     /* wait for every device of the group */
 /* the partitions the two calls above use: columns in whole 128-column tile columns, items in contiguous blocks (host arithmetic only) */
 int fm_mg_column_block(int n, int world, int r, int *first, int *count);

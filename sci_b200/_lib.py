@@ -107,6 +107,7 @@ SIGNATURES = {
     "fm_mg_device_count": (c_int, []),
     "fm_mg_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
     "fm_mg_expm_batched": (c_int, [c_int, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_int, c_int, c_void_p]),
+    "fm_mg_expm": (c_int, [c_int, _DP, c_int, _DP, c_int, c_int, POINTER(c_double), POINTER(c_int32)]),
     "fm_mg_sync": (c_int, []),
     "fm_mg_column_block": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "fm_mg_item_block": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),

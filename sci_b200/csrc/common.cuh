@@ -115,6 +115,7 @@ struct GemmEpilogue {
     double alpha = 1.0, beta = 0.0;
     double diag = 0.0;          // added to C[i,i] after alpha/beta (fused `+ c*I`)
     bool has_diag = false;
+    int diag_col0 = 0;          // C is the column block [diag_col0, ...) of a larger matrix: diag goes to C[j + diag_col0, j]
     double *const *peers = nullptr;  // host array of peer C base pointers (column-shard P2P epilogue)
     int npeers = 0;
     const int32_t *active_until = nullptr;  // batched: item z is skipped when round >= active_until[z]
@@ -148,6 +149,19 @@ int k_swap(long long n, double *x, long long incx, double *y, long long incy);
 int k_gemv(int trans, int m, int n, double alpha, const double *a, int lda, const double *x, long long incx, double beta, double *y, long long incy);
 int k_larnv(int idist, int32_t *iseed_host, long long n, double *x);
 // expm.cu
+// one matrix exponential over the devices of a group (mg.cu: fm_mg_expm): every device keeps full copies of the operands, computes
+// its column block of every product and stores the finished tiles into every peer's copy (the fused all-gather epilogue of dgemm.cu)
+struct ExpmShard {
+    int rank = 0, world = 1;
+    int j0 = 0, nloc = 0;                         // this device's column block
+    const int *device = nullptr;                  // [world] CUDA device of every rank
+    double *const (*ws)[6] = nullptr;             // [world][6] the six n x n workspaces (leading dimension n + (n & 1)) of every rank
+    std::function<int(int)> barrier;              // barrier(rc): everything queued so far on every device completes before anything queued
+                                                  // afterwards on any device starts; returns the group's common verdict
+};
+int k_expm_workspace(int n, double *ws[6]);
+int k_expm_sharded(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *flags_host, const ExpmShard &sh,
+                   int *result_ws);
 int k_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info_host);
 int k_expm_host_out(int n, const double *a, int lda, double *host_out, int ldh, int mode, double *s_out, int32_t *info_host);
 // host(m x n) := dev(m x n) on the download stream, behind the work queued on the compute stream so far and beside what is queued

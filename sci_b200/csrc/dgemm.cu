@@ -66,6 +66,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 struct EpiParams {
     double alpha, beta, diag;
     int has_diag;
+    int diag_col0;  // the diagonal term goes to the elements (row, col) with row == col + diag_col0 (C is a column block of a larger matrix)
     int npeers;
     double *peer[7];
     const int32_t *active_until;  // optional per-item round limit (batched squaring in expm)
@@ -369,7 +370,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // instead of ~45 (ncu source view, batched 256^3 products: the generic epilogue was 1/3 of the DMMA count in
             // issued instructions and 12% of the consumer warps' time, which two CTAs per SM only partly hide).
             double *p0 = Cz + (long long)(n_base + t) * ldc + m_base;
-            const bool dg = ep.has_diag && tm * BM < tn * BN + BN && tn * BN < tm * BM + BM;
+            const bool dg = ep.has_diag && tm * BM < tn * BN + ep.diag_col0 + BN && tn * BN + ep.diag_col0 < tm * BM + BM;
             if (ep.beta == 0.0 && !dg) {
 #pragma unroll
                 for (int ni = 0; ni < NT; ++ni)
@@ -383,7 +384,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (copier) post(tile);
                 continue;
             }
-            const int dm = m_base - (n_base + t);  // element (c, ni, x) sits on the diagonal iff dm + 2*c*GPB == 8*ni + 4*x
+            const int dm = m_base - (n_base + t + ep.diag_col0);  // element (c, ni, x) sits on the diagonal iff dm + 2*c*GPB == 8*ni + 4*x
             const double dgv = dg ? ep.diag : 0.0;
             if (ep.beta != 0.0) {
                 double *q = p0;
@@ -467,8 +468,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 v1 += ep.beta * old[d][x][c].y;
                             }
                             if (ep.has_diag) {
-                                if (m == n) v0 += ep.diag;
-                                if (m + 1 == n) v1 += ep.diag;
+                                if (m == n + ep.diag_col0) v0 += ep.diag;
+                                if (m + 1 == n + ep.diag_col0) v1 += ep.diag;
                             }
                             *reinterpret_cast<double2 *>(Cz + (long long)n * ldc + m) = make_double2(v0, v1);
 #pragma unroll
@@ -505,8 +506,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                     if (ep.has_diag) {
-                        if (m == n) v0 += ep.diag;
-                        if (m + 1 == n) v1 += ep.diag;
+                        if (m == n + ep.diag_col0) v0 += ep.diag;
+                        if (m + 1 == n + ep.diag_col0) v1 += ep.diag;
                     }
                     if (pair) {
                         *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
@@ -605,7 +606,7 @@ dgemm_generic_kernel(int ta, int tb, int M, int N, int K, const double *__restri
                     double *p = C + (long long)n * ldc + m;
                     double v = ep.alpha * acc[mi][ni][x];
                     if (ep.beta != 0.0) v += ep.beta * *p;
-                    if (ep.has_diag && m == n) v += ep.diag;
+                    if (ep.has_diag && m == n + ep.diag_col0) v += ep.diag;
                     *p = v;
 #pragma unroll
                     for (int r = 0; r < 7; ++r)
@@ -655,7 +656,7 @@ int make_map(CUtensorMap *map, const double *base, long long rows, long long col
 // split-K second pass: C := alpha * sum_s W_s + beta * C (+ diag on the diagonal), fixed summation order
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(int m, int n, int ksplit, const double *__restrict__ w, long long ldw, long long wz,
                                                              long long kstride, double *c, long long ldc, long long sc, double alpha, double beta,
-                                                             double diag, int has_diag) {
+                                                             double diag, int has_diag, int diag_col0) {
     const int z = blockIdx.z;
     for (int j = blockIdx.y; j < n; j += gridDim.y)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(int m, int n, int ks
             double v = alpha * acc;
             double *p = c + z * sc + j * ldc + i;
             if (beta != 0.0) v += beta * *p;
-            if (has_diag && i == j) v += diag;
+            if (has_diag && i == j + diag_col0) v += diag;
             *p = v;
         }
 }
@@ -742,6 +743,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.beta = epi.beta;
     ep.diag = epi.diag;
     ep.has_diag = epi.has_diag ? 1 : 0;
+    ep.diag_col0 = epi.diag_col0;
     ep.npeers = epi.npeers;
     for (int r = 0; r < 7; ++r) ep.peer[r] = r < epi.npeers ? epi.peers[r] : nullptr;
     ep.active_until = epi.active_until;
@@ -779,7 +781,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
                 e2.ksplit = ksplit; e2.kstride = kstride;
                 FM_TRY((launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, w, (int)ldw, wz, batch, e2, epi.max_sms)));
                 dim3 grid(ceil_div(m, 256), n < 1024 ? n : 1024, batch);
-                splitk_reduce_kernel<<<grid, 256, 0, ctx().stream>>>(m, n, ksplit, w, ldw, wz, kstride, c, ldc, sc, ep.alpha, ep.beta, ep.diag, ep.has_diag);
+                splitk_reduce_kernel<<<grid, 256, 0, ctx().stream>>>(m, n, ksplit, w, ldw, wz, kstride, c, ldc, sc, ep.alpha, ep.beta, ep.diag, ep.has_diag, ep.diag_col0);
                 FM_LAUNCH_CHECK();
                 return FM_OK;
             }

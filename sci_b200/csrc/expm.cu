@@ -307,6 +307,142 @@ int k_expm_host_out(int n, const double *a, int lda, double *host_out, int ldh, 
     return expm_checked(n, a, lda, 0, host_out, ldh, 0, 1, mode, s_out, true, info_host);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One matrix exponential on `world` devices ("single large expm -- via its dgemms", each product column-sharded and
+// all-gathered).  Every device runs this function with the full matrix A in its own memory:
+//   * elementwise steps and the norm are REPLICATED (n^2 work, cheaper than moving the result);
+//   * every product is SHARDED: rank r computes columns [j0, j0 + nloc) of Z = X Y from its full X and its block of Y, and the GEMM
+//     epilogue stores each finished tile into the same place of every peer's Z (the fused all-gather of dgemm.cu; the `c I` term of
+//     the reference's Horner steps goes to row j0 + j of local column j: GemmEpilogue::diag_col0);
+//   * the LU of the Pade denominator is replicated (no exchange at all), the two triangular solves are sharded by right-hand-side
+//     columns, and each device copies its block of the solution to its peers;
+//   * a group barrier (ExpmShard::barrier: events across the devices' streams) separates a product from what precedes and follows it.
+// out (device memory, may be null): receives the result; *result_ws: the workspace that holds it on every device.
+// flags_host[0] = LU info of this device's factorisation, flags_host[1] = the no-interchange LU's violation word; the caller falls
+// back to the one-device pipeline when either is set (a singular or non-dominant denominator: not reachable for finite input).
+// ---------------------------------------------------------------------------------------------
+int k_expm_workspace(int n, double *ws[6]) {
+    const int ldw = n + (n & 1);
+    for (int i = 0; i < 6; ++i) {
+        ws[i] = static_cast<double *>(g_pool_pd().get(i, (size_t)ldw * n * sizeof(double)));
+        if (!ws[i]) return FM_ERR_NOMEM;
+    }
+    return FM_OK;
+}
+
+int k_expm_sharded(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *flags_host, const ExpmShard &sh,
+                   int *result_ws) {
+    const bool minprod = (mode & 1) != 0, clamp = (mode & 2) != 0;
+    cudaStream_t st = ctx().stream;
+    const int ldw = n + (n & 1), r = sh.rank;
+    double *const *B = sh.ws[r];
+    int rc = FM_OK;
+    char *small = static_cast<char *>(g_pool_pd().get(6, 2 * sizeof(double) + 4 * sizeof(int32_t) + (size_t)n * sizeof(int32_t) + 128));
+    if (!small) rc = FM_ERR_NOMEM;
+    double *d_norm = reinterpret_cast<double *>(small), *d_scale = d_norm + 1;
+    int32_t *d_info = reinterpret_cast<int32_t *>(d_scale + 1), *d_viol = d_info + 1, *d_ipiv = d_viol + 1;
+    double h_norm = 0.0, h_scale = 1.0;
+    int rounds = 0;
+    if (rc == FM_OK) rc = k_norm1_batched(n, a, lda, 0, 1, d_norm);
+    if (rc == FM_OK && cudaMemcpyAsync(&h_norm, d_norm, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "expm (sharded): norm readback failed");
+    if (rc == FM_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "expm (sharded): synchronisation failed");
+    if (rc == FM_OK) {
+        if (std::isnan(h_norm) || std::isinf(h_norm))
+            rc = set_error(FM_ERR_NONFINITE, "expm: ||A||_1 is %f; the reference does not terminate on this input (expm.rkt:209)", h_norm);
+        else {
+            double s = scaling_exponent(h_norm);
+            if (clamp && !(s > 0.0)) s = 0.0;
+            if (s_out) *s_out = s;
+            h_scale = std::pow(2.0, s);
+            rounds = s > 0.0 ? (int)s : 0;
+            if (cudaMemcpyAsync(d_scale, &h_scale, sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "expm (sharded): scale upload failed");
+        }
+    }
+    // every device has read the same A and therefore found the same s; a failure anywhere ends the call everywhere
+    rc = sh.barrier(rc);
+    if (rc != FM_OK) return rc;
+
+    const size_t boff = (size_t)sh.j0 * ldw;
+    auto gemm = [&](int xi, int yi, int zi, double beta, bool has_diag, double diag) -> int {
+        int rc = sh.barrier(FM_OK);  // nobody still reads or writes buffer zi
+        if (rc != FM_OK) return rc;
+        double *peers[7];
+        int np = 0;
+        for (int p = 0; p < sh.world; ++p)
+            if (p != r) peers[np++] = sh.ws[p][zi] + boff;
+        GemmEpilogue ep;
+        ep.alpha = 1.0;
+        ep.beta = beta;
+        ep.has_diag = has_diag;
+        ep.diag = diag;
+        ep.diag_col0 = sh.j0;
+        ep.peers = peers;
+        ep.npeers = np;
+        if (sh.nloc > 0) rc = k_dgemm(FM_NO_TRANS, FM_NO_TRANS, n, sh.nloc, n, B[xi], ldw, 0, B[yi] + boff, ldw, 0, B[zi] + boff, ldw, 0, 1, ep);
+        return sh.barrier(rc);  // every block of zi has arrived on every device
+    };
+#define FM_STEP(call) do { rc = (call); if (rc != FM_OK) return fail(rc); } while (0)
+    // an error between two barriers must not leave the peers waiting at the next one: take part in it with the error, which ends them all
+    auto fail = [&](int rc) { sh.barrier(rc); return rc; };
+    auto lin = [&](double ci, double c1, const double *a1, double c2, const double *a2, double *o) {
+        return k_pade_terms(n, ldw, 1, a1, a2, ci, c1, c2, o, 0.0, 0.0, 0.0, nullptr);
+    };
+    auto lin2 = [&](const double *a1, const double *a2, double ci0, double c10, double c20, double *o0, double ci1, double c11, double c21, double *o1) {
+        return k_pade_terms(n, ldw, 1, a1, a2, ci0, c10, c20, o0, ci1, c11, c21, o1);
+    };
+    int E, O, num, den, spare;
+    FM_STEP(k_div_pow2_batched(n, a, lda, 0, B[0], ldw, 0, d_scale, 1));  // X = A/2^s, full copy on every device
+    rc = gemm(0, 0, 1, 0.0, false, 0.0);                                   // AA
+    if (rc != FM_OK) return rc;
+    if (!minprod) {  // the reference's Horner order (expm.rkt:167-177, 195-196), see expm_pipeline
+        FM_STEP(lin(kC[6], kC[8], B[1], 0.0, nullptr, B[2]));
+        if ((rc = gemm(1, 2, 3, 0.0, true, kC[4])) != FM_OK) return rc;
+        if ((rc = gemm(1, 3, 2, 0.0, true, kC[2])) != FM_OK) return rc;
+        if ((rc = gemm(1, 2, 3, 0.0, true, kC[0])) != FM_OK) return rc;
+        E = 3;
+        FM_STEP(lin(kC[5], kC[7], B[1], 0.0, nullptr, B[2]));
+        if ((rc = gemm(1, 2, 4, 0.0, true, kC[3])) != FM_OK) return rc;
+        if ((rc = gemm(1, 4, 2, 0.0, true, kC[1])) != FM_OK) return rc;
+        if ((rc = gemm(0, 2, 4, 0.0, false, 0.0)) != FM_OK) return rc;
+        O = 4; num = 2; den = 1; spare = 5;
+    } else {
+        if ((rc = gemm(1, 1, 2, 0.0, false, 0.0)) != FM_OK) return rc;  // X^4
+        FM_STEP(lin2(B[1], B[2], 0.0, kC[6], kC[8], B[3], kC[0], kC[2], kC[4], B[4]));
+        if ((rc = gemm(3, 2, 4, 1.0, false, 0.0)) != FM_OK) return rc;  // even
+        E = 4;
+        FM_STEP(lin2(B[1], nullptr, kC[5], kC[7], 0.0, B[3], kC[1], kC[3], 0.0, B[5]));
+        if ((rc = gemm(3, 2, 5, 1.0, false, 0.0)) != FM_OK) return rc;
+        if ((rc = gemm(0, 5, 3, 0.0, false, 0.0)) != FM_OK) return rc;  // odd
+        O = 3; num = 5; den = 1; spare = 2;
+    }
+    FM_STEP(k_addsub(n, n, B[E], ldw, B[O], ldw, B[num], ldw, B[den], ldw));
+    if (cudaMemsetAsync(d_viol, 0, sizeof(int32_t), st) != cudaSuccess) return fail(set_error(FM_ERR_CUDA, "expm (sharded): memset failed"));
+    static const bool always_pivot = getenv("FLOMAT_EXPM_PIVOT") != nullptr;
+    const bool pivot = always_pivot || n > 16384;
+    if (pivot) FM_STEP(k_getrf(n, n, B[den], ldw, 0, d_ipiv, n, d_info, 1));  // replicated: every device factors its own copy
+    else FM_STEP(k_getrf_nopiv(n, B[den], ldw, 0, d_ipiv, n, d_info, d_viol, 1));
+    if (cudaMemcpyAsync(flags_host, d_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(set_error(FM_ERR_CUDA, "expm (sharded): info readback failed"));
+    if (sh.nloc > 0) FM_STEP(k_getrs(n, sh.nloc, B[den], ldw, 0, pivot ? d_ipiv : nullptr, n, B[num] + boff, ldw, 0, 1));  // own right-hand sides
+    rc = sh.barrier(FM_OK);  // every device is past its addsub (which wrote all of its `num`) and has its block of the solution
+    if (rc != FM_OK) return rc;
+    for (int i = 1; i < sh.world && sh.nloc > 0; ++i) {
+        const int p = (r + i) % sh.world;
+        if (cudaMemcpyPeerAsync(sh.ws[p][num] + boff, sh.device[p], B[num] + boff, sh.device[r], (size_t)ldw * sh.nloc * sizeof(double), st) != cudaSuccess)
+            return fail(set_error(FM_ERR_CUDA, "expm (sharded): peer copy of the solution block failed"));
+    }
+    int cur = num, nxt = spare;
+    for (int q = 0; q < rounds; ++q) {  // repeated squaring (expm.rkt:209-210); gemm() opens with the barrier the copies above need
+        if ((rc = gemm(cur, cur, nxt, 0.0, false, 0.0)) != FM_OK) return rc;
+        const int t = cur; cur = nxt; nxt = t;
+    }
+    rc = sh.barrier(FM_OK);
+    if (rc != FM_OK) return rc;
+    if (result_ws) *result_ws = cur;  // every device holds the full result in this workspace
+    if (out) rc = k_copy2d(out, ldo, B[cur], ldw, n, n);
+    return rc;
+#undef FM_STEP
+}
+
 int k_expm_batched(int n, const double *a, int lda, long long sa, double *out, int ldo, long long so, int batch, int mode, double *s_out) {
     if (n < 0 || batch < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "expm_batched: bad dimensions");
     if (n == 0 || batch == 0) return FM_OK;

@@ -116,6 +116,8 @@ struct Group {
     cudaEvent_t ev_home = nullptr;     // home stream: everything queued before the call
     int ev_home_dev = -1;
     double *da[MG_MAX] = {};           // per call: each device's copy of A
+    cudaEvent_t ev_bar[MG_MAX][2] = {};  // fm_mg_expm: device r has reached group barrier k (slot k & 1)
+    double *ws[MG_MAX][6] = {};          // fm_mg_expm: every device's six workspaces
 };
 Group *g_group = nullptr;
 
@@ -200,6 +202,8 @@ int fm_mg_init(int ndev) {
         MG_CUDA(rc, cudaEventCreateWithFlags(&g->ev_a[r], cudaEventDisableTiming));
         MG_CUDA(rc, cudaEventCreateWithFlags(&g->ev_pull[r], cudaEventDisableTiming));
         MG_CUDA(rc, cudaEventCreateWithFlags(&g->ev_done[r], cudaEventDisableTiming));
+        MG_CUDA(rc, cudaEventCreateWithFlags(&g->ev_bar[r][0], cudaEventDisableTiming));
+        MG_CUDA(rc, cudaEventCreateWithFlags(&g->ev_bar[r][1], cudaEventDisableTiming));
         return rc;
     });
     if (rc != FM_OK) return rc;  // (the workers stay parked; a later fm_mg_init may try again with the same count)
@@ -442,6 +446,120 @@ int fm_mg_expm_batched(int n, const double *a, int lda, long long stride_a, doub
     if (a_on)
         for (int r = 0; r < g.ndev; ++r)
             if (r != home) FM_CUDA(cudaStreamWaitEvent(ctx().stream, g.ev_done[r], 0));
+    return FM_OK;
+}
+
+// One matrix exponential over the whole group ("single large expm": every product column-sharded and all-gathered, the
+// solve's right-hand sides sharded, the LU replicated): see expm.cu k_expm_sharded.  a and out: both host memory, or both on the
+// calling thread's device.  Blocks until the result is in place.  *info = LAPACK info of the Pade denominator's LU (0 in practice).
+int fm_mg_expm(int n, const double *a, int lda, double *out, int ldo, int mode, double *s_out, int32_t *info) {
+    if (!g_group) FM_TRY(fm_mg_init(0));
+    Group &g = *g_group;
+    if (n < 0 || lda < (n > 1 ? n : 1) || ldo < (n > 1 ? n : 1)) return set_error(FM_ERR_ARG, "fm_mg_expm: bad dimensions");
+    if (info) *info = 0;
+    if (n == 0) return FM_OK;
+    int a_dev = -1, o_dev = -1;
+    const bool a_on = is_device_pointer(a, &a_dev), o_on = is_device_pointer(out, &o_dev);
+    if (a_on != o_on) return set_error(FM_ERR_ARG, "fm_mg_expm: input and output must be both host or both device memory");
+    FM_TRY(ensure_init());
+    if (a_on && (a_dev != o_dev || ctx().device != a_dev))
+        return set_error(FM_ERR_ARG, "fm_mg_expm: device operands must live on the calling thread's device (%d)", ctx().device);
+    const int home = rank_of_device(g, ctx().device);
+    if (home < 0) return set_error(FM_ERR_ARG, "fm_mg_expm: the calling thread's device %d is not part of the group", ctx().device);
+    auto one_device = [&]() -> int {
+        if (a_on) {
+            FM_TRY(fm_expm(n, a, lda, out, ldo, mode, s_out, info));
+            return fm_sync();
+        }
+        double *da = static_cast<double *>(fm_alloc_bytes((size_t)n * n * 8));
+        if (!da) return FM_ERR_NOMEM;
+        int rc = fm_upload(da, n, a, lda, n, n);
+        if (rc == FM_OK) rc = fm_expm(n, da, n, out, ldo, mode, s_out, info);  // (host result buffer: downloads behind the last squaring)
+        if (rc == FM_OK) rc = fm_sync();
+        fm_free(da);
+        return rc;
+    };
+    if (g.ndev == 1 || n < 128 * g.ndev) return one_device();  // nothing to shard (a column block is at least one 128-column tile column)
+    if (a_on) {
+        if (!g.ev_home || g.ev_home_dev != a_dev) {
+            if (g.ev_home) cudaEventDestroy(g.ev_home);
+            FM_CUDA(cudaEventCreateWithFlags(&g.ev_home, cudaEventDisableTiming));
+            g.ev_home_dev = a_dev;
+        }
+        FM_CUDA(cudaEventRecord(g.ev_home, ctx().stream));
+    }
+    const int lddx = n + (n & 1);
+    int32_t flags[MG_MAX][2] = {};
+    double s_of[MG_MAX] = {};
+    const int rc = g.workers.run([&](int r) -> int {
+        int rc = FM_OK;
+        cudaStream_t st = ctx().stream;
+        int j0, nloc;
+        column_block(n, g.ndev, r, &j0, &nloc);
+        unsigned nbar = 0;
+        auto barrier = [&](int rc_in) -> int {
+            int rc = rc_in;
+            const int slot = (int)(nbar++ & 1u);
+            MG_CUDA(rc, cudaEventRecord(g.ev_bar[r][slot], st));
+            rc = g.workers.agree(rc);  // every record of this barrier precedes every wait on it; two slots: nobody re-records an event a peer has yet to wait on
+            if (rc != FM_OK) return rc;
+            for (int p = 0; p < g.ndev; ++p)
+                if (p != r) MG_CUDA(rc, cudaStreamWaitEvent(st, g.ev_bar[p][slot], 0));
+            return rc;
+        };
+        // ---- a full copy of A on every device ----
+        const bool is_home = a_on && r == home;
+        g.da[r] = is_home ? nullptr : static_cast<double *>(fm_alloc_bytes((size_t)lddx * n * 8));
+        if (!is_home && !g.da[r]) rc = FM_ERR_NOMEM;
+        if (rc == FM_OK) rc = k_expm_workspace(n, g.ws[r]);
+        if (a_on) MG_CUDA(rc, cudaStreamWaitEvent(st, g.ev_home, 0));
+        // own column slice first (from the host over this device's PCIe link, or from the home device), the rest from the peers
+        if (rc == FM_OK && !is_home && nloc > 0) {
+            if (a_on) rc = pull2d(g.da[r] + (size_t)j0 * lddx, lddx, a + (size_t)j0 * lda, lda, a_dev, n, nloc, st);
+            else rc = copy_h2d(g.da[r] + (size_t)j0 * lddx, lddx, a + (size_t)j0 * lda, lda, n, nloc, st);
+        }
+        rc = barrier(rc);  // every slice is in place and every g.da[] / g.ws[] is known
+        if (rc != FM_OK) { if (g.da[r]) fm_free(g.da[r]); g.da[r] = nullptr; return rc; }
+        if (!is_home) {
+            for (int i = 1; i < g.ndev && rc == FM_OK; ++i) {
+                const int p = (r + i) % g.ndev;
+                int pj0, pn;
+                column_block(n, g.ndev, p, &pj0, &pn);
+                if (pn == 0) continue;
+                if (a_on && p == home) rc = pull2d(g.da[r] + (size_t)pj0 * lddx, lddx, a + (size_t)pj0 * lda, lda, a_dev, n, pn, st);
+                else MG_CUDA(rc, cudaMemcpyPeerAsync(g.da[r] + (size_t)pj0 * lddx, g.dev[r], g.da[p] + (size_t)pj0 * lddx, g.dev[p], (size_t)lddx * pn * 8, st));
+            }
+        }
+        ExpmShard sh;
+        sh.rank = r;
+        sh.world = g.ndev;
+        sh.j0 = j0;
+        sh.nloc = nloc;
+        sh.device = g.dev;
+        sh.ws = g.ws;
+        sh.barrier = barrier;
+        // (k_expm_sharded opens with a barrier after the norm: nobody frees or overwrites its copy of A before every peer has read it)
+        double *dout = nullptr;  // device result: straight into `out` on the home device; host result: every device returns its column block
+        if (a_on) dout = is_home ? out : nullptr;
+        const double *src = is_home ? a : g.da[r];
+        const int lds = is_home ? lda : lddx;
+        int where = -1;
+        if (rc != FM_OK) { barrier(rc); }
+        else rc = k_expm_sharded(n, src, lds, dout, ldo, mode, &s_of[r], flags[r], sh, &where);
+        // host result: every device delivers its own column block over its own PCIe link
+        if (rc == FM_OK && !a_on && nloc > 0) rc = copy_d2h(out + (size_t)j0 * ldo, ldo, g.ws[r][where] + (size_t)j0 * lddx, lddx, n, nloc, st);
+        MG_CUDA(rc, cudaStreamSynchronize(st));
+        if (g.da[r]) fm_free(g.da[r]);
+        g.da[r] = nullptr;
+        return rc;
+    });
+    if (rc != FM_OK) return rc;
+    if (s_out) *s_out = s_of[home];
+    bool redo = false;
+    for (int r = 0; r < g.ndev; ++r) redo = redo || flags[r][0] != 0 || flags[r][1] != 0;
+    // singular or not column-dominant denominator: the one-device pipeline knows what LAPACK / the reference do then (and the input
+    // is untouched: the sharded pass only wrote workspaces and `out`)
+    if (redo) return one_device();
     return FM_OK;
 }
 

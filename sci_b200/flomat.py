@@ -846,6 +846,25 @@ def times_host_mg(a: np.ndarray, b: np.ndarray, c: np.ndarray | None = None, alp
     return c
 
 
+def expm_mg(a, mode: int = EXPM_REFERENCE_ORDER, return_s: bool = False):
+    """`expm` (expm.rkt:203) of ONE matrix over every device of the group: the products sharded by column blocks with the all-gather
+    fused into the GEMM epilogue, the LU replicated, the solves sharded by right-hand sides.  `a`: a Flomat on this device (returns a
+    Flomat) or a column-major float64 host array (returns a host array)."""
+    s = c_double()
+    info = c_int32()
+    if isinstance(a, Flomat):
+        _check_square(a, "expm")
+        out = Flomat.alloc(a.m, a.n)
+        check(_L().fm_mg_expm(a.m, a.a, a.lda, out.a, out.lda, int(mode), byref(s), byref(info)), "fm_mg_expm")
+    else:
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.shape[0] == a.shape[1] and a.flags.f_contiguous):
+            raise ValueError("expm_mg: expected a Flomat or a square column-major float64 array")
+        n = a.shape[0]
+        out = np.empty((n, n), dtype=np.float64, order="F")
+        check(_L().fm_mg_expm(n, a.ctypes.data, max(1, n), out.ctypes.data, max(1, n), int(mode), byref(s), byref(info)), "fm_mg_expm")
+    return (out, s.value) if return_s else out
+
+
 def expm_batched_mg(a_ptr: int, n: int, batch: int, out_ptr: int, mode: int = EXPM_REFERENCE_ORDER, s_out: np.ndarray | None = None):
     """`batch` dense n x n matrices stored back to back at a_ptr (host or this device's memory), one contiguous block per device."""
     sp = s_out.ctypes.data if s_out is not None else None

@@ -95,6 +95,35 @@ def test_mg_expm_batched_vs_oracle(fm, ref, ndev, n, batch):
             assert normwise_rel_err(got[z * n * n:(z + 1) * n * n].reshape(n, n, order="F"), want[z]) <= tol(n), z
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n", [1024, 1100, 2304])
+def test_mg_expm_single_matrix_vs_oracle(fm, ref, ndev, n, mode):
+    """fm_mg_expm (one large expm over the group, every product column-sharded with the fused all-gather, LU replicated, solves
+    sharded by right-hand sides) against the oracle at 1x the gate, device and host operands, both product orders; ragged column
+    blocks at n = 1100.  (One device: the same entry point takes the one-device route.)"""
+    a = rnd(70 + n, n, n, 1.0 / np.sqrt(n))
+    want, s_ref = ref.expm(a), ref.scaling_exponent(a)  # (both product orders are gated against the reference's own order)
+    got, s = fm.expm_mg(fm.matrix(a), mode=mode, return_s=True)
+    assert s == s_ref
+    gate(f"fm_mg_expm device n={n} mode={mode} on {ndev} device(s)", got.to_numpy(), want, n)
+    got_h, s = fm.expm_mg(a, mode=mode, return_s=True)
+    assert s == s_ref
+    gate(f"fm_mg_expm host n={n} mode={mode} on {ndev} device(s)", got_h, want, n)
+    # against the one-device pipeline: the same algorithm, other tile shapes
+    one = fm.expm(fm.matrix(a), mode).to_numpy()
+    gate(f"fm_mg_expm vs fm_expm n={n} mode={mode}", got_h, one, n)
+
+
+def test_mg_expm_is_repeatable_and_leaves_the_input_alone(fm, ndev):
+    n = 1536
+    a = rnd(81, n, n, 1.0 / np.sqrt(n))
+    A = fm.matrix(a)
+    first = fm.expm_mg(A).to_numpy()
+    again = fm.expm_mg(A).to_numpy()
+    assert np.array_equal(first, again)  # fixed tile order, fixed split: bit-identical from call to call
+    assert np.array_equal(A.to_numpy(), a)
+
+
 def test_second_device_context(fm, ref):
     """ADVICE r1: fm_init on another device of the same process gets its own context (allocator, workspaces, kernel attributes);
     going back to the first device keeps working.  Needs 2 devices."""
