@@ -509,7 +509,21 @@ def single_process_mg(G: Gpu, args) -> dict:
     ms = G.best_ms(lambda: fm.expm_batched_mg(src.data_ptr(), ni, items, dst.data_ptr(), mode, s_out))
     w = float(sum(expm_flops_min(ni, sv) for sv in s_out))
     out["expm_batched_device_operands"] = {"items": items, "n": ni, "ms": ms, "tflops_wmin_total": w / ms / 1e9}
-    out["ok"] = bool(ok and ok_h)
+    del src, dst
+    # the metric's expm (n = 8192, ONE matrix) over every device: fm_mg_expm against fm_expm on device 0, same input
+    ne = args.n
+    X = G.dev_randn(ne, ne, 6003, 1.0 / math.sqrt(ne))
+    t_one = G.best_ms(lambda: fm.expm(X, mode), 2)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter(); E, s_e = fm.expm_mg(X, mode=mode, return_s=True); best = min(best, (time.perf_counter() - t0) * 1e3)
+    E1 = fm.expm(X, mode)
+    diff = fm.norm(fm.minus(E, E1), 1) / fm.norm(E1, 1)
+    gate = 64.0 * ne * 2.0 ** -52
+    out["expm_one_matrix"] = {"n": ne, "s": s_e, "ms": best, "one_device_ms": t_one, "speedup": t_one / best,
+                              "tflops_wmin_total": expm_flops_min(ne, s_e) / best / 1e9, "rel_diff_vs_one_device": diff, "gate_64_n_eps": gate,
+                              "what": "fm_mg_expm: products column-sharded with the fused all-gather epilogue, LU replicated, solves sharded by right-hand sides; wall clock of the blocking call"}
+    out["ok"] = bool(ok and ok_h and diff <= gate)
     return out
 
 
