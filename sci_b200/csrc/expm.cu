@@ -421,7 +421,16 @@ int k_expm_sharded(int n, const double *a, int lda, double *out, int ldo, int mo
     const bool pivot = always_pivot || n > 16384;
     if (pivot) FM_STEP(k_getrf(n, n, B[den], ldw, 0, d_ipiv, n, d_info, 1));  // replicated: every device factors its own copy
     else FM_STEP(k_getrf_nopiv(n, B[den], ldw, 0, d_ipiv, n, d_info, d_viol, 1));
-    if (cudaMemcpyAsync(flags_host, d_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(set_error(FM_ERR_CUDA, "expm (sharded): info readback failed"));
+    // info + violation word to this device's pinned words (a copy to pageable memory would hold this thread until the LU has run)
+    InfoBack &ib = g_info_pd();
+    if (ib.cap < 2) {
+        if (ib.h) cudaFreeHost(ib.h);
+        ib.h = nullptr;
+        ib.cap = 0;
+        if (cudaMallocHost(&ib.h, 64 * sizeof(int32_t)) != cudaSuccess) return fail(set_error(FM_ERR_CUDA, "expm (sharded): pinned allocation failed"));
+        ib.cap = 64;
+    }
+    if (cudaMemcpyAsync(ib.h, d_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail(set_error(FM_ERR_CUDA, "expm (sharded): info readback failed"));
     if (sh.nloc > 0) FM_STEP(k_getrs(n, sh.nloc, B[den], ldw, 0, pivot ? d_ipiv : nullptr, n, B[num] + boff, ldw, 0, 1));  // own right-hand sides
     rc = sh.barrier(FM_OK);  // every device is past its addsub (which wrote all of its `num`) and has its block of the solution
     if (rc != FM_OK) return rc;
@@ -439,6 +448,9 @@ int k_expm_sharded(int n, const double *a, int lda, double *out, int ldo, int mo
     if (rc != FM_OK) return rc;
     if (result_ws) *result_ws = cur;  // every device holds the full result in this workspace
     if (out) rc = k_copy2d(out, ldo, B[cur], ldw, n, n);
+    if (rc == FM_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = set_error(FM_ERR_CUDA, "expm (sharded): synchronisation failed");
+    flags_host[0] = ib.h[0];
+    flags_host[1] = ib.h[1];
     return rc;
 #undef FM_STEP
 }

@@ -170,3 +170,42 @@ def test_chunked_factorisation_on_a_device_matrix(fm, ref):
     want_lu, want_piv, _ = ref.lu(a)
     assert np.array_equal(piv.to_numpy(), want_piv)
     gate("fm_getrf_chunked", A.to_numpy(), want_lu, n)
+
+
+def test_host_pipeline_operand_placements(fm, ref):
+    """What the compat symbols accept besides plain host buffers: no right-hand side at all, b already in HBM (solved only after info is
+    known: dgesv must leave it untouched for a singular A), ipiv in HBM, and PINNED host memory (asynchronous copies, no staging)."""
+    import torch
+
+    lib = fm.load()
+    n, nrhs = 2304, 4
+    a, b = rnd(7700, n, n), rnd(7701, n, nrhs)
+    want_x = ref.mldivide(a, b)
+    want_lu, want_piv, _ = ref.lu(a)
+    info = c_int(-99)
+    # nrhs = 0
+    A = a.copy(order="F"); ipiv = np.zeros(n, dtype=np.int32)
+    lib.dgesv_(byref(c_int(n)), byref(c_int(0)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, None, byref(c_int(n)), byref(info))
+    assert info.value == 0 and np.array_equal(ipiv, want_piv)
+    gate("L\\U, nrhs = 0", A, want_lu, n)
+    # b on the device
+    A = a.copy(order="F"); B = fm.matrix(b)
+    lib.dgesv_(byref(c_int(n)), byref(c_int(nrhs)), A.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, B.a, byref(c_int(B.lda)), byref(info))
+    assert info.value == 0
+    gate_solve("dgesv_(host A, device b)", a, b, B.to_numpy(), want_x, n)
+    sing = a.copy(order="F"); sing[:, 1000] = 0.0
+    B = fm.matrix(b)
+    lib.dgesv_(byref(c_int(n)), byref(c_int(nrhs)), sing.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, B.a, byref(c_int(B.lda)), byref(info))
+    assert info.value == 1001 and np.array_equal(B.to_numpy(), b)
+    # ipiv on the device
+    A = a.copy(order="F"); piv = fm.Pivots(n)
+    lib.dgetrf_(byref(c_int(n)), byref(c_int(n)), A.ctypes.data, byref(c_int(n)), piv.ptr, byref(info))
+    assert info.value == 0 and np.array_equal(piv.to_numpy(), want_piv)
+    # pinned host memory
+    pa = torch.empty((n, n), dtype=torch.float64, pin_memory=True).numpy().T  # F-contiguous view
+    pb = torch.empty((nrhs, n), dtype=torch.float64, pin_memory=True).numpy().T
+    pa[...] = a; pb[...] = b
+    lib.dgesv_(byref(c_int(n)), byref(c_int(nrhs)), pa.ctypes.data, byref(c_int(n)), ipiv.ctypes.data, pb.ctypes.data, byref(c_int(n)), byref(info))
+    assert info.value == 0 and np.array_equal(ipiv, want_piv)
+    gate_solve("dgesv_(pinned host operands)", a, b, pb, want_x, n)
+    gate("L\\U(pinned host operands)", pa, want_lu, n)
