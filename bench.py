@@ -280,6 +280,13 @@ class Gpu:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        # one process per GPU: keep this rank's host threads and pinned buffers on the GPU's NUMA node (before anything allocates)
+        self.affinity = None
+        self.cpus_before = os.sched_getaffinity(0)
+        if self.world > 1 and not os.environ.get("FLOMAT_BENCH_NO_AFFINITY"):
+            from sci_b200.multigpu import bind_host_near_device
+
+            self.affinity = bind_host_near_device(self.local)
         torch.cuda.set_device(self.local)
         fm.init(self.local)
         self.lib = fm.load()
@@ -472,6 +479,7 @@ def single_process_mg(G: Gpu, args) -> dict:
     import numpy as np
 
     fm, lib, torch, n = G.fm, G.lib, G.torch, args.colshard_n
+    os.sched_setaffinity(0, G.cpus_before)  # this process now drives every device: its worker threads must not inherit rank 0's NUMA binding
     ndev = fm.mg_init(G.world)
     out = {"devices": ndev, "n": n}
     A, B = G.dev_randn(n, n, 4001), G.dev_randn(n, n, 4002)
@@ -580,7 +588,7 @@ def run_gpu(args):
                          "peak_source": f"profiles/fp64_peak.json ({peak['how']}; {peak['sm_mhz']} MHz)"},
             "e2e": {"value": j["flops_step"] / (j["e2e_ms"] * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": j["e2e_bytes"][0],
                     "d2h_bytes_per_step": j["e2e_bytes"][1], "ms_per_step": j["e2e_ms"], "steps": j["e2e_steps"], "api": j["e2e_api"]},
-            "gpu_launches": j["launches"], "clocks": j["clocks"]})
+            "gpu_launches": j["launches"], "clocks": j["clocks"], "host_affinity_rank0": G.affinity})
         if not args.no_replicas:  # the round-1 weak-scaling number: one independent n = 8192 step per GPU, no collective
             r = metric_step_n8192(G, args, max(2, min(args.steps, 3)), 3, False, None, seed_offset=rank)
             r.pop("host")

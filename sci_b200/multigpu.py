@@ -342,3 +342,40 @@ class ShardedJob:
 
     def close(self):
         self.cs.close()
+
+
+def bind_host_near_device(device: int) -> dict:
+    """Pin the calling thread (and every thread it creates later: the library's copy pool, torch's helpers) to the cores of the NUMA
+    node the GPU hangs off, so that pinned host buffers are first-touched there and the staging copies do not cross the socket link.
+    One process per GPU only (a single process that drives all devices must stay unbound).  Best effort: returns what it found and
+    did; a box that does not expose the topology (numa_node = -1, as most virtual machines) is left alone."""
+    import os
+
+    info = {"device": device, "bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else device
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}"
+        node = int(open(path + "/numa_node").read().strip())
+        cpulist = open(path + "/local_cpulist").read().strip()
+        info.update({"pci": bus, "numa_node": node, "local_cpulist": cpulist})
+        if node < 0 or not cpulist:
+            return info
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+            info["cpus"] = len(cpus)
+    except Exception as e:  # noqa: BLE001  (no NVML, no sysfs, no permission: stay unbound)
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
