@@ -442,6 +442,43 @@ def test_expm_falls_back_to_pivoting_when_the_check_fails(fm, ref):
     assert normwise_rel_err(E, ref.expm(a)) <= tol(300)
 
 
+@pytest.mark.parametrize("n", [2, 7, 64, 130, 512, 1000, 1024, 1025])
+def test_expm_small_matrices_minimal_work_mode_vs_oracle(fm, ref, n):
+    """EXPM_MIN_PRODUCTS on ONE matrix of n <= 1024 forms den^-1 num by the factored Neumann product (I+E)(I+E^2)...(I+E^16), E = I - den,
+    ||E||_1 <= 0.282 checked on the device (expm.cu) instead of an LU -- nine products, no latency chain.  Against the oracle (the
+    reference's dgesv path) at 1x the gate; n = 1025 is the first size back on the LU."""
+    a = rnd(900 + n, n, n, 1.0 / math.sqrt(n))
+    E, s = fm.expm(up(fm, a), fm.EXPM_MIN_PRODUCTS, return_s=True)
+    assert s == ref.scaling_exponent(a)
+    gate(f"expm min-products n={n}", E.to_numpy(), ref.expm(a), n)
+    a = rnd(950 + n, n, n, 3.0)  # a larger norm: more squarings amplify whatever the solve left
+    gate(f"expm min-products n={n}, norm ~ {3 * math.sqrt(n):.0f}", fm.expm(up(fm, a), fm.EXPM_MIN_PRODUCTS).to_numpy(), ref.expm(a), n)
+
+
+def test_expm_neumann_solve_against_the_lu_solve():
+    """The same call with the Neumann solve switched off (LU), and with its dominance bound lowered so that the device-side check
+    fails and the pipeline repeats itself with the pivoting LU (fresh processes: the switches are read once)."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, math, numpy as np
+sys.path.insert(0, {root!r})
+import sci_b200 as fm
+fm.init(0)
+a = np.asfortranarray(np.random.default_rng(4242).standard_normal((512, 512)) / math.sqrt(512))
+np.save(sys.argv[1], fm.expm(fm.matrix(a), fm.EXPM_MIN_PRODUCTS).to_numpy())
+"""
+    outs = {}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, env in (("neumann", {}), ("lu", {"FLOMAT_EXPM_NEUMANN_MAX_N": "0"}), ("fallback", {"FLOMAT_EXPM_NEUMANN_BOUND": "0.001"}),
+                         ("pivot", {"FLOMAT_EXPM_PIVOT": "1"})):
+            f = os.path.join(d, tag + ".npy")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env}, timeout=600)
+            outs[tag] = np.load(f)
+    gate("expm: Neumann solve vs LU solve", outs["neumann"], outs["lu"], 512)
+    assert np.array_equal(outs["fallback"], outs["pivot"])  # the repeated pass IS the pivoting pipeline
+
+
 # ---------------------------------------------------------------- expm
 @pytest.mark.parametrize("mode", [0, 1])
 def test_expm_closed_forms_and_quirks(fm, mode):
