@@ -73,6 +73,8 @@ struct EpiParams {
     int round;
     unsigned zero;  // always 0; opaque to the compiler (see the stage-release token in the consumer loop)
     int pdl_wait;   // launched as a programmatic dependent of the previous kernel: wait for it before exiting
+    int pdl_start;  // split-K chains of small products: launched as a programmatic dependent, lets ITS dependent (the reduction) become
+                    // resident at once and waits for the previous kernel only after its own prologue (launch, barrier init, descriptor fetch)
     int ksplit;     // > 1: the k range is cut into ksplit slices, slice s of tile t writes its raw partial product to C + s * kstride
     long long kstride;
     int *tile_counter;  // non-null: tiles are handed out dynamically (atomic counter) instead of round-robin; see the producer loop
@@ -152,6 +154,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (ep.pdl_start) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous kernels wrote is visible from here on
+    }
     const int KT = (K + BK - 1) / BK;
 
     if (warp >= NW) {
@@ -657,6 +663,9 @@ int make_map(CUtensorMap *map, const double *base, long long rows, long long col
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(int m, int n, int ksplit, const double *__restrict__ w, long long ldw, long long wz,
                                                              long long kstride, double *c, long long ldc, long long sc, double alpha, double beta,
                                                              double diag, int has_diag, int diag_col0) {
+    // launched as a programmatic dependent of the product that fills w: resident early, starts when the product has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int z = blockIdx.z;
     for (int j = blockIdx.y; j < n; j += gridDim.y)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
@@ -709,7 +718,7 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = ep.pdl_wait ? 1 : 0;
+    cfg.numAttrs = (ep.pdl_wait || ep.pdl_start) ? 1 : 0;
     FM_CUDA(cudaLaunchKernelEx(&cfg, dgemm_tma_kernel<Cfg, COPIER>, tmA, tmB, c, (long long)ldc, sc, m, n, k, tiles_m, tiles_n, (int)total, epl, vec_all));
     count_launch();
     return FM_OK;
@@ -721,6 +730,7 @@ bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
 bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
 // shortest k slice of a split-K product.  64 against 128 (round 1): 256^3 19.1 -> 14.8 us, 384^3 19.3 -> 15.1, 512^3 20.2 -> 19.6 (tools/small_gemm_time.py)
 int g_splitk_min_k = getenv("FLOMAT_GEMM_SPLITK_MIN_K") && atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) >= 16 ? atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) : 64;
+bool g_pdl_chain = getenv("FLOMAT_GEMM_NO_PDL_CHAIN") == nullptr;
 bool g_copier_enabled = getenv("FLOMAT_GEMM_NO_COPIER") == nullptr;  // off: the consumer warps store to the peers themselves (round-1 epilogue)
 int g_copier_min_peers = getenv("FLOMAT_GEMM_COPIER_MIN_PEERS") ? atoi(getenv("FLOMAT_GEMM_COPIER_MIN_PEERS")) : 3;
 int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_STAGGER_NS")) : 6000;  // measured best for k = 128..256
@@ -750,6 +760,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.round = epi.round;
     ep.zero = 0u;
     ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
+    ep.pdl_start = 0;
     ep.tile_counter = nullptr;
     ep.counter_to_clear = nullptr;
     ep.ksplit = 1;
@@ -779,10 +790,23 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
                 EpiParams e2 = ep;
                 e2.alpha = 1.0; e2.beta = 0.0; e2.has_diag = 0; e2.diag = 0.0;
                 e2.ksplit = ksplit; e2.kstride = kstride;
+                // product -> reduction -> next product ... are chained as programmatic dependents (FLOMAT_GEMM_NO_PDL_CHAIN: plain launches):
+                // each kernel's launch and prologue overlap the tail of the one before, and each waits for it before touching memory
+                e2.pdl_start = g_pdl_chain ? 1 : 0;
                 FM_TRY((launch_tma<CfgHalf>(m, n, k, a, lda, sa, b, ldb, sb, w, (int)ldw, wz, batch, e2, epi.max_sms)));
                 dim3 grid(ceil_div(m, 256), n < 1024 ? n : 1024, batch);
-                splitk_reduce_kernel<<<grid, 256, 0, ctx().stream>>>(m, n, ksplit, w, ldw, wz, kstride, c, ldc, sc, ep.alpha, ep.beta, ep.diag, ep.has_diag, ep.diag_col0);
-                FM_LAUNCH_CHECK();
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid;
+                cfg.blockDim = dim3(256, 1, 1);
+                cfg.stream = ctx().stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = g_pdl_chain ? 1 : 0;
+                FM_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel, m, n, ksplit, (const double *)w, ldw, wz, kstride, c, (long long)ldc, sc, ep.alpha,
+                                           ep.beta, ep.diag, ep.has_diag, ep.diag_col0));
+                count_launch();
                 return FM_OK;
             }
         }
