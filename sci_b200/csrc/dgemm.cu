@@ -730,6 +730,8 @@ bool g_stagger_all = getenv("FLOMAT_GEMM_STAGGER_ALL") != nullptr;
 bool g_dynamic_enabled = getenv("FLOMAT_GEMM_NO_DYNAMIC") == nullptr;
 // shortest k slice of a split-K product.  64 against 128 (round 1): 256^3 19.1 -> 14.8 us, 384^3 19.3 -> 15.1, 512^3 20.2 -> 19.6 (tools/small_gemm_time.py)
 int g_splitk_min_k = getenv("FLOMAT_GEMM_SPLITK_MIN_K") && atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) >= 16 ? atoi(getenv("FLOMAT_GEMM_SPLITK_MIN_K")) : 64;
+bool g_tail_rule = getenv("FLOMAT_GEMM_NO_TAIL_RULE") == nullptr;
+bool g_force_half = getenv("FLOMAT_GEMM_FORCE_HALF") != nullptr;  // developer switch: 64x128 tiles, two CTAs per SM, for every shape
 bool g_pdl_chain = getenv("FLOMAT_GEMM_NO_PDL_CHAIN") == nullptr;
 bool g_copier_enabled = getenv("FLOMAT_GEMM_NO_COPIER") == nullptr;  // off: the consumer warps store to the peers themselves (round-1 epilogue)
 int g_copier_min_peers = getenv("FLOMAT_GEMM_COPIER_MIN_PEERS") ? atoi(getenv("FLOMAT_GEMM_COPIER_MIN_PEERS")) : 3;
@@ -775,7 +777,11 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
                         (batch == 1 || (sa % 2 == 0 && sb % 2 == 0)) && encode_fn() != nullptr;
     if (tma_ok) {
         const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
-        const bool half = (big_tiles < 2LL * ctx().sm_count || k <= 256) && g_half_enabled;
+        // a short last wave (128x128 tiles, one CTA per SM): two small CTAs per SM finish it in about half the time, because the few CTAs
+        // left over run one to an SM.  Measured (tools/gemm_wave_shapes.py): 2.16 waves 25.5 -> 29.8 TFLOP/s; no difference from 0.46 of a wave on
+        const long long full_waves = big_tiles / ctx().sm_count, rest_tiles = big_tiles % ctx().sm_count;
+        const bool short_tail = g_tail_rule && full_waves >= 2 && full_waves <= 7 && rest_tiles > 0 && 10 * rest_tiles <= 3 * ctx().sm_count;
+        const bool half = ((big_tiles < 2LL * ctx().sm_count || k <= 256 || short_tail) && g_half_enabled) || g_force_half;
         // Few tiles and a long inner dimension (n <= ~1100): one 64x128 tile per CTA leaves most SMs idle while each warp walks
         // k/16 steps alone.  Cut k into slices (one CTA each, raw partial products to a workspace) and reduce in a second pass.
         const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
