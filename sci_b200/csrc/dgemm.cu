@@ -81,6 +81,8 @@ struct EpiParams {
     int *counter_to_clear;  // a counter slot no kernel in flight uses: zeroed for a later launch
     int stagger_ns;  // two CTAs per SM: the second wave of CTAs starts this much later, so that one CTA's epilogue overlaps the other's main loop
     int copier;      // npeers > 0: the three spare warps of the producer warpgroup forward every finished tile to the peers (see below)
+    int *spread;     // two CTAs per SM, static schedule, more tiles than CTAs: zeroed counters {low, high, per-SM arrivals[]}.  The CTAs renumber
+                     // themselves so that the ids that receive the tiles of the last, partial round (the lowest) sit on distinct SMs
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int &z) {
@@ -148,7 +150,19 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr bool copier = COPIER;  // a separate instantiation: the plain product keeps its register allocation (168, no spills)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int s_cta;  // this CTA's position in the static tile schedule
     if (threadIdx.x == 0) {
+        int id = (int)blockIdx.x;
+        if (Cfg::CTAS_PER_SM == 2 && ep.spread != nullptr) {
+            // first CTA to arrive on its SM: next id from the low end; second: next id from the high end.  Dense whatever the placement,
+            // and the low ids -- which walk one tile more when the tile count is not a multiple of the grid -- are alone on their SMs
+            // in that last round, where a CTA without a neighbour runs ~1.8x faster.
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int arrival = atomicAdd(ep.spread + 2 + smid, 1);
+            id = arrival == 0 ? atomicAdd(ep.spread, 1) : (int)gridDim.x - 1 - atomicAdd(ep.spread + 1, 1);
+        }
+        s_cta = id;
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NW); }
         for (int s = 0; s < 2; ++s) { mbar_init(copy_full(s), NW); mbar_init(copy_empty(s), 3); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,7 +187,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // slot written before the first k-step of the tile is armed; a negative id ends the consumers.  CTAs that only become
             // resident when the panel exits simply join in.
             if (dynamic && blockIdx.x == 0) *ep.counter_to_clear = 0;
-            int tile = dynamic ? atomicAdd(ep.tile_counter, 1) : (int)blockIdx.x;
+            int tile = dynamic ? atomicAdd(ep.tile_counter, 1) : s_cta;
             for (;;) {
                 if (tile >= total_tiles) {
                     if (dynamic) {
@@ -297,7 +311,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x;; tile += gridDim.x) {
+    for (int tile = s_cta;; tile += gridDim.x) {
         if (dynamic) {  // the id of the tile whose first k-step is (or will be) in this stage
             mbar_wait(full_bar(stage), phase);
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(tile_slot + 4u * stage) : "memory");
@@ -685,6 +699,8 @@ using CfgBig = GemmCfg<128, 128, 16, 2, 4, 6>;
 // -- the case of the rank-128/256 updates inside LU and the triangular solves.
 using CfgHalf = GemmCfg<64, 128, 16, 1, 4, 4, 2>;
 
+bool g_spread = getenv("FLOMAT_GEMM_NO_SPREAD") == nullptr;  // developer switch: no renumbering of the CTAs for a partial last round
+
 template <class Cfg, bool COPIER = false>
 int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb, double *c, int ldc,
                long long sc, int batch, const EpiParams &ep, int max_sms) {
@@ -709,6 +725,18 @@ int launch_tma(int m, int n, int k, const double *a, int lda, long long sa, cons
         if (reinterpret_cast<uintptr_t>(ep.peer[r]) & 15u) vec_all = 0;
     EpiParams epl = ep;
     if (total < 4LL * grid) epl.stagger_ns = 0;  // the head start only pays when every CTA walks several tiles
+    epl.spread = nullptr;
+    if (Cfg::CTAS_PER_SM == 2 && g_spread && !ep.tile_counter && !ep.pdl_wait && !ep.pdl_start && total > grid && total % grid != 0 &&
+        2 * (total % grid) <= grid) {
+        // a partial last round of at most one tile per SM: see the renumbering at the top of the kernel.  (Not for launches that
+        // must follow their predecessor directly as programmatic dependents: the memset would come between the two.)
+        static PerDevice<int *> buf_pd;
+        int *&buf = buf_pd();
+        constexpr int WORDS = 2 + 1024;  // %smid stays far below 1024
+        if (!buf) FM_CUDA(cudaMalloc(&buf, WORDS * sizeof(int)));
+        FM_CUDA(cudaMemsetAsync(buf, 0, WORDS * sizeof(int), ctx().stream));
+        epl.spread = buf;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
@@ -763,6 +791,7 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     ep.zero = 0u;
     ep.pdl_wait = epi.pdl_dependent ? 1 : 0;
     ep.pdl_start = 0;
+    ep.spread = nullptr;
     ep.tile_counter = nullptr;
     ep.counter_to_clear = nullptr;
     ep.ksplit = 1;
@@ -777,10 +806,17 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
                         (batch == 1 || (sa % 2 == 0 && sb % 2 == 0)) && encode_fn() != nullptr;
     if (tma_ok) {
         const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
-        // a short last wave (128x128 tiles, one CTA per SM): two small CTAs per SM finish it in about half the time, because the few CTAs
-        // left over run one to an SM.  Measured (tools/gemm_wave_shapes.py): 2.16 waves 25.5 -> 29.8 TFLOP/s; no difference from 0.46 of a wave on
-        const long long full_waves = big_tiles / ctx().sm_count, rest_tiles = big_tiles % ctx().sm_count;
-        const bool short_tail = g_tail_rule && full_waves >= 2 && full_waves <= 7 && rest_tiles > 0 && 10 * rest_tiles <= 3 * ctx().sm_count;
+        // Wave quantisation decides between the two configurations for everything larger (round 2, tools/gemm_wave_shapes.py).  In units of
+        // one 128x128 tile on one SM: 128x128 tiles cost ceil(tiles / SMs); 64x128 tiles run two to an SM, a full round of 2 x SMs of
+        // them costs 1.01, and a last round of at most ONE tile per SM costs 0.56 -- its CTAs have no neighbour (the kernel renumbers
+        // the CTAs so that this holds, see `spread`) and run ~1.8x faster.  3.46 waves: 4 against 3.59 (30.8 -> 34.2 TFLOP/s measured),
+        // 2.16: 3 against 2.58 (25.5 -> 29.8), 4.11: 5 against 4.60; 2.7 / 3.89 / 6.92 / 27.7 waves stay with 128x128 tiles.
+        const long long sms_ = ctx().sm_count;
+        const long long half_count = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
+        const long long h_full = half_count / (2 * sms_), h_rest = half_count % (2 * sms_);
+        const double t_big = (double)((big_tiles + sms_ - 1) / sms_);
+        const double t_half = 1.01 * (double)h_full + (h_rest == 0 ? 0.0 : (h_rest <= sms_ && g_spread ? 0.56 : 1.01));
+        const bool short_tail = g_tail_rule && t_half < t_big;
         const bool half = ((big_tiles < 2LL * ctx().sm_count || k <= 256 || short_tail) && g_half_enabled) || g_force_half;
         // Few tiles and a long inner dimension (n <= ~1100): one 64x128 tile per CTA leaves most SMs idle while each warp walks
         // k/16 steps alone.  Cut k into slices (one CTA each, raw partial products to a workspace) and reduce in a second pass.

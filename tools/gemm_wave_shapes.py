@@ -12,7 +12,7 @@ def best(fn, reps=5):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); b = min(b, e0.elapsed_time(e1))
     return b
 out = {"force_half": os.environ.get("FLOMAT_GEMM_FORCE_HALF") is not None, "tail_rule": os.environ.get("FLOMAT_GEMM_NO_TAIL_RULE") is None}
-for m, n, k in ((8192, 1024, 8192), (8192, 2048, 8192), (2560, 2560, 2560), (3072, 3072, 3072), (4096, 4096, 4096), (8192, 8192, 8192), (5120, 1024, 5120), (8192, 640, 8192), (2304, 2304, 2304), (4096, 2432, 4096), (4096, 3072, 4096), (6144, 1536, 6144), (4608, 4608, 4608)):
+for m, n, k in ((8192, 1024, 8192), (8192, 2048, 8192), (2560, 2560, 2560), (3072, 3072, 3072), (4096, 4096, 4096), (8192, 8192, 8192), (5120, 1024, 5120), (8192, 640, 8192), (2304, 2304, 2304), (4096, 2432, 4096), (4096, 3072, 4096), (6144, 1536, 6144), (4608, 4608, 4608), (10624, 3072, 4096), (8192, 1152, 8192), (1920, 1920, 1920)):
     a = torch.randn(m * k, dtype=torch.float64, device=dev); b = torch.randn(k * n, dtype=torch.float64, device=dev); c = torch.empty(m * n, dtype=torch.float64, device=dev)
     ms = best(lambda: lib.fm_dgemm(111, 111, m, n, k, 1.0, a.data_ptr(), m, b.data_ptr(), k, 0.0, c.data_ptr(), m))
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
