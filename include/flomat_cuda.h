@@ -158,6 +158,11 @@ int fm_dgemm_host(int m, int n, int k, double alpha, const double *a, int lda, c
 /* the column blocks fm_dgemm_host cuts an m x n result into on a device with `sms` SMs (<= 0: 148): block width (a multiple of 128)
  * and block count, the last block taking the remainder.  Host arithmetic only; callable without a GPU. */
 int fm_dgemm_host_plan(int m, int n, int sms, int *width, int *nblocks);
+/* which configuration of the GEMM kernel an aligned NN product takes on `sms` SMs: *tile_rows = 128 (128x128 tiles, one CTA per SM) or 64
+ * (64x128 tiles, two CTAs per SM), *ksplit = k slices (1 = none); and the column chunks of the host-operand LU pipeline of dgesv_ /
+ * dgetrf_ (bounds[0] = 0 < ... < bounds[*nchunks] = n).  Pure host arithmetic: callable without a GPU. */
+int fm_dgemm_tile_plan(int m, int n, int k, int batch, int sms, int *tile_rows, int *ksplit);
+int fm_lu_host_plan(int n, int *bounds, int max_bounds, int *nchunks);
 /* as fm_dgemm (NN only) and then adds diag to C[i,i]: the `(plus (.* c I) (times A P))` step of mpoly, expm.rkt:176 */
 int fm_dgemm_diag(int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb, double beta,
                   double *c, int ldc, double diag);

@@ -85,6 +85,8 @@ SIGNATURES = {
     "fm_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int]),
     "fm_dgemm_host": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_int]),
     "fm_dgemm_host_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "fm_dgemm_tile_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "fm_lu_host_plan": (c_int, [c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     "fm_dgemm_diag": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, _DP, c_int, c_double, _DP, c_int, c_double]),
     "fm_dgemm_batched": (c_int, [c_int, c_int, c_int, c_double, _DP, c_int, c_longlong, _DP, c_int, c_longlong, c_double, _DP, c_int,
                                  c_longlong, c_double, c_int]),

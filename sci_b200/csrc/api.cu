@@ -457,6 +457,24 @@ int fm_dgemm_host_plan(int m, int n, int sms, int *width, int *nblocks) {
     return FM_OK;
 }
 
+// Which configuration of the DMMA GEMM an untransposed, aligned m x n x k product takes on `sms` SMs (dgemm.cu: gemm_tile_plan):
+// *tile_rows = 128 or 64 (x 128 columns; 64: two CTAs per SM), *ksplit = number of k slices (1 = no split).  Pure host arithmetic.
+int fm_dgemm_tile_plan(int m, int n, int k, int batch, int sms, int *tile_rows, int *ksplit) {
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || !tile_rows || !ksplit) return set_error(FM_ERR_ARG, "fm_dgemm_tile_plan: bad arguments");
+    *tile_rows = gemm_tile_plan(m, n, k, batch, sms, true, ksplit) ? 64 : 128;
+    return FM_OK;
+}
+// The column chunks in which dgesv_ / dgetrf_ move a HOST matrix of order n through the LU pipeline (getrf_host_pipeline): bounds[0] = 0
+// < bounds[1] < ... < bounds[*nchunks] = n, every bound but the last a multiple of 128.  Pure host arithmetic.
+int fm_lu_host_plan(int n, int *bounds, int max_bounds, int *nchunks) {
+    if (n <= 0 || !bounds || !nchunks || max_bounds < 2) return set_error(FM_ERR_ARG, "fm_lu_host_plan: bad arguments");
+    const std::vector<int> b = lu_host_bounds(n);
+    if ((int)b.size() > max_bounds) return set_error(FM_ERR_ARG, "fm_lu_host_plan: %d bounds do not fit %d", (int)b.size(), max_bounds);
+    for (size_t i = 0; i < b.size(); ++i) bounds[i] = b[i];
+    *nchunks = (int)b.size() - 1;
+    return FM_OK;
+}
+
 // C := alpha*A*B + beta*C with all three operands in HOST memory (what the unmodified reference passes to cblas_dgemm,
 // flomat.rkt:888): instead of upload / compute / download one after the other, B and C travel in column blocks -- A goes up once,
 // then block j of B is uploaded while the product of block j-1 runs and block j-2 of C comes down (uploads on the transfer stream,
@@ -589,14 +607,18 @@ std::vector<int> lu_chunk_bounds(int n, int first, int cap) {
     }
     return b;
 }
-int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, double *b, int ldb, int32_t *hinfo) {
-    FM_TRY(xfer_init());
-    const int ldd = n + (n & 1);
+// the chunks getrf_host_pipeline uses for a matrix of order n: 1024, 1024, then doubling up to n/4 columns
+std::vector<int> lu_host_bounds(int n) {
     int first = 1024, cap = (n / 4 / 128) * 128;  // two chunks (a window) arrive before the first panel can start; 512 .. 2048 measured alike
     if (cap < first) cap = first;
     if (const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_FIRST")) { const int v = atoi(e); if (v >= 128 && v % 128 == 0) { first = v; if (cap < first) cap = first; } }
     if (const char *e = getenv("FLOMAT_CUDA_LU_PIPELINE_CHUNK")) { const int v = atoi(e); if (v >= 128 && v % 128 == 0) first = cap = v; }  // developer switch: uniform chunks
-    const std::vector<int> bounds = lu_chunk_bounds(n, first, cap);
+    return lu_chunk_bounds(n, first, cap);
+}
+int getrf_host_pipeline(int n, double *a, int lda, int32_t *ipiv, int nrhs, double *b, int ldb, int32_t *hinfo) {
+    FM_TRY(xfer_init());
+    const int ldd = n + (n & 1);
+    const std::vector<int> bounds = lu_host_bounds(n);
     const int nchunks = (int)bounds.size() - 1;
     auto chunk_of = [&](int c0) { int j = 0; while (bounds[j] != c0) ++j; return j; };
     int rc = FM_OK;

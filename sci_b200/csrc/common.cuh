@@ -126,12 +126,14 @@ struct GemmEpilogue {
 };
 int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,
             double *c, int ldc, long long sc, int batch, const GemmEpilogue &ep);
+int gemm_tile_plan(int m, int n, int k, int batch, int sms, bool splitk_allowed, int *ksplit_out);
 // lu.cu
 int k_getrf(int m, int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int batch);
 int k_getrf_streamed(int n, double *a, int lda, int32_t *ipiv, int32_t *info, const std::vector<int> &bounds,
                      const std::function<int(int, int)> &arrive, const std::function<int(int, int, int)> &upper_done,
                      const std::function<int(int, int, int)> &done);
 std::vector<int> lu_chunk_bounds(int n, int first, int cap);
+std::vector<int> lu_host_bounds(int n);
 int k_getrf_nopiv(int n, double *a, int lda, long long sa, int32_t *ipiv, long long sp, int32_t *info, int32_t *viol, int batch);
 int k_getrs(int n, int nrhs, const double *lu, int lda, long long sa, const int32_t *ipiv, long long sp, double *b, int ldb, long long sb, int batch);
 int k_det_device(int n, const double *lu, int lda, const int32_t *ipiv, double *d_out);

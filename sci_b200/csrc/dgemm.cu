@@ -767,6 +767,38 @@ int g_stagger_ns = getenv("FLOMAT_GEMM_STAGGER_NS") ? atoi(getenv("FLOMAT_GEMM_S
 
 }  // namespace
 
+// Which kernel configuration a TMA-path product takes: 0 = 128x128 tiles (one CTA per SM), 1 = 64x128 tiles (two CTAs per SM);
+// *ksplit > 1: 64x128 tiles with the k range cut into that many slices + the reduction kernel.  Pure host arithmetic (exported as
+// fm_dgemm_tile_plan for the CPU tests).
+//   * fewer than 2 x SMs tiles of 128x128, or k <= 256 (rank-k updates, triangular sweeps): 64x128 -- twice the tiles, two independent
+//     CTAs per SM (one's epilogue under the other's main loop);
+//   * otherwise wave quantisation decides (round 2, tools/gemm_wave_shapes.py).  In units of one 128x128 tile on one SM: 128x128 tiles
+//     cost ceil(tiles / SMs); 64x128 tiles run two to an SM, a full round of 2 x SMs of them costs 1.01, and a last round of at most
+//     ONE tile per SM costs 0.56 -- its CTAs have no neighbour (the kernel renumbers the CTAs so that this holds, see `spread`) and
+//     run ~1.8x faster.  3.46 waves: 4 against 3.59 (30.8 -> 34.2 TFLOP/s measured), 2.16: 3 against 2.58 (25.5 -> 29.6), 4.11: 5
+//     against 4.60; 2.7 / 3.89 / 6.92 / 27.7 waves stay with 128x128 tiles;
+//   * at most SMs tiles of 64x128 and k >= 256 (n <= ~1100): one tile per CTA leaves most SMs idle while each warp walks k/16 steps
+//     alone -- cut k into slices of at least 64 (one CTA each, raw partial products to a workspace) and reduce in a second pass.
+int gemm_tile_plan(int m, int n, int k, int batch, int sms, bool splitk_allowed, int *ksplit_out) {
+    const long long sms_ = sms > 0 ? sms : 148;
+    const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
+    const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
+    const long long h_full = half_tiles / (2 * sms_), h_rest = half_tiles % (2 * sms_);
+    const double t_big = (double)((big_tiles + sms_ - 1) / sms_);
+    const double t_half = 1.01 * (double)h_full + (h_rest == 0 ? 0.0 : (h_rest <= sms_ && g_spread ? 0.56 : 1.01));
+    const bool short_tail = g_tail_rule && t_half < t_big;
+    const bool half = ((big_tiles < 2 * sms_ || k <= 256 || short_tail) && g_half_enabled) || g_force_half;
+    int ksplit = 1;
+    if (half && g_splitk_enabled && splitk_allowed && half_tiles <= sms_ && k >= 256) {
+        ksplit = (int)((2 * sms_) / half_tiles);
+        if (ksplit > k / g_splitk_min_k) ksplit = k / g_splitk_min_k;
+        if (ksplit > 16) ksplit = 16;
+        if (ksplit < 2) ksplit = 1;
+    }
+    if (ksplit_out) *ksplit_out = ksplit;
+    return half ? 1 : 0;
+}
+
 int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int lda, long long sa, const double *b, int ldb, long long sb,
             double *c, int ldc, long long sc, int batch, const GemmEpilogue &epi) {
     const bool ta = (transA == FM_TRANS), tb = (transB == FM_TRANS);
@@ -805,26 +837,9 @@ int k_dgemm(int transA, int transB, int m, int n, int k, const double *a, int ld
     const bool tma_ok = !ta && !tb && k > 0 && al16(a) && al16(b) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                         (batch == 1 || (sa % 2 == 0 && sb % 2 == 0)) && encode_fn() != nullptr;
     if (tma_ok) {
-        const long long big_tiles = (long long)ceil_div(m, 128) * ceil_div(n, 128) * batch;
-        // Wave quantisation decides between the two configurations for everything larger (round 2, tools/gemm_wave_shapes.py).  In units of
-        // one 128x128 tile on one SM: 128x128 tiles cost ceil(tiles / SMs); 64x128 tiles run two to an SM, a full round of 2 x SMs of
-        // them costs 1.01, and a last round of at most ONE tile per SM costs 0.56 -- its CTAs have no neighbour (the kernel renumbers
-        // the CTAs so that this holds, see `spread`) and run ~1.8x faster.  3.46 waves: 4 against 3.59 (30.8 -> 34.2 TFLOP/s measured),
-        // 2.16: 3 against 2.58 (25.5 -> 29.8), 4.11: 5 against 4.60; 2.7 / 3.89 / 6.92 / 27.7 waves stay with 128x128 tiles.
-        const long long sms_ = ctx().sm_count;
-        const long long half_count = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
-        const long long h_full = half_count / (2 * sms_), h_rest = half_count % (2 * sms_);
-        const double t_big = (double)((big_tiles + sms_ - 1) / sms_);
-        const double t_half = 1.01 * (double)h_full + (h_rest == 0 ? 0.0 : (h_rest <= sms_ && g_spread ? 0.56 : 1.01));
-        const bool short_tail = g_tail_rule && t_half < t_big;
-        const bool half = ((big_tiles < 2LL * ctx().sm_count || k <= 256 || short_tail) && g_half_enabled) || g_force_half;
-        // Few tiles and a long inner dimension (n <= ~1100): one 64x128 tile per CTA leaves most SMs idle while each warp walks
-        // k/16 steps alone.  Cut k into slices (one CTA each, raw partial products to a workspace) and reduce in a second pass.
-        const long long half_tiles = (long long)ceil_div(m, 64) * ceil_div(n, 128) * batch;
-        if (half && g_splitk_enabled && half_tiles <= ctx().sm_count && k >= 256 && epi.npeers == 0 && !epi.active_until) {
-            int ksplit = (int)((2LL * ctx().sm_count) / half_tiles);
-            if (ksplit > k / g_splitk_min_k) ksplit = k / g_splitk_min_k;
-            if (ksplit > 16) ksplit = 16;
+        int ksplit = 1;
+        const bool half = gemm_tile_plan(m, n, k, batch, ctx().sm_count, epi.npeers == 0 && !epi.active_until, &ksplit) != 0;
+        {
             if (ksplit >= 2) {
                 const long long ldw = m + (m & 1), wz = ldw * n, kstride = wz * batch;
                 double *w = static_cast<double *>(scratch((size_t)kstride * ksplit * sizeof(double)));

@@ -123,3 +123,62 @@ def test_host_operand_entry_points_check_arguments_before_device_work():
         expm_to_host(sq, np.zeros((3, 4), order="F"))
     with pytest.raises(ValueError, match="column-major"):
         expm_to_host(sq, np.zeros((3, 3), dtype=np.float32, order="F"))
+
+
+def test_dgemm_tile_plan_follows_the_wave_model():
+    """fm_dgemm_tile_plan (dgemm.cu: gemm_tile_plan, host arithmetic): 64 x 128 tiles (two CTAs per SM) for few tiles, short inner dimensions
+    and partial last waves of at most one tile per SM; 128 x 128 tiles otherwise; k slices only for single small products.  The shapes are
+    the ones measured in profiles/r02_gemm_wave_shapes.json -- the plan must pick the faster configuration of each."""
+    from ctypes import byref, c_int
+
+    from sci_b200 import _lib
+
+    lib = _lib.load()
+
+    def plan(m, n, k, batch=1, sms=148):
+        rows, ks = c_int(-1), c_int(-1)
+        assert lib.fm_dgemm_tile_plan(m, n, k, batch, sms, byref(rows), byref(ks)) == 0
+        return rows.value, ks.value
+
+    faster_with_128 = [(8192, 8192, 8192), (16384, 16384, 16384), (4096, 4096, 4096), (8192, 2048, 8192), (3072, 3072, 3072), (2560, 2560, 2560),
+                       (6144, 1536, 6144), (4608, 4608, 4608), (16384, 2048, 16384)]
+    faster_with_64 = [(8192, 1024, 8192), (5120, 1024, 5120), (8192, 640, 8192), (2304, 2304, 2304), (4096, 2432, 4096), (4096, 3072, 4096),
+                      (10624, 3072, 4096)]
+    for shape in faster_with_128:
+        assert plan(*shape) == (128, 1), shape
+    for shape in faster_with_64:
+        assert plan(*shape) == (64, 1), shape
+    assert plan(8192, 8192, 128) == (64, 1)        # rank-128 update of the LU: short k
+    assert plan(2048, 2048, 2048) == (64, 1)       # 256 tiles of 128 x 128 cannot fill 2 x 148 slots
+    assert plan(512, 512, 512) == (64, 8)          # 32 tiles: k cut into slices of >= 64, at most 2 x 148 CTAs
+    assert plan(256, 256, 256) == (64, 4)
+    assert plan(1024, 1024, 1024) == (64, 2)
+    assert plan(256, 256, 256, batch=512) == (64, 1)   # a batch fills the machine without slicing k
+    assert plan(512, 512, 128)[1] == 1             # nothing to slice below k = 256
+    assert lib.fm_dgemm_tile_plan(0, 1, 1, 1, 148, byref(c_int()), byref(c_int())) != 0
+
+
+def test_lu_host_plan_chunks():
+    """fm_lu_host_plan: the column chunks of the host-operand LU pipeline (api.cu getrf_host_pipeline): they cover [0, n), every inner bound
+    is a multiple of the 128-column panel, the first two chunks are small (their upload overlaps nothing), no chunk exceeds n / 4
+    rounded down to a panel (the last chunk's rows come down after everything else), and a short remainder rides with the last chunk."""
+    from ctypes import byref, c_int
+
+    from sci_b200 import _lib
+
+    lib = _lib.load()
+    for n in (2048, 6144, 8192, 8200, 9100, 16384, 20000, 32768, 1, 127, 1500):
+        buf = (c_int * 128)()
+        cnt = c_int(-1)
+        assert lib.fm_lu_host_plan(n, buf, 128, byref(cnt)) == 0
+        b = list(buf[: cnt.value + 1])
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:])), (n, b)
+        assert all(x % 128 == 0 for x in b[:-1]), (n, b)
+        widths = [y - x for x, y in zip(b, b[1:])]
+        cap = max(1024, n // 4 // 128 * 128)
+        assert all(w <= cap + 127 for w in widths), (n, widths)
+        if n >= 4096:
+            assert widths[0] == widths[1] == 1024, (n, widths)
+        assert widths[-1] >= min(128, n), (n, widths)
+    assert list((lambda buf, cnt: (lib.fm_lu_host_plan(8192, buf, 128, byref(cnt)), buf[: cnt.value + 1])[1])((c_int * 128)(), c_int())) == [0, 1024, 2048, 4096, 6144, 8192]
+    assert lib.fm_lu_host_plan(8192, (c_int * 2)(), 2, byref(c_int())) != 0  # does not fit
