@@ -40,8 +40,10 @@ N8 = _pade8()
 
 
 class RacketFrontEnd:
-    def __init__(self):
-        self.L = _lib.load()
+    def __init__(self, lib=None):
+        """lib: the object whose attributes are the eight foreign functions (default: libflomat_cuda.so through ctypes -- the product).
+        The CPU tests pass a host BLAS/LAPACK with the same symbols, which turns this class into the reference itself."""
+        self.L = lib if lib is not None else _lib.load()
         self.calls: Counter = Counter()
 
     # ---- allocation and copies (flomat.rkt:437-545) ------------------------------------------------------------------
