@@ -287,6 +287,63 @@ def flomat_plus_bang(a: Flomat, b: Flomat) -> Flomat:
     return b
 
 
+def constant_times_flomat_plus_flomat_bang(alpha: float, a: Flomat, b: Flomat) -> Flomat:
+    """constant*flomat+flomat! (flomat.rkt:805-813): B := alpha*A + B in place (n cblas_daxpy in the reference, one kernel here
+    with daxpy's arithmetic per element)."""
+    _check_same(a, b, "constant*flomat+flomat!")
+    check(_L().fm_axpy2d(a.m, a.n, float(alpha), a.a, a.lda, b.a, b.lda), "fm_axpy2d")
+    return b
+
+
+def constant_times_flomat_plus_flomat(alpha: float, a: Flomat, b: Flomat) -> Flomat:
+    """constant*flomat+flomat (flomat.rkt:815-819): alpha*A + B on a copy of B."""
+    if alpha in (1.0, -1.0):
+        return _axpy_into_copy(float(alpha), a, b, "constant*flomat+flomat")
+    return constant_times_flomat_plus_flomat_bang(alpha, a, copy_flomat(b))
+
+
+def flomat_minus_bang(a: Flomat, b: Flomat) -> Flomat:
+    """flomat-! (flomat.rkt:831-834): A := A - B in place, as B' := -1.0*B + A with the roles the reference gives them."""
+    _check_same(a, b, "flomat-!")
+    return constant_times_flomat_plus_flomat_bang(-1.0, b, a)
+
+
+def flomat_scale_bang(s: float, a: Flomat) -> Flomat:
+    """flomat-scale! (flomat.rkt:1032) -> constant*matrix! (:1020-1030): A := s*A in place (cblas_dscal)."""
+    check(_L().fm_scal2d(a.m, a.n, float(s), a.a, a.lda), "fm_scal2d")
+    return a
+
+
+def plus_bang(a: Flomat, *bs):
+    """`plus!` (flomat.rkt:3148-3156): every matrix B is added into A (`flomat+! B A`), every number through `.+!`; returns A."""
+    if not isinstance(a, Flomat):
+        raise TypeError("plus!: expected a flomat as first argument")  # check-flomat
+    _check_all_same([x for x in (a, *bs) if isinstance(x, Flomat)], "plus!")
+    for b in bs:
+        if isinstance(b, Flomat):
+            flomat_plus_bang(b, a)
+        else:
+            dot_plus(a, b, a)
+    return a
+
+
+def minus_bang(a: Flomat, *bs):
+    """`minus!` (flomat.rkt:3168-3178).  No further argument: A := -A (`.-!`).  A number: A := A - x.  A MATRIX argument B is handled by
+    `(flomat-! B A)`, which is B := B - A (flomat.rkt:831): the reference subtracts into the OPERAND and returns A unchanged -- reproduced
+    here as it stands (a caller that wants A := A - B calls flomat_minus_bang(A, B))."""
+    if not isinstance(a, Flomat):
+        raise TypeError("minus!: expected a flomat as first argument")
+    _check_all_same([x for x in (a, *bs) if isinstance(x, Flomat)], "minus!")
+    if not bs:
+        return dot_minus(a, None, a)
+    for b in bs:
+        if isinstance(b, Flomat):
+            flomat_minus_bang(b, a)
+        else:
+            dot_minus(a, b, a)
+    return a
+
+
 def flomat_scale(s: float, a: Flomat) -> Flomat:
     """flomat-scale (flomat.rkt:1036) = copy + dscal; fused into one s*a_ij pass."""
     return _ewise(OP_MUL, float(s), a, None, "flomat-scale")

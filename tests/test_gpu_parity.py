@@ -479,6 +479,47 @@ np.save(sys.argv[1], fm.expm(fm.matrix(a), fm.EXPM_MIN_PRODUCTS).to_numpy())
     assert np.array_equal(outs["fallback"], outs["pivot"])  # the repeated pass IS the pivoting pipeline
 
 
+def test_in_place_sum_family(fm):
+    """plus! / minus! / flomat+! / flomat-! / flomat-scale! / constant*flomat+flomat(!) (flomat.rkt:3148-3178, :821-834, :1032, :805-819):
+    in place, bit-exact (one rounding per element, alpha*x + y for a general alpha as daxpy does it), views included -- and the
+    reference's `minus!` quirk: a matrix argument is subtracted INTO (`flomat-! B A` is B := B - A), A comes back unchanged."""
+    a, b, c = rnd(61, 37, 21), rnd(62, 37, 21), rnd(63, 37, 21)
+    A, B, C = up(fm, a), up(fm, b), up(fm, c)
+    R = fm.plus_bang(A, B, 2.5, C)
+    assert R is A and np.array_equal(A.to_numpy(), ((a + b) + 2.5) + c) and np.array_equal(B.to_numpy(), b)
+    A = up(fm, a)
+    assert np.array_equal(fm.minus_bang(A).to_numpy(), -a)
+    A = up(fm, a)
+    R = fm.minus_bang(A, 0.75)
+    assert R is A and np.array_equal(A.to_numpy(), a - 0.75)
+    A, B = up(fm, a), up(fm, b)
+    R = fm.minus_bang(A, B)                       # the quirk
+    assert R is A and np.array_equal(A.to_numpy(), a) and np.array_equal(B.to_numpy(), b - a)
+    A, B = up(fm, a), up(fm, b)
+    assert fm.flomat_minus_bang(A, B) is A and np.array_equal(A.to_numpy(), a - b) and np.array_equal(B.to_numpy(), b)
+    A = up(fm, a)
+    assert fm.flomat_scale_bang(-3.0, A) is A and np.array_equal(A.to_numpy(), -3.0 * a)
+    A, B = up(fm, a), up(fm, b)
+    assert fm.constant_times_flomat_plus_flomat_bang(0.3, A, B) is B
+    got, want = B.to_numpy(), 0.3 * a + b
+    assert np.all(np.abs(got - want) <= np.spacing(np.abs(want)))  # a general alpha: fused or unfused multiply-add, one ulp apart at most
+    A, B = up(fm, a), up(fm, b)
+    out = fm.constant_times_flomat_plus_flomat(-1.0, A, B)
+    assert np.array_equal(out.to_numpy(), b - a) and np.array_equal(B.to_numpy(), b)
+    out = fm.constant_times_flomat_plus_flomat(2.0, A, B)
+    assert np.array_equal(out.to_numpy(), 2.0 * a + b) and np.array_equal(B.to_numpy(), b)  # (2x is exact: fused or not, the same)
+    # on a view (lda > m): only the view changes
+    big = rnd(64, 50, 30)
+    Bg = up(fm, big)
+    V = Bg.sub(5, 3, 37, 21)
+    fm.plus_bang(V, up(fm, a))
+    want = big.copy()
+    want[5:42, 3:24] += a
+    assert np.array_equal(Bg.to_numpy(), want)
+    with pytest.raises(ValueError):
+        fm.plus_bang(up(fm, a), up(fm, rnd(65, 3, 3)))
+
+
 # ---------------------------------------------------------------- expm
 @pytest.mark.parametrize("mode", [0, 1])
 def test_expm_closed_forms_and_quirks(fm, mode):
