@@ -20,6 +20,8 @@ from __future__ import annotations
 import ctypes
 from ctypes import byref, c_double, c_int32
 
+import math
+
 import numpy as np
 
 from . import _lib
@@ -598,6 +600,91 @@ def det(a: Flomat) -> float:
     out = c_double()
     check(_L().fm_det(a.m, lu.a, lu.lda, piv.ptr, byref(out)), "fm_det")
     return out.value
+
+
+def flomat_inverse_bang(a: Flomat) -> Flomat:
+    """flomat-inverse! (flomat.rkt:1770-1779): A := A^-1 in place (dgetrf_, dgetri_ with the copy as workspace in the reference; the
+    device path needs no workspace).  `info` is dropped, as the reference drops it."""
+    _check_square(a, "flomat-inverse!")
+    piv = _pivots(a.m)
+    check(_L().fm_getrf(a.m, a.n, a.a, a.lda, piv.ptr, piv.info_ptr), "fm_getrf")
+    check(_L().fm_getri(a.m, a.a, a.lda, piv.ptr, None), "fm_getri")
+    return a
+
+
+def flomat_inverse(a: Flomat) -> Flomat:
+    """flomat-inverse (flomat.rkt:1781): (flomat-inverse! (copy-flomat A))."""
+    return flomat_inverse_bang(copy_flomat(a))
+
+
+def pivots_sign(piv: Pivots) -> int:
+    """pivots-sign (flomat.rkt:1487): (-1)^(number of rows i with ipiv[i] != i)."""
+    return piv.sign()
+
+
+def flomat_determinant_from_plu(lu: Flomat, piv: Pivots) -> float:
+    """flomat-determinant-from-plu (flomat.rkt:1837-1842): pivots-sign times the left-to-right product of the diagonal of L\\U."""
+    _check_square(lu, "flomat-determinant-from-plu")
+    out = c_double()
+    check(_L().fm_det(lu.m, lu.a, lu.lda, piv.ptr, byref(out)), "fm_det")
+    return out.value
+
+
+flomat_determinant = det      # flomat.rkt:1844
+flomat_zeros = zeros          # flomat.rkt:548
+flomat_ones = ones            # flomat.rkt:551
+flomat_eye = eye              # flomat.rkt:2642
+flomat_expt = power           # flomat.rkt:918
+
+
+def flomat_identity(m: int) -> Flomat:
+    """flomat-identity (flomat.rkt:571)."""
+    return eye(m)
+
+
+def flomat_norm(a: Flomat, kind="frob") -> float:
+    """flomat-norm (flomat.rkt:1328; default 'frob) and its four named forms (:1343-1352)."""
+    return norm(a, kind)
+
+
+def flomat_norm1(a: Flomat) -> float:
+    return norm(a, 1)
+
+
+def flomat_norm_inf(a: Flomat) -> float:
+    return norm(a, "inf")
+
+
+def flomat_norm_frob(a: Flomat) -> float:
+    return norm(a, "frob")
+
+
+def flomat_norm_max(a: Flomat) -> float:
+    return norm(a, "max")
+
+
+def flomat_times_bang(a: Flomat, b: Flomat, c: Flomat, alpha: float = 1.0, beta: float = 1.0, transpose_a: bool = False,
+                      transpose_b: bool = False) -> Flomat:
+    """flomat*! (flomat.rkt:898-903): C := alpha*op(A)*op(B) + beta*C into the caller's C."""
+    return flomat_times(a, b, c, alpha, beta, transpose_a, transpose_b)
+
+
+def find_scaling_exponent(a: Flomat) -> float:
+    """find-scaling-exponent (expm.rkt:212-215): s = 1 + ceiling(log(||A||_1) / log 2), as a float (it may be <= 0, -inf for the zero matrix)."""
+    nrm = norm(a, 1)
+    if nrm == 0.0:
+        return -math.inf
+    if math.isnan(nrm) or math.isinf(nrm):
+        return nrm
+    return 1.0 + math.ceil(math.log(nrm) / math.log(2.0))
+
+
+def repeated_squaring(a: Flomat, s) -> Flomat:
+    """repeated-squaring (expm.rkt:209-210): A^(2^s) by s squarings; s <= 0 returns A itself."""
+    while s > 0:
+        a = flomat_times(a, a)
+        s -= 1
+    return a
 
 
 # --------------------------------------------------------------------------------------------------

@@ -520,6 +520,39 @@ def test_in_place_sum_family(fm):
         fm.plus_bang(up(fm, a), up(fm, rnd(65, 3, 3)))
 
 
+def test_named_forms_of_the_lu_norm_and_expm_helpers(fm, ref):
+    """The reference's other names on the path: flomat-inverse(!) (:1770-1782), flomat-determinant(-from-plu) (:1837-1848), pivots-sign
+    (:1487), flomat-norm and its named forms (:1328-1352), flomat-identity / -zeros / -ones (:548-571), flomat*! (:898), and expm's two
+    helpers find-scaling-exponent / repeated-squaring (expm.rkt:209-215) -- the same answers as the front-door functions."""
+    n = 96
+    a, b = rnd(71, n, n), rnd(72, n, n)
+    A = up(fm, a)
+    gate_inverse("flomat-inverse", a, fm.flomat_inverse(A).to_numpy(), ref.inv(a), n)
+    assert np.array_equal(A.to_numpy(), a)
+    W = up(fm, a)
+    assert fm.flomat_inverse_bang(W) is W and np.array_equal(W.to_numpy(), fm.inv(A).to_numpy())
+    LU = up(fm, a)
+    piv = fm.flomat_lu_bang(LU)
+    piv = piv[0] if isinstance(piv, tuple) else piv
+    d = fm.flomat_determinant_from_plu(LU, piv)
+    assert d == fm.det(A) == fm.flomat_determinant(A) and math.isclose(d, ref.det(a), rel_tol=1e-10)
+    assert fm.pivots_sign(piv) in (1, -1) and fm.pivots_sign(piv) == piv.sign()
+    for kind, f in ((1, fm.flomat_norm1), ("inf", fm.flomat_norm_inf), ("frob", fm.flomat_norm_frob), ("max", fm.flomat_norm_max)):
+        assert f(A) == fm.norm(A, kind) == fm.flomat_norm(A, kind)
+    assert fm.flomat_norm(A) == fm.norm(A, "frob")
+    assert np.array_equal(fm.flomat_identity(5).to_numpy(), np.eye(5)) and np.array_equal(fm.flomat_zeros(2, 3).to_numpy(), np.zeros((2, 3)))
+    assert np.array_equal(fm.flomat_ones(3, 2).to_numpy(), np.ones((3, 2)))
+    C = fm.zeros(n, n)
+    assert fm.flomat_times_bang(A, up(fm, b), C) is C
+    gate("flomat*!", C.to_numpy(), ref.times(a, b), n)
+    assert fm.find_scaling_exponent(A) == ref.scaling_exponent(a)
+    assert fm.find_scaling_exponent(fm.zeros(3, 3)) == -math.inf
+    x = rnd(73, n, n, 0.02)
+    X = up(fm, x)
+    gate("repeated-squaring", fm.repeated_squaring(X, 3).to_numpy(), np.linalg.matrix_power(x, 8), n)
+    assert fm.repeated_squaring(X, 0) is X and fm.repeated_squaring(X, -2) is X
+
+
 # ---------------------------------------------------------------- expm
 @pytest.mark.parametrize("mode", [0, 1])
 def test_expm_closed_forms_and_quirks(fm, mode):
